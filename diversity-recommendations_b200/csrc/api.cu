@@ -1,0 +1,312 @@
+// api.cu -- the extern "C" boundary (include/divrec_b200.h): argument checks, workspace carving,
+// kernel sequencing.  No torch types, no allocation, no device synchronisation.
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "../../include/divrec_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace divrec {
+
+static std::atomic<int64_t> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, const char* detail = "") {
+  snprintf(g_err, sizeof(g_err), fmt, detail);
+  return code;
+}
+static int cuda_fail(cudaError_t e, const char* where) {
+  snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
+  return DIVREC_ERR_CUDA;
+}
+
+struct DevInfo { int sm_count = 0; int cc_major = 0; bool ok = false; };
+static DevInfo device_info() {
+  static std::mutex mu;
+  static DevInfo cache[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return DevInfo{};
+  std::lock_guard<std::mutex> lk(mu);
+  if (!cache[dev].ok) {
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return DevInfo{};
+    cache[dev].sm_count = prop.multiProcessorCount;
+    cache[dev].cc_major = prop.major;
+    cache[dev].ok = true;
+  }
+  return cache[dev];
+}
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// workspace layout of score_topk / score_dense
+struct WsLayout {
+  int d_pad, K;
+  bool needA, needB;  // operands have to be rewritten into the workspace
+  size_t offA, offB, offLists, offCounts, offScalars, total;
+};
+static WsLayout ws_layout(int64_t nU, int64_t nI, int d, int dtype) {
+  WsLayout w{};
+  w.d_pad = (int)align_up((size_t)d, 64);
+  if (dtype == DIVREC_F32) { w.K = 3 * w.d_pad; w.needA = w.needB = true; }
+  else { w.K = w.d_pad; w.needA = w.needB = (d != w.d_pad); }
+  size_t off = 0;
+  w.offA = off; if (w.needA) off += align_up((size_t)nU * w.K * 2, 1024);
+  w.offB = off; if (w.needB) off += align_up((size_t)nI * w.K * 2, 1024);
+  const size_t nU_pad = align_up((size_t)nU, 128);
+  w.offLists = off; off += align_up(nU_pad * 2 * LIST_CAP * sizeof(uint2), 1024);
+  w.offCounts = off; off += align_up(nU_pad * 2 * sizeof(int32_t), 1024);
+  w.offScalars = off; off += 1024;  // [0..1] amax bits, [2..3] scale exps
+  w.total = off;
+  return w;
+}
+
+static int check_score_args(const void* U, const void* V, int64_t nU, int64_t nI, int d, int dtype, int mode) {
+  if (!U || !V) return fail(DIVREC_ERR_ARG, "score: null embedding table");
+  if (nU <= 0 || nI <= 0 || d <= 0) return fail(DIVREC_ERR_ARG, "score: nU, nI, d must be positive");
+  if (nI >= (int64_t)1 << 31) return fail(DIVREC_ERR_ARG, "score: nI must be < 2^31");
+  if (dtype == DIVREC_F32) {
+    if (mode != DIVREC_MODE_FP32_PARITY) return fail(DIVREC_ERR_ARG, "score: f32 tables need mode FP32_PARITY");
+    if (d > 128) return fail(DIVREC_ERR_ARG, "score: f32 tables support d <= 128 in this version");
+  } else if (dtype == DIVREC_BF16) {
+    if (mode != DIVREC_MODE_BF16) return fail(DIVREC_ERR_ARG, "score: bf16 tables need mode BF16");
+    if (d > 384) return fail(DIVREC_ERR_ARG, "score: bf16 tables support d <= 384 in this version");
+    if ((reinterpret_cast<uintptr_t>(U) & 15) || (reinterpret_cast<uintptr_t>(V) & 15))
+      return fail(DIVREC_ERR_ARG, "score: bf16 tables must be 16-byte aligned");
+  } else {
+    return fail(DIVREC_ERR_ARG, "score: unknown dtype");
+  }
+  DevInfo di = device_info();
+  if (!di.ok) return fail(DIVREC_ERR_CUDA, "score: cannot query the CUDA device");
+  if (di.cc_major != 10) return fail(DIVREC_ERR_DEVICE, "score: this library only runs on sm_100 (B200)");
+  return DIVREC_OK;
+}
+
+// prepare 16-bit K-major operand planes; returns pointers the TMA descriptors are built on
+static int prepare_operands(const void* U, const void* V, int64_t nU, int64_t nI, int d, int dtype, const WsLayout& w,
+                            uint8_t* ws, cudaStream_t st, const void** A16, const void** B16, int* fmt,
+                            const int32_t** scale_exps) {
+  uint32_t* scal = reinterpret_cast<uint32_t*>(ws + w.offScalars);
+  if (dtype == DIVREC_F32) {
+    cudaError_t e = cudaMemsetAsync(scal, 0, 16, st);
+    if (e != cudaSuccess) return cuda_fail(e, "memset scalars");
+    e = launch_split_f32(reinterpret_cast<const float*>(U), nU, d, w.d_pad, 0, reinterpret_cast<__half*>(ws + w.offA),
+                         scal + 0, reinterpret_cast<int32_t*>(scal + 2), st);
+    if (e != cudaSuccess) return cuda_fail(e, "split user table");
+    e = launch_split_f32(reinterpret_cast<const float*>(V), nI, d, w.d_pad, 1, reinterpret_cast<__half*>(ws + w.offB),
+                         scal + 1, reinterpret_cast<int32_t*>(scal + 3), st);
+    if (e != cudaSuccess) return cuda_fail(e, "split item table");
+    *A16 = ws + w.offA; *B16 = ws + w.offB; *fmt = 0;
+    *scale_exps = reinterpret_cast<const int32_t*>(scal + 2);
+  } else {
+    *A16 = U; *B16 = V; *fmt = 1; *scale_exps = nullptr;
+    if (w.needA) {
+      cudaError_t e = launch_pad_bf16(U, nU, d, w.d_pad, ws + w.offA, st);
+      if (e != cudaSuccess) return cuda_fail(e, "pad user table");
+      e = launch_pad_bf16(V, nI, d, w.d_pad, ws + w.offB, st);
+      if (e != cudaSuccess) return cuda_fail(e, "pad item table");
+      *A16 = ws + w.offA; *B16 = ws + w.offB;
+    }
+  }
+  return DIVREC_OK;
+}
+
+}  // namespace divrec
+
+using namespace divrec;
+
+extern "C" {
+
+int divrec_version(void) { return DIVREC_B200_VERSION; }
+const char* divrec_last_error(void) { return g_err; }
+int64_t divrec_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+size_t divrec_score_topk_workspace(int64_t nU, int64_t nI, int d, int dtype, int k) {
+  (void)k;
+  if (nU <= 0 || nI <= 0 || d <= 0) return 0;
+  return ws_layout(nU, nI, d, dtype).total;
+}
+
+int divrec_score_topk(const void* U, const void* V, int64_t nU, int64_t nI, int d, int dtype, int mode,
+                      const int64_t* seen_rowptr, const int32_t* seen_items, int64_t item_id_offset, int k,
+                      float* out_scores, int64_t* out_items, void* workspace, size_t ws_bytes, void* stream) {
+  int rc = check_score_args(U, V, nU, nI, d, dtype, mode);
+  if (rc != DIVREC_OK) return rc;
+  if (k <= 0 || k > MAX_K) return fail(DIVREC_ERR_ARG, "score_topk: k must be in [1,128]");
+  if (!out_scores || !out_items) return fail(DIVREC_ERR_ARG, "score_topk: null output");
+  if (seen_rowptr == nullptr && seen_items != nullptr)
+    return fail(DIVREC_ERR_ARG, "score_topk: seen_items without seen_rowptr");
+  const WsLayout w = ws_layout(nU, nI, d, dtype);
+  if (!workspace || ws_bytes < w.total) return fail(DIVREC_ERR_WORKSPACE, "score_topk: workspace too small");
+  if (reinterpret_cast<uintptr_t>(workspace) & 1023) return fail(DIVREC_ERR_ARG, "score_topk: workspace must be 1024-byte aligned");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+
+  const void *A16, *B16;
+  int fmt;
+  const int32_t* scale_exps;
+  rc = prepare_operands(U, V, nU, nI, d, dtype, w, ws, st, &A16, &B16, &fmt, &scale_exps);
+  if (rc != DIVREC_OK) return rc;
+
+  FilterParams fp{};
+  fp.nU = nU; fp.nI = (int32_t)nI; fp.kblocks = w.K / 64; fp.fmt = fmt; fp.k = k;
+  fp.seen_rowptr = seen_items ? seen_rowptr : nullptr; fp.seen_items = seen_items; fp.item_id_offset = item_id_offset;
+  fp.lists = reinterpret_cast<uint2*>(ws + w.offLists);
+  fp.list_count = reinterpret_cast<int32_t*>(ws + w.offCounts);
+  fp.dump = nullptr; fp.scale_exps = scale_exps;
+  const char* err = "";
+  cudaError_t e = launch_score_filter(A16, B16, fp, device_info().sm_count, st, &err);
+  if (e != cudaSuccess) return cuda_fail(e, err[0] ? err : "score_filter launch");
+
+  SelectParams sp{};
+  sp.nU = nU; sp.nI = (int32_t)nI; sp.k = k; sp.lists = fp.lists; sp.list_count = fp.list_count;
+  sp.seen_rowptr = fp.seen_rowptr; sp.seen_items = seen_items; sp.item_id_offset = item_id_offset;
+  sp.scale_exps = scale_exps; sp.out_scores = out_scores; sp.out_items = out_items;
+  e = launch_select_topk(sp, st);
+  if (e != cudaSuccess) return cuda_fail(e, "select_topk launch");
+  return DIVREC_OK;
+}
+
+int divrec_score_dense(const void* U, const void* V, int64_t nU, int64_t nI, int d, int dtype, int mode, float* out,
+                       void* workspace, size_t ws_bytes, void* stream) {
+  int rc = check_score_args(U, V, nU, nI, d, dtype, mode);
+  if (rc != DIVREC_OK) return rc;
+  if (!out) return fail(DIVREC_ERR_ARG, "score_dense: null output");
+  const WsLayout w = ws_layout(nU, nI, d, dtype);
+  if (!workspace || ws_bytes < w.total) return fail(DIVREC_ERR_WORKSPACE, "score_dense: workspace too small");
+  if (reinterpret_cast<uintptr_t>(workspace) & 1023) return fail(DIVREC_ERR_ARG, "score_dense: workspace must be 1024-byte aligned");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  const void *A16, *B16;
+  int fmt;
+  const int32_t* scale_exps;
+  rc = prepare_operands(U, V, nU, nI, d, dtype, w, ws, st, &A16, &B16, &fmt, &scale_exps);
+  if (rc != DIVREC_OK) return rc;
+  FilterParams fp{};
+  fp.nU = nU; fp.nI = (int32_t)nI; fp.kblocks = w.K / 64; fp.fmt = fmt; fp.k = 1;
+  fp.lists = reinterpret_cast<uint2*>(ws + w.offLists);
+  fp.list_count = reinterpret_cast<int32_t*>(ws + w.offCounts);
+  fp.dump = out; fp.scale_exps = scale_exps;
+  const char* err = "";
+  cudaError_t e = launch_score_filter(A16, B16, fp, device_info().sm_count, st, &err);
+  if (e != cudaSuccess) return cuda_fail(e, err[0] ? err : "score_filter launch");
+  return DIVREC_OK;
+}
+
+int divrec_topk_merge(const float* gathered_scores, const int64_t* gathered_items, int n_shards, int64_t nU, int k,
+                      float* out_scores, int64_t* out_items, void* stream) {
+  if (!gathered_scores || !gathered_items || !out_scores || !out_items) return fail(DIVREC_ERR_ARG, "topk_merge: null pointer");
+  if (n_shards <= 0 || nU <= 0 || k <= 0) return fail(DIVREC_ERR_ARG, "topk_merge: n_shards, nU, k must be positive");
+  cudaError_t e = launch_topk_merge(gathered_scores, gathered_items, n_shards, nU, k, out_scores, out_items,
+                                    reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "topk_merge launch");
+  return DIVREC_OK;
+}
+
+int divrec_ild_cosine(const void* V, int64_t nI, int d, int dtype, const int64_t* recs, int64_t nU, int k,
+                      int ild_mode, float* inv_norm, float* out_per_user, void* stream) {
+  if (!V || !recs || !inv_norm || !out_per_user) return fail(DIVREC_ERR_ARG, "ild_cosine: null pointer");
+  if (nI <= 0 || nU <= 0 || k < 2) return fail(DIVREC_ERR_ARG, "ild_cosine: need nI > 0, nU > 0, k >= 2");
+  if (d <= 0 || (d & 3) || d > 1024) return fail(DIVREC_ERR_ARG, "ild_cosine: d must be a multiple of 4, <= 1024");
+  if (dtype != DIVREC_F32 && dtype != DIVREC_BF16) return fail(DIVREC_ERR_ARG, "ild_cosine: unknown dtype");
+  if (reinterpret_cast<uintptr_t>(V) & 15) return fail(DIVREC_ERR_ARG, "ild_cosine: V must be 16-byte aligned");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  cudaError_t e = launch_inv_norm(V, nI, d, dtype, inv_norm, st);
+  if (e != cudaSuccess) return cuda_fail(e, "inv_norm launch");
+  if (ild_mode == DIVREC_ILD_SUMVEC) e = launch_ild_sumvec(V, nI, d, dtype, recs, nU, k, inv_norm, out_per_user, st);
+  else if (ild_mode == DIVREC_ILD_PAIRWISE) e = launch_ild_pairwise(V, nI, d, dtype, recs, nU, k, inv_norm, out_per_user, st);
+  else return fail(DIVREC_ERR_ARG, "ild_cosine: unknown ild_mode");
+  if (e != cudaSuccess) return cuda_fail(e, "ild launch");
+  return DIVREC_OK;
+}
+
+int divrec_ild_matrix(const void* D, int d_is_int32, int64_t nI, const int64_t* recs, int64_t nU, int k,
+                      float* out_per_user, void* stream) {
+  if (!D || !recs || !out_per_user) return fail(DIVREC_ERR_ARG, "ild_matrix: null pointer");
+  if (nI <= 0 || nU <= 0 || k < 2) return fail(DIVREC_ERR_ARG, "ild_matrix: need nI > 0, nU > 0, k >= 2");
+  cudaError_t e = launch_ild_matrix(D, d_is_int32, nI, recs, nU, k, out_per_user, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "ild_matrix launch");
+  return DIVREC_OK;
+}
+
+int divrec_coverage_hist(const int64_t* recs, int64_t n, int64_t nI, int32_t* counts, void* stream) {
+  if (!recs || !counts) return fail(DIVREC_ERR_ARG, "coverage_hist: null pointer");
+  if (n < 0 || nI <= 0) return fail(DIVREC_ERR_ARG, "coverage_hist: bad sizes");
+  if (n == 0) return DIVREC_OK;
+  if (reinterpret_cast<uintptr_t>(recs) & 15) return fail(DIVREC_ERR_ARG, "coverage_hist: recs must be 16-byte aligned");
+  cudaError_t e = launch_coverage_hist(recs, n, nI, counts, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "coverage_hist launch");
+  return DIVREC_OK;
+}
+
+int divrec_entropy_from_counts(const int32_t* counts, int64_t nI, float* out2, void* stream) {
+  if (!counts || !out2 || nI <= 0) return fail(DIVREC_ERR_ARG, "entropy_from_counts: bad argument");
+  cudaError_t e = launch_entropy(counts, nI, out2, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "entropy launch");
+  return DIVREC_OK;
+}
+
+static int check_rows(const float* U, const float* V, int d, const char* who) {
+  if (!U || !V) return fail(DIVREC_ERR_ARG, "%s: null embedding table", who);
+  if (d <= 0 || (d & 3) || d > 1024) return fail(DIVREC_ERR_ARG, "%s: d must be a multiple of 4, <= 1024", who);
+  if ((reinterpret_cast<uintptr_t>(U) & 15) || (reinterpret_cast<uintptr_t>(V) & 15))
+    return fail(DIVREC_ERR_ARG, "%s: tables must be 16-byte aligned", who);
+  return DIVREC_OK;
+}
+
+int divrec_bpr_fwd(const float* U, const float* V, const int64_t* u, const int64_t* p, const int64_t* n, int64_t B,
+                   int d, float* pos, float* neg, float* loss_sum, int32_t* auc_sum, void* stream) {
+  int rc = check_rows(U, V, d, "bpr_fwd");
+  if (rc != DIVREC_OK) return rc;
+  if (!u || !p || !n || !pos || !neg) return fail(DIVREC_ERR_ARG, "bpr_fwd: null pointer");
+  if (B <= 0) return fail(DIVREC_ERR_ARG, "bpr_fwd: B must be positive");
+  cudaError_t e = launch_bpr_fwd(U, V, u, p, n, B, d, pos, neg, loss_sum, auc_sum, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "bpr_fwd launch");
+  return DIVREC_OK;
+}
+
+int divrec_bpr_bwd(const float* U, const float* V, const int64_t* u, const int64_t* p, const int64_t* n,
+                   const float* pos, const float* neg, const float* g, float grad_scale, int64_t B, int d, float* gU,
+                   float* gV, void* stream) {
+  int rc = check_rows(U, V, d, "bpr_bwd");
+  if (rc != DIVREC_OK) return rc;
+  if (!u || !p || !n) return fail(DIVREC_ERR_ARG, "bpr_bwd: null index pointer");
+  if (!g && (!pos || !neg)) return fail(DIVREC_ERR_ARG, "bpr_bwd: need g or (pos,neg)");
+  if (B <= 0) return fail(DIVREC_ERR_ARG, "bpr_bwd: B must be positive");
+  if ((gU && (reinterpret_cast<uintptr_t>(gU) & 15)) || (gV && (reinterpret_cast<uintptr_t>(gV) & 15)))
+    return fail(DIVREC_ERR_ARG, "bpr_bwd: gradient tables must be 16-byte aligned");
+  cudaError_t e = launch_bpr_bwd(U, V, u, p, n, pos, neg, g, grad_scale, B, d, gU, gV, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "bpr_bwd launch");
+  return DIVREC_OK;
+}
+
+int divrec_pair_scores(const float* U, const float* V, const int64_t* user_id, const int64_t* item_id, int64_t L,
+                       int d, float* out, void* stream) {
+  int rc = check_rows(U, V, d, "pair_scores");
+  if (rc != DIVREC_OK) return rc;
+  if (!user_id || !item_id || !out) return fail(DIVREC_ERR_ARG, "pair_scores: null pointer");
+  if (L <= 0) return fail(DIVREC_ERR_ARG, "pair_scores: L must be positive");
+  cudaError_t e = launch_pair_scores(U, V, user_id, item_id, L, d, out, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "pair_scores launch");
+  return DIVREC_OK;
+}
+
+int divrec_pair_scores_bwd(const float* U, const float* V, const int64_t* user_id, const int64_t* item_id,
+                           const float* g, int64_t L, int d, float* gU, float* gV, void* stream) {
+  int rc = check_rows(U, V, d, "pair_scores_bwd");
+  if (rc != DIVREC_OK) return rc;
+  if (!user_id || !item_id || !g) return fail(DIVREC_ERR_ARG, "pair_scores_bwd: null pointer");
+  if (L <= 0) return fail(DIVREC_ERR_ARG, "pair_scores_bwd: L must be positive");
+  if ((gU && (reinterpret_cast<uintptr_t>(gU) & 15)) || (gV && (reinterpret_cast<uintptr_t>(gV) & 15)))
+    return fail(DIVREC_ERR_ARG, "pair_scores_bwd: gradient tables must be 16-byte aligned");
+  cudaError_t e = launch_pair_scores_bwd(U, V, user_id, item_id, g, L, d, gU, gV, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "pair_scores_bwd launch");
+  return DIVREC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,180 @@
+// bpr.cu -- BPR (log-sigmoid difference) loss: embedding gather + forward, scatter-add backward.
+//
+// Replaces, for one batch of (user, positive, negative) triples:
+//   forward  : model(u,pos), model(u,neg)  -- divrec/train/utils.py:145-146 through
+//              divrec/models/matrix_factorization.py:26-28; loss -logsigmoid(pos-neg) with mean
+//              reduction -- divrec/losses/log_sigmoid_difference_loss.py:14, base_losses.py:25-26;
+//              AUC (pos >= neg) -- divrec/metrics/auc_score.py:10
+//   backward : loss.backward() -- divrec/train/utils.py:149, i.e. autograd's dense embedding
+//              backward: gU[u] += g (V[p]-V[n]); gV[p] += g U[u]; gV[n] -= g U[u]
+// One warp per triple; rows move as 128-bit vectors; the backward uses vectorised
+// red.global.add.v4.f32 so duplicates of a row accumulate in L2 without a read-back.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace divrec {
+
+namespace {
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
+}
+
+// torch.nn.LogSigmoid: min(x,0) - log1p(exp(-|x|))
+__device__ __forceinline__ float neg_logsigmoid(float x) { return log1pf(expf(-fabsf(x))) - fminf(x, 0.f); }
+
+__global__ void __launch_bounds__(256)
+bpr_fwd_kernel(const float* __restrict__ U, const float* __restrict__ V, const int64_t* __restrict__ u,
+               const int64_t* __restrict__ p, const int64_t* __restrict__ n, int64_t B, int d,
+               float* __restrict__ pos, float* __restrict__ neg, float* __restrict__ loss_sum,
+               int32_t* __restrict__ auc_sum) {
+  __shared__ float red_loss[8];
+  __shared__ int red_auc[8];
+  const uint32_t lane = lane_id();
+  const int warp = threadIdx.x >> 5;
+  const int nvec = d >> 2;
+  float wl = 0.f;
+  int wa = 0;
+  for (int64_t b = (int64_t)blockIdx.x * 8 + warp; b < B; b += (int64_t)gridDim.x * 8) {
+    const float4* ur = reinterpret_cast<const float4*>(U + u[b] * d);
+    const float4* pr = reinterpret_cast<const float4*>(V + p[b] * d);
+    const float4* nr = reinterpret_cast<const float4*>(V + n[b] * d);
+    float sp = 0.f, sn = 0.f;
+    for (int c = lane; c < nvec; c += 32) {
+      const float4 a = __ldg(ur + c), x = __ldg(pr + c), y = __ldg(nr + c);
+      sp = fmaf(a.x, x.x, sp); sp = fmaf(a.y, x.y, sp); sp = fmaf(a.z, x.z, sp); sp = fmaf(a.w, x.w, sp);
+      sn = fmaf(a.x, y.x, sn); sn = fmaf(a.y, y.y, sn); sn = fmaf(a.z, y.z, sn); sn = fmaf(a.w, y.w, sn);
+    }
+    sp = warp_sum(sp);
+    sn = warp_sum(sn);
+    if (lane == 0) {
+      pos[b] = sp;
+      neg[b] = sn;
+      wl += neg_logsigmoid(sp - sn);
+      wa += (sp >= sn) ? 1 : 0;
+    }
+  }
+  if (lane == 0) { red_loss[warp] = wl; red_auc[warp] = wa; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float l = 0.f;
+    int a = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { l += red_loss[i]; a += red_auc[i]; }
+    if (loss_sum) atomicAdd(loss_sum, l);
+    if (auc_sum) atomicAdd(auc_sum, a);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+bpr_bwd_kernel(const float* __restrict__ U, const float* __restrict__ V, const int64_t* __restrict__ u,
+               const int64_t* __restrict__ p, const int64_t* __restrict__ n, const float* __restrict__ pos,
+               const float* __restrict__ neg, const float* __restrict__ g, float grad_scale, int64_t B, int d,
+               float* __restrict__ gU, float* __restrict__ gV) {
+  const uint32_t lane = lane_id();
+  const int warp = threadIdx.x >> 5;
+  const int nvec = d >> 2;
+  for (int64_t b = (int64_t)blockIdx.x * 8 + warp; b < B; b += (int64_t)gridDim.x * 8) {
+    const int64_t iu = u[b], ip = p[b], in = n[b];
+    float c;
+    if (g != nullptr) {
+      c = g[b];
+    } else {
+      const float x = pos[b] - neg[b];
+      c = -grad_scale / (1.0f + expf(x));  // d/dx [-logsigmoid(x)] = -sigmoid(-x)
+    }
+    const float4* ur = reinterpret_cast<const float4*>(U + iu * d);
+    const float4* pr = reinterpret_cast<const float4*>(V + ip * d);
+    const float4* nr = reinterpret_cast<const float4*>(V + in * d);
+    for (int v = lane; v < nvec; v += 32) {
+      const float4 a = __ldg(ur + v), x = __ldg(pr + v), y = __ldg(nr + v);
+      if (gU) red_add_v4(gU + iu * d + v * 4, c * (x.x - y.x), c * (x.y - y.y), c * (x.z - y.z), c * (x.w - y.w));
+      if (gV) {
+        red_add_v4(gV + ip * d + v * 4, c * a.x, c * a.y, c * a.z, c * a.w);
+        red_add_v4(gV + in * d + v * 4, -c * a.x, -c * a.y, -c * a.z, -c * a.w);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+pair_scores_kernel(const float* __restrict__ U, const float* __restrict__ V, const int64_t* __restrict__ uid,
+                   const int64_t* __restrict__ iid, int64_t L, int d, float* __restrict__ out) {
+  const uint32_t lane = lane_id();
+  const int warp = threadIdx.x >> 5;
+  const int nvec = d >> 2;
+  for (int64_t l = (int64_t)blockIdx.x * 8 + warp; l < L; l += (int64_t)gridDim.x * 8) {
+    const float4* ur = reinterpret_cast<const float4*>(U + uid[l] * d);
+    const float4* vr = reinterpret_cast<const float4*>(V + iid[l] * d);
+    float s = 0.f;
+    for (int c = lane; c < nvec; c += 32) {
+      const float4 a = __ldg(ur + c), x = __ldg(vr + c);
+      s = fmaf(a.x, x.x, s); s = fmaf(a.y, x.y, s); s = fmaf(a.z, x.z, s); s = fmaf(a.w, x.w, s);
+    }
+    s = warp_sum(s);
+    if (lane == 0) out[l] = s;
+  }
+}
+
+// backward of pair_scores: gU[uid[l]] += g[l] V[iid[l]];  gV[iid[l]] += g[l] U[uid[l]]
+__global__ void __launch_bounds__(256)
+pair_scores_bwd_kernel(const float* __restrict__ U, const float* __restrict__ V, const int64_t* __restrict__ uid,
+                       const int64_t* __restrict__ iid, const float* __restrict__ g, int64_t L, int d,
+                       float* __restrict__ gU, float* __restrict__ gV) {
+  const uint32_t lane = lane_id();
+  const int warp = threadIdx.x >> 5;
+  const int nvec = d >> 2;
+  for (int64_t l = (int64_t)blockIdx.x * 8 + warp; l < L; l += (int64_t)gridDim.x * 8) {
+    const int64_t iu = uid[l], ii = iid[l];
+    const float c = g[l];
+    const float4* ur = reinterpret_cast<const float4*>(U + iu * d);
+    const float4* vr = reinterpret_cast<const float4*>(V + ii * d);
+    for (int v = lane; v < nvec; v += 32) {
+      const float4 a = __ldg(ur + v), x = __ldg(vr + v);
+      if (gU) red_add_v4(gU + iu * d + v * 4, c * x.x, c * x.y, c * x.z, c * x.w);
+      if (gV) red_add_v4(gV + ii * d + v * 4, c * a.x, c * a.y, c * a.z, c * a.w);
+    }
+  }
+}
+
+inline unsigned warp_grid(int64_t items) {
+  int64_t g = (items + 7) / 8;
+  if (g > 148 * 16) g = 148 * 16;
+  if (g < 1) g = 1;
+  return (unsigned)g;
+}
+
+}  // namespace
+
+cudaError_t launch_bpr_fwd(const float* U, const float* V, const int64_t* u, const int64_t* p, const int64_t* n,
+                           int64_t B, int d, float* pos, float* neg, float* loss_sum, int32_t* auc_sum,
+                           cudaStream_t stream) {
+  bpr_fwd_kernel<<<warp_grid(B), 256, 0, stream>>>(U, V, u, p, n, B, d, pos, neg, loss_sum, auc_sum);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_bpr_bwd(const float* U, const float* V, const int64_t* u, const int64_t* p, const int64_t* n,
+                           const float* pos, const float* neg, const float* g, float grad_scale, int64_t B, int d,
+                           float* gU, float* gV, cudaStream_t stream) {
+  bpr_bwd_kernel<<<warp_grid(B), 256, 0, stream>>>(U, V, u, p, n, pos, neg, g, grad_scale, B, d, gU, gV);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pair_scores(const float* U, const float* V, const int64_t* uid, const int64_t* iid, int64_t L,
+                               int d, float* out, cudaStream_t stream) {
+  pair_scores_kernel<<<warp_grid(L), 256, 0, stream>>>(U, V, uid, iid, L, d, out);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pair_scores_bwd(const float* U, const float* V, const int64_t* uid, const int64_t* iid,
+                                   const float* g, int64_t L, int d, float* gU, float* gV, cudaStream_t stream) {
+  pair_scores_bwd_kernel<<<warp_grid(L), 256, 0, stream>>>(U, V, uid, iid, g, L, d, gU, gV);
+  count_launch();
+  return cudaGetLastError();
+}
+
+}  // namespace divrec

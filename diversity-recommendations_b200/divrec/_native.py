@@ -1,0 +1,314 @@
+"""ctypes binding of libdivrec_b200.so (the C ABI declared in include/divrec_b200.h).
+
+PyTorch is used here for device memory and streams only: every wrapper takes CUDA tensors,
+passes raw device pointers and the current CUDA stream to the library, and returns tensors it
+allocated.  There is no CPU path: a CPU tensor raises TypeError, a missing library raises
+ImportError at first use (the product must fail loudly when the CUDA extension is absent).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional, Tuple
+
+import torch
+
+_PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(_PKG_DIR, "libdivrec_b200.so")
+
+DIVREC_F32, DIVREC_BF16 = 0, 1
+MODE_FP32_PARITY, MODE_BF16 = 0, 1
+ILD_SUMVEC, ILD_PAIRWISE = 0, 1
+MAX_K = 128
+
+_c = ctypes
+_vp, _i64, _i32, _f32, _sz = _c.c_void_p, _c.c_int64, _c.c_int, _c.c_float, _c.c_size_t
+
+# name -> (restype, argtypes); mirrors include/divrec_b200.h one to one
+SIGNATURES = {
+    "divrec_version": (_i32, []),
+    "divrec_last_error": (_c.c_char_p, []),
+    "divrec_launch_count": (_i64, []),
+    "divrec_score_topk_workspace": (_sz, [_i64, _i64, _i32, _i32, _i32]),
+    "divrec_score_topk": (_i32, [_vp, _vp, _i64, _i64, _i32, _i32, _i32, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _sz, _vp]),
+    "divrec_score_dense": (_i32, [_vp, _vp, _i64, _i64, _i32, _i32, _i32, _vp, _vp, _sz, _vp]),
+    "divrec_topk_merge": (_i32, [_vp, _vp, _i32, _i64, _i32, _vp, _vp, _vp]),
+    "divrec_ild_cosine": (_i32, [_vp, _i64, _i32, _i32, _vp, _i64, _i32, _i32, _vp, _vp, _vp]),
+    "divrec_ild_matrix": (_i32, [_vp, _i32, _i64, _vp, _i64, _i32, _vp, _vp]),
+    "divrec_coverage_hist": (_i32, [_vp, _i64, _i64, _vp, _vp]),
+    "divrec_entropy_from_counts": (_i32, [_vp, _i64, _vp, _vp]),
+    "divrec_bpr_fwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "divrec_bpr_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _i64, _i32, _vp, _vp, _vp]),
+    "divrec_pair_scores": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp]),
+    "divrec_pair_scores_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp]),
+}
+
+_lib = None
+
+
+class DivrecNativeError(RuntimeError):
+    pass
+
+
+def load_library(path: Optional[str] = None):
+    """dlopen the shared library and set the prototypes.  Does not touch the GPU."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise ImportError(
+            f"{p} is missing: build it with `python diversity-recommendations_b200/build.py` "
+            "(nvcc, sm_100a). divrec_b200 has no CPU or PyTorch fallback."
+        )
+    lib = ctypes.CDLL(p)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        msg = load_library().divrec_last_error().decode("utf-8", "replace")
+        if rc == -1:
+            raise ValueError(f"{what}: {msg}")
+        raise DivrecNativeError(f"{what} failed (status {rc}): {msg}")
+
+
+def _cuda(t: torch.Tensor, name: str, dtype=None) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor, got {type(t).__name__}")
+    if not t.is_cuda:
+        raise TypeError(f"{name} must be a CUDA tensor: divrec_b200 has no CPU path")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"{name} must have dtype {dtype}, got {t.dtype}")
+    return t.contiguous()
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream(dev) -> int:
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def _table_dtype(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return DIVREC_F32
+    if t.dtype == torch.bfloat16:
+        return DIVREC_BF16
+    raise TypeError(f"embedding tables must be float32 or bfloat16, got {t.dtype}")
+
+
+def launch_count() -> int:
+    return int(load_library().divrec_launch_count())
+
+
+_ws_cache = {}
+
+
+def _workspace(nbytes: int, dev) -> torch.Tensor:
+    """One cached byte buffer per device, grown on demand (1024-byte aligned by the allocator)."""
+    key = (dev.index if dev.index is not None else torch.cuda.current_device())
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = None
+        _ws_cache.pop(key, None)
+        buf = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
+        _ws_cache[key] = buf
+    off = (-buf.data_ptr()) % 1024
+    return buf[off:off + nbytes]
+
+
+def score_topk(U: torch.Tensor, V: torch.Tensor, k: int, seen_rowptr: Optional[torch.Tensor] = None,
+               seen_items: Optional[torch.Tensor] = None, item_id_offset: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(scores [nU,k] fp32, items [nU,k] int64): the k best unmasked items per user, (score desc, id asc)."""
+    lib = load_library()
+    U = _cuda(U, "U")
+    V = _cuda(V, "V", U.dtype)
+    dt = _table_dtype(U)
+    if U.dim() != 2 or V.dim() != 2 or U.shape[1] != V.shape[1]:
+        raise ValueError("U and V must be [n,d] with the same d")
+    nU, d = U.shape
+    nI = V.shape[0]
+    if seen_rowptr is not None:
+        seen_rowptr = _cuda(seen_rowptr, "seen_rowptr", torch.int64)
+        if seen_rowptr.numel() != nU + 1:
+            raise ValueError("seen_rowptr must have nU + 1 entries")
+        if seen_items is not None:
+            seen_items = _cuda(seen_items, "seen_items", torch.int32)
+            if seen_items.numel() == 0:
+                seen_items = None
+    with torch.cuda.device(U.device):
+        ws_bytes = lib.divrec_score_topk_workspace(nU, nI, d, dt, k)
+        ws = _workspace(ws_bytes, U.device)
+        out_s = torch.empty((nU, k), dtype=torch.float32, device=U.device)
+        out_i = torch.empty((nU, k), dtype=torch.int64, device=U.device)
+        mode = MODE_FP32_PARITY if dt == DIVREC_F32 else MODE_BF16
+        rc = lib.divrec_score_topk(_ptr(U), _ptr(V), nU, nI, d, dt, mode, _ptr(seen_rowptr), _ptr(seen_items),
+                                   item_id_offset, k, _ptr(out_s), _ptr(out_i), _ptr(ws), ws_bytes, _stream(U.device))
+    _check(rc, "divrec_score_topk")
+    return out_s, out_i
+
+
+def score_dense(U: torch.Tensor, V: torch.Tensor) -> torch.Tensor:
+    lib = load_library()
+    U = _cuda(U, "U")
+    V = _cuda(V, "V", U.dtype)
+    dt = _table_dtype(U)
+    nU, d = U.shape
+    nI = V.shape[0]
+    with torch.cuda.device(U.device):
+        ws_bytes = lib.divrec_score_topk_workspace(nU, nI, d, dt, 1)
+        ws = _workspace(ws_bytes, U.device)
+        out = torch.empty((nU, nI), dtype=torch.float32, device=U.device)
+        mode = MODE_FP32_PARITY if dt == DIVREC_F32 else MODE_BF16
+        rc = lib.divrec_score_dense(_ptr(U), _ptr(V), nU, nI, d, dt, mode, _ptr(out), _ptr(ws), ws_bytes, _stream(U.device))
+    _check(rc, "divrec_score_dense")
+    return out
+
+
+def topk_merge(gathered_scores: torch.Tensor, gathered_items: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    lib = load_library()
+    gs = _cuda(gathered_scores, "gathered_scores", torch.float32)
+    gi = _cuda(gathered_items, "gathered_items", torch.int64)
+    if gs.dim() != 3 or gs.shape != gi.shape:
+        raise ValueError("gathered tensors must be [n_shards, nU, k]")
+    n_shards, nU, k = gs.shape
+    out_s = torch.empty((nU, k), dtype=torch.float32, device=gs.device)
+    out_i = torch.empty((nU, k), dtype=torch.int64, device=gs.device)
+    with torch.cuda.device(gs.device):
+        rc = lib.divrec_topk_merge(_ptr(gs), _ptr(gi), n_shards, nU, k, _ptr(out_s), _ptr(out_i), _stream(gs.device))
+    _check(rc, "divrec_topk_merge")
+    return out_s, out_i
+
+
+def ild_cosine(V: torch.Tensor, recs: torch.Tensor, mode: int = ILD_SUMVEC) -> torch.Tensor:
+    """per-user sum_{a<b}(1 - cos(V[rec_a], V[rec_b])) / (k (k-1)), fp32 [nU]"""
+    lib = load_library()
+    V = _cuda(V, "V")
+    dt = _table_dtype(V)
+    recs = _cuda(recs, "recommendations", torch.int64)
+    if recs.dim() != 2:
+        raise ValueError("recommendations must be [U,k]")
+    nU, k = recs.shape
+    nI, d = V.shape
+    inv = torch.empty(nI, dtype=torch.float32, device=V.device)
+    out = torch.empty(nU, dtype=torch.float32, device=V.device)
+    with torch.cuda.device(V.device):
+        rc = lib.divrec_ild_cosine(_ptr(V), nI, d, dt, _ptr(recs), nU, k, mode, _ptr(inv), _ptr(out), _stream(V.device))
+    _check(rc, "divrec_ild_cosine")
+    return out
+
+
+def ild_matrix(D: torch.Tensor, recs: torch.Tensor) -> torch.Tensor:
+    lib = load_library()
+    if D.dtype not in (torch.float32, torch.int32):
+        raise TypeError("distance_matrix must be float32 or int32")
+    D = _cuda(D, "distance_matrix")
+    recs = _cuda(recs, "recommendations", torch.int64)
+    nU, k = recs.shape
+    nI = D.shape[0]
+    if D.dim() != 2 or D.shape[1] != nI:
+        raise ValueError("distance_matrix must be square [I,I]")
+    out = torch.empty(nU, dtype=torch.float32, device=D.device)
+    with torch.cuda.device(D.device):
+        rc = lib.divrec_ild_matrix(_ptr(D), int(D.dtype == torch.int32), nI, _ptr(recs), nU, k, _ptr(out), _stream(D.device))
+    _check(rc, "divrec_ild_matrix")
+    return out
+
+
+def coverage_hist(recs: torch.Tensor, n_items: int, counts: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """int32 [n_items] histogram of the recommended ids (accumulates into `counts` if given)."""
+    lib = load_library()
+    recs = _cuda(recs, "recommendations", torch.int64)
+    if counts is None:
+        counts = torch.zeros(n_items, dtype=torch.int32, device=recs.device)
+    else:
+        counts = _cuda(counts, "counts", torch.int32)
+    with torch.cuda.device(recs.device):
+        rc = lib.divrec_coverage_hist(_ptr(recs), recs.numel(), n_items, _ptr(counts), _stream(recs.device))
+    _check(rc, "divrec_coverage_hist")
+    return counts
+
+
+def entropy_from_counts(counts: torch.Tensor) -> torch.Tensor:
+    """fp32 [2]: (-sum p log p, number of non-zero counts)"""
+    lib = load_library()
+    counts = _cuda(counts, "counts", torch.int32)
+    out = torch.empty(2, dtype=torch.float32, device=counts.device)
+    with torch.cuda.device(counts.device):
+        rc = lib.divrec_entropy_from_counts(_ptr(counts), counts.numel(), _ptr(out), _stream(counts.device))
+    _check(rc, "divrec_entropy_from_counts")
+    return out
+
+
+def bpr_fwd(U, V, u, p, n):
+    """returns pos [B], neg [B], loss_sum [1] fp32, auc_sum [1] int32"""
+    lib = load_library()
+    U = _cuda(U, "U", torch.float32)
+    V = _cuda(V, "V", torch.float32)
+    u = _cuda(u, "user_id", torch.int64)
+    p = _cuda(p, "positive_item_id", torch.int64)
+    n = _cuda(n, "negative_item_id", torch.int64)
+    B = u.numel()
+    d = U.shape[1]
+    pos = torch.empty(B, dtype=torch.float32, device=U.device)
+    neg = torch.empty(B, dtype=torch.float32, device=U.device)
+    loss_sum = torch.zeros(1, dtype=torch.float32, device=U.device)
+    auc_sum = torch.zeros(1, dtype=torch.int32, device=U.device)
+    with torch.cuda.device(U.device):
+        rc = lib.divrec_bpr_fwd(_ptr(U), _ptr(V), _ptr(u), _ptr(p), _ptr(n), B, d, _ptr(pos), _ptr(neg),
+                                _ptr(loss_sum), _ptr(auc_sum), _stream(U.device))
+    _check(rc, "divrec_bpr_fwd")
+    return pos, neg, loss_sum, auc_sum
+
+
+def bpr_bwd(U, V, u, p, n, pos, neg, grad_scale: float, gU: torch.Tensor, gV: torch.Tensor, g: Optional[torch.Tensor] = None):
+    lib = load_library()
+    U = _cuda(U, "U", torch.float32)
+    V = _cuda(V, "V", torch.float32)
+    for name, t in (("gU", gU), ("gV", gV)):
+        if t is not None and (not t.is_cuda or not t.is_contiguous() or t.dtype != torch.float32):
+            raise TypeError(f"{name} must be a contiguous float32 CUDA tensor")
+    B = u.numel()
+    d = U.shape[1]
+    with torch.cuda.device(U.device):
+        rc = lib.divrec_bpr_bwd(_ptr(U), _ptr(V), _ptr(u), _ptr(p), _ptr(n), _ptr(pos), _ptr(neg), _ptr(g),
+                                float(grad_scale), B, d, _ptr(gU), _ptr(gV), _stream(U.device))
+    _check(rc, "divrec_bpr_bwd")
+
+
+def pair_scores(U, V, user_id, item_id) -> torch.Tensor:
+    lib = load_library()
+    U = _cuda(U, "U", torch.float32)
+    V = _cuda(V, "V", torch.float32)
+    user_id = _cuda(user_id, "user_id", torch.int64)
+    item_id = _cuda(item_id, "item_id", torch.int64)
+    if user_id.shape != item_id.shape:
+        raise ValueError("user_id and item_id must have the same shape")
+    L = user_id.numel()
+    out = torch.empty(L, dtype=torch.float32, device=U.device)
+    if L == 0:
+        return out
+    with torch.cuda.device(U.device):
+        rc = lib.divrec_pair_scores(_ptr(U), _ptr(V), _ptr(user_id), _ptr(item_id), L, U.shape[1], _ptr(out), _stream(U.device))
+    _check(rc, "divrec_pair_scores")
+    return out
+
+
+def pair_scores_bwd(U, V, user_id, item_id, g, gU: Optional[torch.Tensor], gV: Optional[torch.Tensor]):
+    lib = load_library()
+    g = _cuda(g, "grad_output", torch.float32)
+    L = user_id.numel()
+    if L == 0:
+        return
+    with torch.cuda.device(U.device):
+        rc = lib.divrec_pair_scores_bwd(_ptr(U), _ptr(V), _ptr(user_id), _ptr(item_id), _ptr(g), L, U.shape[1],
+                                        _ptr(gU), _ptr(gV), _stream(U.device))
+    _check(rc, "divrec_pair_scores_bwd")

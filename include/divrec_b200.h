@@ -1,0 +1,162 @@
+/*
+ * divrec_b200.h -- C ABI of libdivrec_b200.so (B200 / sm_100a only).
+ *
+ * The reference (amtsyplov/diversity-recommendations, "divrec") has no FFI: its boundary is
+ * the Python API.  Each entry point below replaces the arithmetic behind one reference call
+ * site; the citation after "replaces:" is the reference file:line (relative to the reference
+ * repository root).  The Python shim in diversity-recommendations_b200/divrec/ binds these
+ * with ctypes (see INTEGRATION.md for the binding a reference maintainer would add).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer into caller-owned memory unless marked "host";
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - functions enqueue work on `stream` and return; they never synchronise the device,
+ *     never allocate outputs and never free anything the caller owns;
+ *   - return value: DIVREC_OK (0) or a negative divrec_status; divrec_last_error() gives the
+ *     message of the last failure on the calling thread;
+ *   - there is no CPU path: a box without an sm_100 device gets DIVREC_ERR_DEVICE.
+ */
+#ifndef DIVREC_B200_H
+#define DIVREC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DIVREC_B200_VERSION 100 /* 0.1.0 */
+
+typedef enum divrec_status {
+  DIVREC_OK = 0,
+  DIVREC_ERR_ARG = -1,       /* bad argument (shape, alignment, unsupported size) */
+  DIVREC_ERR_WORKSPACE = -2, /* workspace too small */
+  DIVREC_ERR_CUDA = -3,      /* a CUDA runtime / driver call failed */
+  DIVREC_ERR_DEVICE = -4     /* current device is not sm_100 */
+} divrec_status;
+
+typedef enum divrec_dtype {
+  DIVREC_F32 = 0, /* fp32 embedding tables (the reference's nn.Embedding default) */
+  DIVREC_BF16 = 1 /* bf16 embedding tables (BASELINE.json config 4) */
+} divrec_dtype;
+
+typedef enum divrec_score_mode {
+  /* fp32 tables are split into three fp16 planes (hi, hi*2^-11, lo*2^11) so that one fp16
+   * tensor-core pass over K = 3*d reproduces the fp32 dot product to ~3*2^-22 relative. */
+  DIVREC_MODE_FP32_PARITY = 0,
+  /* single pass over the table as stored (bf16 tables), fp32 accumulation */
+  DIVREC_MODE_BF16 = 1
+} divrec_score_mode;
+
+typedef enum divrec_ild_mode {
+  DIVREC_ILD_SUMVEC = 0,  /* sum_{a<b} cos = (|sum_a e_a|^2 - sum_a |e_a|^2) / 2 : O(k d)  */
+  DIVREC_ILD_PAIRWISE = 1 /* explicit k(k-1)/2 pairwise cosines in shared memory: O(k^2 d) */
+} divrec_ild_mode;
+
+int divrec_version(void);
+const char* divrec_last_error(void);
+/* number of CUDA kernels this library has launched in this process (bench.py "gpu_launches") */
+int64_t divrec_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------
+ * score + seen-mask + per-user top-k
+ *   replaces: divrec/train/utils.py:53-77 (get_model_recommendations) together with
+ *             divrec/datasets/base_datasets.py:136-171 (RankingDataset.__iter__, the mask)
+ *             and divrec/models/matrix_factorization.py:26-28 (MatrixFactorization.forward)
+ *
+ *   U [nU,d], V [nI,d] row-major, dtype f32 or bf16.  seen_rowptr [nU+1] / seen_items
+ *   (global item ids, ascending inside a row) is the CSR of the `frozen` interactions; pass
+ *   NULL/NULL for "no mask".  item_id_offset is added to local row indices of V to form the
+ *   reported (global) item ids and subtracted from seen_items (item-sharded catalogue).
+ *   Output row u = the k best unmasked items by (score desc, item id asc); rows with fewer
+ *   than k unmasked items are padded with score -inf / item -1.
+ *   Limits of this version: k <= 128; d <= 128 (f32) or d <= 384 (bf16); nI < 2^31.
+ * ------------------------------------------------------------------------------------- */
+size_t divrec_score_topk_workspace(int64_t nU, int64_t nI, int d, int dtype, int k);
+
+int divrec_score_topk(const void* U, const void* V, int64_t nU, int64_t nI, int d, int dtype,
+                      int mode, const int64_t* seen_rowptr, const int32_t* seen_items,
+                      int64_t item_id_offset, int k, float* out_scores /*[nU,k]*/,
+                      int64_t* out_items /*[nU,k]*/, void* workspace, size_t ws_bytes,
+                      void* stream);
+
+/* Debug/validation aid: the raw tensor-core score matrix S = U V^T (no mask, no top-k),
+ * written densely to out [nU,nI] fp32 by the same kernel that feeds the top-k filter. */
+int divrec_score_dense(const void* U, const void* V, int64_t nU, int64_t nI, int d, int dtype,
+                       int mode, float* out /*[nU,nI]*/, void* workspace, size_t ws_bytes,
+                       void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * merge per-shard top-k lists after the all-gather (item-sharded catalogue)
+ *   replaces: the argsort at divrec/train/utils.py:73-75 across catalogue shards
+ *   gathered_* are [n_shards, nU, k]; every shard list is sorted (score desc, id asc) and
+ *   padded with (-inf, -1).  Output: global top-k per user in the same order.
+ * ------------------------------------------------------------------------------------- */
+int divrec_topk_merge(const float* gathered_scores, const int64_t* gathered_items, int n_shards,
+                      int64_t nU, int k, float* out_scores, int64_t* out_items, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * intra-list diversity with cosine distance over the item table
+ *   replaces: divrec/losses/intra_list_diversity_score.py:20-42 fed with
+ *             D = 1 - En En^T  (D is never materialised)
+ *   out_per_user[u] = sum_{a<b} (1 - cos(V[rec_a], V[rec_b])) / (k (k-1)); items < 0 ignored.
+ *   inv_norm [nI] fp32 scratch: 1/|V_i| (filled by this call).
+ * ------------------------------------------------------------------------------------- */
+int divrec_ild_cosine(const void* V, int64_t nI, int d, int dtype, const int64_t* recs /*[nU,k]*/,
+                      int64_t nU, int k, int ild_mode, float* inv_norm /*[nI]*/,
+                      float* out_per_user /*[nU]*/, void* stream);
+
+/* ILD over an explicit distance matrix D [nI,nI] (fp32 or int32), rank order D[rec_a,rec_b], a<b
+ *   replaces: divrec/losses/intra_list_diversity_score.py:36-42 (user_ild) for a caller-supplied D */
+int divrec_ild_matrix(const void* D, int d_is_int32, int64_t nI, const int64_t* recs, int64_t nU,
+                      int k, float* out_per_user, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * coverage counts: histogram of recommended item ids
+ *   replaces: torch.unique(recommendations, return_counts=True) at
+ *             divrec/metrics/entropy_diversity_score.py:22
+ *   counts [nI] int32 must be zeroed by the caller (so shards can accumulate); ids < 0 skipped.
+ *   divrec_entropy_from_counts: out[0] = -sum p log p with p = counts / sum(counts)
+ *   (entropy_diversity_score.py:23-24), out[1] = number of non-zero counts (as float).
+ * ------------------------------------------------------------------------------------- */
+int divrec_coverage_hist(const int64_t* recs, int64_t n, int64_t nI, int32_t* counts, void* stream);
+int divrec_entropy_from_counts(const int32_t* counts, int64_t nI, float* out2, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * BPR loss: gather + forward, and scatter-add backward
+ *   replaces: divrec/models/matrix_factorization.py:26-28 called twice at
+ *             divrec/train/utils.py:145-146, divrec/losses/log_sigmoid_difference_loss.py:14,
+ *             divrec/metrics/auc_score.py:10, and autograd's embedding backward behind
+ *             divrec/train/utils.py:149.
+ *   fwd: pos[b] = <U[u_b],V[p_b]>, neg[b] = <U[u_b],V[n_b]>, loss_sum += -logsigmoid(pos-neg),
+ *        auc_sum += (pos >= neg).  loss_sum [1] fp32 and auc_sum [1] int32 are caller-zeroed.
+ *   bwd: with g_b = dL/dx_b supplied per triple (x = pos-neg):
+ *        gU[u] += g (V[p]-V[n]);  gV[p] += g U[u];  gV[n] -= g U[u]   (duplicates accumulate)
+ *        If g == NULL it is recomputed as -sigmoid(-(pos-neg)) * grad_scale.
+ *   d must be a multiple of 4 and <= 1024; fp32 tables.
+ * ------------------------------------------------------------------------------------- */
+int divrec_bpr_fwd(const float* U, const float* V, const int64_t* u, const int64_t* p,
+                   const int64_t* n, int64_t B, int d, float* pos /*[B]*/, float* neg /*[B]*/,
+                   float* loss_sum, int32_t* auc_sum, void* stream);
+
+int divrec_bpr_bwd(const float* U, const float* V, const int64_t* u, const int64_t* p,
+                   const int64_t* n, const float* pos, const float* neg, const float* g,
+                   float grad_scale, int64_t B, int d, float* gU, float* gV, void* stream);
+
+/* paired scoring  out[l] = <U[user_id[l]], V[item_id[l]]>
+ *   replaces: divrec/models/matrix_factorization.py:19-28 (MatrixFactorization.forward) */
+int divrec_pair_scores(const float* U, const float* V, const int64_t* user_id,
+                       const int64_t* item_id, int64_t L, int d, float* out, void* stream);
+
+/* backward of divrec_pair_scores: gU[user_id[l]] += g[l] V[item_id[l]]; gV[item_id[l]] += g[l] U[user_id[l]]
+ *   replaces: autograd's embedding_dense_backward behind loss_value.backward() at
+ *             divrec/train/utils.py:149 for a single model(...) call; gU / gV may be NULL. */
+int divrec_pair_scores_bwd(const float* U, const float* V, const int64_t* user_id,
+                           const int64_t* item_id, const float* g, int64_t L, int d, float* gU,
+                           float* gV, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIVREC_B200_H */
