@@ -25,6 +25,24 @@ static int cuda_fail(cudaError_t e, const char* where) {
   return DIVREC_ERR_CUDA;
 }
 
+// ---- optional per-kernel timing (bench.py roofline): CUDA events on the launching stream ----
+enum ProfSlot { PROF_PREP = 0, PROF_FILTER = 1, PROF_SELECT = 2, PROF_ILD = 3, PROF_COVERAGE = 4, PROF_SLOTS = 5 };
+static std::atomic<int> g_prof_on{0};
+static cudaEvent_t g_prof_ev[PROF_SLOTS][2];
+static bool g_prof_made = false;
+static bool g_prof_set[PROF_SLOTS];
+static std::mutex g_prof_mu;
+static void prof_mark(int slot, int which, cudaStream_t st) {
+  if (!g_prof_on.load(std::memory_order_relaxed)) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (!g_prof_made) {
+    for (int i = 0; i < PROF_SLOTS; ++i) { cudaEventCreate(&g_prof_ev[i][0]); cudaEventCreate(&g_prof_ev[i][1]); g_prof_set[i] = false; }
+    g_prof_made = true;
+  }
+  cudaEventRecord(g_prof_ev[slot][which], st);
+  if (which == 1) g_prof_set[slot] = true;
+}
+
 struct DevInfo { int sm_count = 0; int cc_major = 0; bool ok = false; };
 static DevInfo device_info() {
   static std::mutex mu;
@@ -126,6 +144,20 @@ int divrec_version(void) { return DIVREC_B200_VERSION; }
 const char* divrec_last_error(void) { return g_err; }
 int64_t divrec_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
+void divrec_set_profiling(int on) { g_prof_on.store(on ? 1 : 0); }
+
+int divrec_profile_read(float* ms_out, int n) {
+  if (!ms_out || n <= 0) return fail(DIVREC_ERR_ARG, "profile_read: bad argument");
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (int i = 0; i < n; ++i) {
+    ms_out[i] = -1.0f;
+    if (i < PROF_SLOTS && g_prof_made && g_prof_set[i]) {
+      if (cudaEventSynchronize(g_prof_ev[i][1]) == cudaSuccess) cudaEventElapsedTime(&ms_out[i], g_prof_ev[i][0], g_prof_ev[i][1]);
+    }
+  }
+  return DIVREC_OK;
+}
+
 size_t divrec_score_topk_workspace(int64_t nU, int64_t nI, int d, int dtype, int k) {
   (void)k;
   if (nU <= 0 || nI <= 0 || d <= 0) return 0;
@@ -150,8 +182,10 @@ int divrec_score_topk(const void* U, const void* V, int64_t nU, int64_t nI, int 
   const void *A16, *B16;
   int fmt;
   const int32_t* scale_exps;
+  prof_mark(PROF_PREP, 0, st);
   rc = prepare_operands(U, V, nU, nI, d, dtype, w, ws, st, &A16, &B16, &fmt, &scale_exps);
   if (rc != DIVREC_OK) return rc;
+  prof_mark(PROF_PREP, 1, st);
 
   FilterParams fp{};
   fp.nU = nU; fp.nI = (int32_t)nI; fp.kblocks = w.K / 64; fp.fmt = fmt; fp.k = k;
@@ -160,15 +194,19 @@ int divrec_score_topk(const void* U, const void* V, int64_t nU, int64_t nI, int 
   fp.list_count = reinterpret_cast<int32_t*>(ws + w.offCounts);
   fp.dump = nullptr; fp.scale_exps = scale_exps;
   const char* err = "";
+  prof_mark(PROF_FILTER, 0, st);
   cudaError_t e = launch_score_filter(A16, B16, fp, device_info().sm_count, st, &err);
   if (e != cudaSuccess) return cuda_fail(e, err[0] ? err : "score_filter launch");
+  prof_mark(PROF_FILTER, 1, st);
 
   SelectParams sp{};
   sp.nU = nU; sp.nI = (int32_t)nI; sp.k = k; sp.lists = fp.lists; sp.list_count = fp.list_count;
   sp.seen_rowptr = fp.seen_rowptr; sp.seen_items = seen_items; sp.item_id_offset = item_id_offset;
   sp.scale_exps = scale_exps; sp.out_scores = out_scores; sp.out_items = out_items;
+  prof_mark(PROF_SELECT, 0, st);
   e = launch_select_topk(sp, st);
   if (e != cudaSuccess) return cuda_fail(e, "select_topk launch");
+  prof_mark(PROF_SELECT, 1, st);
   return DIVREC_OK;
 }
 
@@ -216,12 +254,14 @@ int divrec_ild_cosine(const void* V, int64_t nI, int d, int dtype, const int64_t
   if (dtype != DIVREC_F32 && dtype != DIVREC_BF16) return fail(DIVREC_ERR_ARG, "ild_cosine: unknown dtype");
   if (reinterpret_cast<uintptr_t>(V) & 15) return fail(DIVREC_ERR_ARG, "ild_cosine: V must be 16-byte aligned");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  prof_mark(PROF_ILD, 0, st);
   cudaError_t e = launch_inv_norm(V, nI, d, dtype, inv_norm, st);
   if (e != cudaSuccess) return cuda_fail(e, "inv_norm launch");
   if (ild_mode == DIVREC_ILD_SUMVEC) e = launch_ild_sumvec(V, nI, d, dtype, recs, nU, k, inv_norm, out_per_user, st);
   else if (ild_mode == DIVREC_ILD_PAIRWISE) e = launch_ild_pairwise(V, nI, d, dtype, recs, nU, k, inv_norm, out_per_user, st);
   else return fail(DIVREC_ERR_ARG, "ild_cosine: unknown ild_mode");
   if (e != cudaSuccess) return cuda_fail(e, "ild launch");
+  prof_mark(PROF_ILD, 1, st);
   return DIVREC_OK;
 }
 
@@ -239,8 +279,10 @@ int divrec_coverage_hist(const int64_t* recs, int64_t n, int64_t nI, int32_t* co
   if (n < 0 || nI <= 0) return fail(DIVREC_ERR_ARG, "coverage_hist: bad sizes");
   if (n == 0) return DIVREC_OK;
   if (reinterpret_cast<uintptr_t>(recs) & 15) return fail(DIVREC_ERR_ARG, "coverage_hist: recs must be 16-byte aligned");
+  prof_mark(PROF_COVERAGE, 0, reinterpret_cast<cudaStream_t>(stream));
   cudaError_t e = launch_coverage_hist(recs, n, nI, counts, reinterpret_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "coverage_hist launch");
+  prof_mark(PROF_COVERAGE, 1, reinterpret_cast<cudaStream_t>(stream));
   return DIVREC_OK;
 }
 
@@ -306,6 +348,52 @@ int divrec_pair_scores_bwd(const float* U, const float* V, const int64_t* user_i
     return fail(DIVREC_ERR_ARG, "pair_scores_bwd: gradient tables must be 16-byte aligned");
   cudaError_t e = launch_pair_scores_bwd(U, V, user_id, item_id, g, L, d, gU, gV, reinterpret_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "pair_scores_bwd launch");
+  return DIVREC_OK;
+}
+
+int divrec_ild_labels(const int64_t* labels, int64_t nI, const int64_t* recs, int64_t nU, int k, float* out_per_user,
+                      void* stream) {
+  if (!labels || !recs || !out_per_user) return fail(DIVREC_ERR_ARG, "ild_labels: null pointer");
+  if (nI <= 0 || nU <= 0 || k < 2) return fail(DIVREC_ERR_ARG, "ild_labels: need nI > 0, nU > 0, k >= 2");
+  cudaError_t e = launch_ild_labels(labels, nI, recs, nU, k, out_per_user, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "ild_labels launch");
+  return DIVREC_OK;
+}
+
+int divrec_coverage_hist_ranks(const int64_t* recs, int64_t nU, int k, int64_t nI, int32_t* counts, uint64_t* rank_sums,
+                               void* stream) {
+  if (!recs || !counts || !rank_sums) return fail(DIVREC_ERR_ARG, "coverage_hist_ranks: null pointer");
+  if (nU < 0 || k <= 0 || nI <= 0) return fail(DIVREC_ERR_ARG, "coverage_hist_ranks: bad sizes");
+  if (nU == 0) return DIVREC_OK;
+  cudaError_t e = launch_coverage_hist_ranks(recs, nU, k, nI, counts, reinterpret_cast<unsigned long long*>(rank_sums),
+                                             reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "coverage_hist_ranks launch");
+  return DIVREC_OK;
+}
+
+int divrec_relevance_metrics(const int64_t* recs, int64_t nU, int k, const int64_t* pos_rowptr, const int32_t* pos_items,
+                             const int32_t* raw_counts, float* out, void* stream) {
+  if (!recs || !pos_rowptr || !raw_counts || !out) return fail(DIVREC_ERR_ARG, "relevance_metrics: null pointer");
+  if (nU <= 0 || k <= 0) return fail(DIVREC_ERR_ARG, "relevance_metrics: nU, k must be positive");
+  cudaError_t e = launch_relevance(recs, nU, k, pos_rowptr, pos_items, raw_counts, out, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "relevance_metrics launch");
+  return DIVREC_OK;
+}
+
+int divrec_bpr_loss_fwd(const float* pos, const float* neg, int64_t B, float* loss_values, int32_t* hits, void* stream) {
+  if (!pos || !neg) return fail(DIVREC_ERR_ARG, "bpr_loss_fwd: null pointer");
+  if (B <= 0) return fail(DIVREC_ERR_ARG, "bpr_loss_fwd: B must be positive");
+  cudaError_t e = launch_bpr_loss_fwd(pos, neg, B, loss_values, hits, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "bpr_loss_fwd launch");
+  return DIVREC_OK;
+}
+
+int divrec_bpr_loss_bwd(const float* pos, const float* neg, const float* g, int64_t B, float* gpos, float* gneg,
+                        void* stream) {
+  if (!pos || !neg || !g || !gpos || !gneg) return fail(DIVREC_ERR_ARG, "bpr_loss_bwd: null pointer");
+  if (B <= 0) return fail(DIVREC_ERR_ARG, "bpr_loss_bwd: B must be positive");
+  cudaError_t e = launch_bpr_loss_bwd(pos, neg, g, B, gpos, gneg, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "bpr_loss_bwd launch");
   return DIVREC_OK;
 }
 

@@ -138,6 +138,28 @@ pair_scores_bwd_kernel(const float* __restrict__ U, const float* __restrict__ V,
   }
 }
 
+// elementwise loss on precomputed scores: lv[b] = -logsigmoid(pos[b] - neg[b]) (log_sigmoid_difference_loss.py:14),
+// hit[b] = (pos[b] >= neg[b]) (auc_score.py:10); either output may be null
+__global__ void __launch_bounds__(256)
+bpr_loss_fwd_kernel(const float* __restrict__ pos, const float* __restrict__ neg, int64_t B, float* __restrict__ lv,
+                    int32_t* __restrict__ hit) {
+  for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (int64_t)gridDim.x * blockDim.x) {
+    const float p = pos[b], n = neg[b];
+    if (lv) lv[b] = neg_logsigmoid(p - n);
+    if (hit) hit[b] = (p >= n) ? 1 : 0;
+  }
+}
+// gpos[b] = -sigmoid(-(pos-neg)) g[b];  gneg[b] = -gpos[b]
+__global__ void __launch_bounds__(256)
+bpr_loss_bwd_kernel(const float* __restrict__ pos, const float* __restrict__ neg, const float* __restrict__ g, int64_t B,
+                    float* __restrict__ gpos, float* __restrict__ gneg) {
+  for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (int64_t)gridDim.x * blockDim.x) {
+    const float c = -g[b] / (1.0f + expf(pos[b] - neg[b]));
+    gpos[b] = c;
+    gneg[b] = -c;
+  }
+}
+
 inline unsigned warp_grid(int64_t items) {
   int64_t g = (items + 7) / 8;
   if (g > 148 * 16) g = 148 * 16;
@@ -173,6 +195,23 @@ cudaError_t launch_pair_scores(const float* U, const float* V, const int64_t* ui
 cudaError_t launch_pair_scores_bwd(const float* U, const float* V, const int64_t* uid, const int64_t* iid,
                                    const float* g, int64_t L, int d, float* gU, float* gV, cudaStream_t stream) {
   pair_scores_bwd_kernel<<<warp_grid(L), 256, 0, stream>>>(U, V, uid, iid, g, L, d, gU, gV);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_bpr_loss_fwd(const float* pos, const float* neg, int64_t B, float* lv, int32_t* hit, cudaStream_t stream) {
+  int64_t g = (B + 255) / 256;
+  if (g > 148 * 8) g = 148 * 8;
+  bpr_loss_fwd_kernel<<<(unsigned)g, 256, 0, stream>>>(pos, neg, B, lv, hit);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_bpr_loss_bwd(const float* pos, const float* neg, const float* g, int64_t B, float* gpos, float* gneg,
+                                cudaStream_t stream) {
+  int64_t gr = (B + 255) / 256;
+  if (gr > 148 * 8) gr = 148 * 8;
+  bpr_loss_bwd_kernel<<<(unsigned)gr, 256, 0, stream>>>(pos, neg, g, B, gpos, gneg);
   count_launch();
   return cudaGetLastError();
 }

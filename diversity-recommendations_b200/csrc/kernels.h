@@ -80,4 +80,14 @@ cudaError_t launch_pair_scores(const float* U, const float* V, const int64_t* ui
 cudaError_t launch_pair_scores_bwd(const float* U, const float* V, const int64_t* uid, const int64_t* iid,
                                    const float* g, int64_t L, int d, float* gU, float* gV, cudaStream_t stream);
 
+cudaError_t launch_ild_labels(const int64_t* labels, int64_t nI, const int64_t* recs, int64_t nU, int k, float* out,
+                              cudaStream_t stream);
+cudaError_t launch_coverage_hist_ranks(const int64_t* recs, int64_t nU, int k, int64_t nI, int32_t* counts,
+                                       unsigned long long* rank_sums, cudaStream_t stream);
+cudaError_t launch_relevance(const int64_t* recs, int64_t nU, int k, const int64_t* rowptr, const int32_t* items,
+                             const int32_t* raw_counts, float* out, cudaStream_t stream);
+cudaError_t launch_bpr_loss_fwd(const float* pos, const float* neg, int64_t B, float* lv, int32_t* hit, cudaStream_t stream);
+cudaError_t launch_bpr_loss_bwd(const float* pos, const float* neg, const float* g, int64_t B, float* gpos, float* gneg,
+                                cudaStream_t stream);
+
 }  // namespace divrec

@@ -213,6 +213,97 @@ coverage_hist_kernel(const int64_t* __restrict__ recs, int64_t n, int64_t nI, in
   }
 }
 
+// label distance D[i,j] = (label_i == label_j) (IntraListBinaryUnfairnessScore,
+// divrec/losses/intra_list_diversity_score.py:60-63) without the [I,I] matrix: one warp per user,
+// the k labels sit in registers / shared memory and every pair is compared once.
+__global__ void __launch_bounds__(256)
+ild_labels_kernel(const int64_t* __restrict__ labels, int64_t nI, const int64_t* __restrict__ recs, int64_t nU, int k,
+                  float* __restrict__ out) {
+  extern __shared__ long long lab_s[];  // [8 warps][k]
+  const int warp = threadIdx.x >> 5;
+  const uint32_t lane = lane_id();
+  const int64_t u = (int64_t)blockIdx.x * 8 + warp;
+  if (u >= nU) return;
+  long long* lab = lab_s + (size_t)warp * k;
+  for (int a = lane; a < k; a += 32) {
+    const int64_t id = recs[u * k + a];
+    // invalid ids get distinct sentinels so they never compare equal
+    lab[a] = (id >= 0 && id < nI) ? (long long)__ldg(labels + id) : (long long)(INT64_MIN + a);
+  }
+  __syncwarp();
+  int same = 0;
+  for (int a = 0; a < k - 1; ++a) {
+    const long long la = lab[a];
+    if (la <= (long long)(INT64_MIN + k)) continue;
+    for (int b = a + 1 + lane; b < k; b += 32) same += (lab[b] == la) ? 1 : 0;
+  }
+  same = __reduce_add_sync(0xffffffffu, same);
+  if (lane == 0) out[u] = (float)same / ((float)k * (float)(k - 1));
+}
+
+// coverage histogram that also accumulates the sum of list positions per item (avg_rank,
+// divrec/metrics/popularity_rank_correlation_for_items.py:27-41)
+__global__ void __launch_bounds__(256)
+coverage_hist_ranks_kernel(const int64_t* __restrict__ recs, int64_t nU, int k, int64_t nI, int32_t* __restrict__ counts,
+                           unsigned long long* __restrict__ rank_sums) {
+  const int64_t n = nU * k;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t v = __ldg(recs + i);
+    if (v >= 0 && v < nI) {
+      atomicAdd(counts + v, 1);
+      atomicAdd(rank_sums + v, (unsigned long long)(i % k));
+    }
+  }
+}
+
+// relevance metrics @k: one warp per user; membership of each recommended id in the user's positives
+// (CSR row, ascending) by binary search.  out [4][nU]: precision, recall, "average precision", ndcg
+// (divrec/metrics/precision_at_k.py:16-22, recall_at_k.py:16-22, average_precision_at_k.py:18-24,
+//  normalized_discounted_cumulative_gain.py:16-23)
+__global__ void __launch_bounds__(256)
+relevance_kernel(const int64_t* __restrict__ recs, int64_t nU, int k, const int64_t* __restrict__ rowptr,
+                 const int32_t* __restrict__ items, const int32_t* __restrict__ raw_counts, float* __restrict__ out) {
+  const int warp = threadIdx.x >> 5;
+  const uint32_t lane = lane_id();
+  const int64_t u = (int64_t)blockIdx.x * 8 + warp;
+  if (u >= nU) return;
+  const int64_t s0 = rowptr[u], s1 = rowptr[u + 1];
+  float idcg = 0.f;
+  for (int r = lane; r < k; r += 32) idcg += 1.0f / log2f((float)(r + 2));
+  idcg = warp_sum(idcg);
+  int hits_before = 0;  // relevant items in earlier 32-chunks
+  float ap = 0.f, dcg = 0.f;
+  for (int base = 0; base < k; base += 32) {
+    const int r = base + lane;
+    bool rel = false;
+    if (r < k) {
+      const int64_t id = recs[u * k + r];
+      int64_t lo = s0, hi = s1;
+      while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if ((int64_t)items[mid] < id) lo = mid + 1; else hi = mid;
+      }
+      rel = lo < s1 && (int64_t)items[lo] == id;
+    }
+    const uint32_t m = __ballot_sync(0xffffffffu, rel);
+    if (r < k) {
+      const int cum = hits_before + __popc(m & (lanemask_lt() | (1u << lane)));  // inclusive cumsum of relevance
+      ap += (float)cum / (float)(r + 1);
+      if (rel) dcg += 1.0f / log2f((float)(r + 2));
+    }
+    hits_before += __popc(m);
+  }
+  ap = warp_sum(ap);
+  dcg = warp_sum(dcg);
+  if (lane == 0) {
+    const float hits = (float)hits_before;
+    out[0 * nU + u] = hits / (float)k;
+    out[1 * nU + u] = hits / (float)raw_counts[u];
+    out[2 * nU + u] = ap / (float)k;
+    out[3 * nU + u] = dcg / idcg;
+  }
+}
+
 // single CTA: out[0] = -sum p log p, p = c / sum(c) (fp32 p as the reference, fp64 accumulation); out[1] = #non-zero
 __global__ void __launch_bounds__(1024)
 entropy_kernel(const int32_t* __restrict__ counts, int64_t nI, float* __restrict__ out2) {
@@ -300,6 +391,36 @@ cudaError_t launch_coverage_hist(const int64_t* recs, int64_t n, int64_t nI, int
 
 cudaError_t launch_entropy(const int32_t* counts, int64_t nI, float* out2, cudaStream_t stream) {
   entropy_kernel<<<1, 1024, 0, stream>>>(counts, nI, out2);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_ild_labels(const int64_t* labels, int64_t nI, const int64_t* recs, int64_t nU, int k, float* out,
+                              cudaStream_t stream) {
+  const size_t smem = (size_t)8 * k * sizeof(long long);
+  if (smem > 200 * 1024) return cudaErrorInvalidValue;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(ild_labels_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  ild_labels_kernel<<<(unsigned)((nU + 7) / 8), 256, smem, stream>>>(labels, nI, recs, nU, k, out);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_coverage_hist_ranks(const int64_t* recs, int64_t nU, int k, int64_t nI, int32_t* counts,
+                                       unsigned long long* rank_sums, cudaStream_t stream) {
+  int64_t g = (nU * k + 255) / 256;
+  if (g > 148 * 8) g = 148 * 8;
+  if (g < 1) g = 1;
+  coverage_hist_ranks_kernel<<<(unsigned)g, 256, 0, stream>>>(recs, nU, k, nI, counts, rank_sums);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_relevance(const int64_t* recs, int64_t nU, int k, const int64_t* rowptr, const int32_t* items,
+                             const int32_t* raw_counts, float* out, cudaStream_t stream) {
+  relevance_kernel<<<(unsigned)((nU + 7) / 8), 256, 0, stream>>>(recs, nU, k, rowptr, items, raw_counts, out);
   count_launch();
   return cudaGetLastError();
 }

@@ -29,6 +29,8 @@ SIGNATURES = {
     "divrec_version": (_i32, []),
     "divrec_last_error": (_c.c_char_p, []),
     "divrec_launch_count": (_i64, []),
+    "divrec_set_profiling": (None, [_i32]),
+    "divrec_profile_read": (_i32, [_c.POINTER(_c.c_float), _i32]),
     "divrec_score_topk_workspace": (_sz, [_i64, _i64, _i32, _i32, _i32]),
     "divrec_score_topk": (_i32, [_vp, _vp, _i64, _i64, _i32, _i32, _i32, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _sz, _vp]),
     "divrec_score_dense": (_i32, [_vp, _vp, _i64, _i64, _i32, _i32, _i32, _vp, _vp, _sz, _vp]),
@@ -41,6 +43,11 @@ SIGNATURES = {
     "divrec_bpr_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _i64, _i32, _vp, _vp, _vp]),
     "divrec_pair_scores": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp]),
     "divrec_pair_scores_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp]),
+    "divrec_ild_labels": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _vp]),
+    "divrec_coverage_hist_ranks": (_i32, [_vp, _i64, _i32, _i64, _vp, _vp, _vp]),
+    "divrec_relevance_metrics": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "divrec_bpr_loss_fwd": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp]),
+    "divrec_bpr_loss_bwd": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _vp]),
 }
 
 _lib = None
@@ -107,6 +114,20 @@ def _table_dtype(t: torch.Tensor) -> int:
 
 def launch_count() -> int:
     return int(load_library().divrec_launch_count())
+
+
+def set_profiling(on: bool) -> None:
+    load_library().divrec_set_profiling(1 if on else 0)
+
+
+PROFILE_SLOTS = ("prep_ms", "score_filter_ms", "select_ms", "ild_ms", "coverage_ms")
+
+
+def profile_read() -> dict:
+    """Durations (ms) of the library's last phases, from CUDA events on the launching stream."""
+    buf = (_c.c_float * len(PROFILE_SLOTS))()
+    _check(load_library().divrec_profile_read(buf, len(PROFILE_SLOTS)), "divrec_profile_read")
+    return {name: float(buf[i]) for i, name in enumerate(PROFILE_SLOTS)}
 
 
 _ws_cache = {}
@@ -312,3 +333,85 @@ def pair_scores_bwd(U, V, user_id, item_id, g, gU: Optional[torch.Tensor], gV: O
         rc = lib.divrec_pair_scores_bwd(_ptr(U), _ptr(V), _ptr(user_id), _ptr(item_id), _ptr(g), L, U.shape[1],
                                         _ptr(gU), _ptr(gV), _stream(U.device))
     _check(rc, "divrec_pair_scores_bwd")
+
+
+def ild_labels(labels: torch.Tensor, recs: torch.Tensor) -> torch.Tensor:
+    """per-user sum_{a<b} (label[rec_a] == label[rec_b]) / (k (k-1)), fp32 [nU]"""
+    lib = load_library()
+    recs = _cuda(recs, "recommendations", torch.int64)
+    labels = _cuda(labels.to(torch.int64) if labels.dtype != torch.int64 else labels, "item_labels", torch.int64)
+    nU, k = recs.shape
+    out = torch.empty(nU, dtype=torch.float32, device=recs.device)
+    with torch.cuda.device(recs.device):
+        rc = lib.divrec_ild_labels(_ptr(labels), labels.numel(), _ptr(recs), nU, k, _ptr(out), _stream(recs.device))
+    _check(rc, "divrec_ild_labels")
+    return out
+
+
+def coverage_hist_ranks(recs: torch.Tensor, n_items: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(counts int32 [n_items], rank_sums int64 [n_items])"""
+    lib = load_library()
+    recs = _cuda(recs, "recommendations", torch.int64)
+    nU, k = recs.shape
+    counts = torch.zeros(n_items, dtype=torch.int32, device=recs.device)
+    sums = torch.zeros(n_items, dtype=torch.int64, device=recs.device)
+    with torch.cuda.device(recs.device):
+        rc = lib.divrec_coverage_hist_ranks(_ptr(recs), nU, k, n_items, _ptr(counts), _ptr(sums), _stream(recs.device))
+    _check(rc, "divrec_coverage_hist_ranks")
+    return counts, sums
+
+
+def relevance_metrics(recs: torch.Tensor, pos_rowptr: torch.Tensor, pos_items: torch.Tensor, raw_counts: torch.Tensor) -> torch.Tensor:
+    """fp32 [4, nU]: precision, recall, average precision, ndcg @k"""
+    lib = load_library()
+    recs = _cuda(recs, "recommendations", torch.int64)
+    pos_rowptr = _cuda(pos_rowptr, "pos_rowptr", torch.int64)
+    pos_items = _cuda(pos_items, "pos_items", torch.int32)
+    raw_counts = _cuda(raw_counts, "raw_counts", torch.int32)
+    nU, k = recs.shape
+    out = torch.empty((4, nU), dtype=torch.float32, device=recs.device)
+    with torch.cuda.device(recs.device):
+        rc = lib.divrec_relevance_metrics(_ptr(recs), nU, k, _ptr(pos_rowptr), _ptr(pos_items) if pos_items.numel() else None,
+                                          _ptr(raw_counts), _ptr(out), _stream(recs.device))
+    _check(rc, "divrec_relevance_metrics")
+    return out
+
+
+def bpr_loss_fwd(pos: torch.Tensor, neg: torch.Tensor) -> torch.Tensor:
+    lib = load_library()
+    pos = _cuda(pos.detach(), "positives", torch.float32)
+    neg = _cuda(neg.detach(), "negatives", torch.float32)
+    out = torch.empty_like(pos)
+    if pos.numel() == 0:
+        return out
+    with torch.cuda.device(pos.device):
+        rc = lib.divrec_bpr_loss_fwd(_ptr(pos), _ptr(neg), pos.numel(), _ptr(out), None, _stream(pos.device))
+    _check(rc, "divrec_bpr_loss_fwd")
+    return out
+
+
+def auc_indicator(pos: torch.Tensor, neg: torch.Tensor) -> torch.Tensor:
+    lib = load_library()
+    pos = _cuda(pos, "positives", torch.float32)
+    neg = _cuda(neg, "negatives", torch.float32)
+    out = torch.empty(pos.shape, dtype=torch.int32, device=pos.device)
+    if pos.numel() == 0:
+        return out
+    with torch.cuda.device(pos.device):
+        rc = lib.divrec_bpr_loss_fwd(_ptr(pos), _ptr(neg), pos.numel(), None, _ptr(out), _stream(pos.device))
+    _check(rc, "divrec_bpr_loss_fwd")
+    return out
+
+
+def bpr_loss_bwd(pos: torch.Tensor, neg: torch.Tensor, g: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    lib = load_library()
+    pos = _cuda(pos.detach(), "positives", torch.float32)
+    neg = _cuda(neg.detach(), "negatives", torch.float32)
+    g = _cuda(g, "grad_output", torch.float32)
+    gp, gn = torch.empty_like(pos), torch.empty_like(pos)
+    if pos.numel() == 0:
+        return gp, gn
+    with torch.cuda.device(pos.device):
+        rc = lib.divrec_bpr_loss_bwd(_ptr(pos), _ptr(neg), _ptr(g), pos.numel(), _ptr(gp), _ptr(gn), _stream(pos.device))
+    _check(rc, "divrec_bpr_loss_bwd")
+    return gp, gn

@@ -1,0 +1,221 @@
+"""Score and train loops with the reference's signatures (divrec/train/utils.py:10-216).
+
+The bodies of the two hot loops change shape:
+  * get_model_recommendations: the reference iterates RankingDataset in Python (one model call and one
+    full argsort per user, :59-77).  With a MatrixFactorization model the whole thing is ONE call of the
+    fused scorer (tcgen05 GEMM + seen mask + per-user top-k, divrec_score_topk); other RankingModels are
+    scored candidate list by candidate list and ranked on the device.
+  * pair_wise_train_loop: with MatrixFactorization + LogSigmoidDifferenceLoss each batch is ONE fused
+    gather + loss + AUC kernel and ONE scatter-add backward kernel (bpr_step); other combinations take
+    the generic forward/backward route through the same native ops.
+"""
+from typing import List, Optional, Tuple
+
+import torch
+
+from .. import _native
+from ..datasets import PairWiseDataset, PointWiseDataset, RankingDataset
+from ..losses import LogSigmoidDifferenceLoss, PairWiseLoss, PointWiseLoss, RecommendationsAwareLoss
+from ..metrics.auc_score import AUCScore
+from ..models import MatrixFactorization, RankingModel
+
+
+def _model_device(model: torch.nn.Module) -> torch.device:
+    for p in model.parameters():
+        return p.device
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _reduce_all(losses, chunks):
+    return [loss.reduce_loss_values(torch.concatenate(chunks[i])) for i, loss in enumerate(losses)]
+
+
+def point_wise_score_loop(dataset: PointWiseDataset, model: RankingModel, losses: List[PointWiseLoss], **loader_params):
+    model.eval()
+    dev = _model_device(model)
+    chunks = [[] for _ in losses]
+    for user_id, item_id, user_features, item_features, true_relevance in dataset.loader(**loader_params):
+        predicted = model(user_id.to(dev), item_id.to(dev), user_features, item_features)
+        for i, loss in enumerate(losses):
+            chunks[i].append(loss.point_wise(true_relevance.to(dev), predicted))
+    return _reduce_all(losses, chunks)
+
+
+def pair_wise_score_loop(dataset: PairWiseDataset, model: RankingModel, losses: List[PairWiseLoss], **loader_params):
+    model.eval()
+    dev = _model_device(model)
+    chunks = [[] for _ in losses]
+    for user_id, pos, neg, user_features, pos_features, neg_features in dataset.loader(**loader_params):
+        user_id = user_id.to(dev)
+        positives = model(user_id, pos.to(dev), user_features, pos_features)
+        negatives = model(user_id, neg.to(dev), user_features, neg_features)
+        for i, loss in enumerate(losses):
+            chunks[i].append(loss.pair_wise(positives, negatives))
+    return _reduce_all(losses, chunks)
+
+
+@torch.no_grad()
+def get_model_recommendations(dataset: RankingDataset, model: RankingModel, number_of_recommendations: int) -> torch.LongTensor:
+    """[U,k] int64 item ids by (score desc, item id asc), on the model's device."""
+    dev = _model_device(model)
+    if dev.type != "cuda":
+        raise TypeError("divrec_b200 computes on a B200 only: move the model with .to('cuda')")
+    k = int(number_of_recommendations)
+    if isinstance(model, MatrixFactorization):
+        rowptr, items = dataset.seen_csr(dev)
+        recs, _ = model.recommend(k, rowptr, items if items.numel() else None)
+        return recs
+    # generic RankingModel: score each user's candidates with the model, rank on the device
+    out = []
+    for user_rep, _pos, candidates, user_features, item_features in dataset:
+        scores = model(user_rep.to(dev), candidates.to(dev), user_features, item_features).float()
+        order = torch.argsort(scores, descending=True, stable=True)[:k]
+        out.append(candidates.to(dev)[order])
+    return torch.stack(out)
+
+
+def recommendations_score_loop(dataset: RankingDataset, model: RankingModel, losses: List[RecommendationsAwareLoss],
+                               number_of_recommendations: int):
+    model.eval()
+    interactions = dataset.data.interactions
+    recommendations = get_model_recommendations(dataset, model, number_of_recommendations)
+    return [loss(interactions, recommendations) for loss in losses]
+
+
+def point_wise_train_loop(dataset: PointWiseDataset, model: RankingModel, loss: PointWiseLoss,
+                          optimizer: torch.optim.Optimizer, scores: Optional[List[PointWiseLoss]] = None,
+                          **loader_params) -> Tuple[float, List[float]]:
+    assert scores is None or all(score.reduce for score in scores)
+    model.train()
+    dev = _model_device(model)
+    scores = scores or []
+    n, loss_total, score_totals = 0, 0.0, [0.0] * len(scores)
+    for user_id, item_id, user_features, item_features, true_relevance in dataset.loader(**loader_params):
+        true_relevance = true_relevance.to(dev)
+        predicted = model(user_id.to(dev), item_id.to(dev), user_features, item_features)
+        value = loss(true_relevance, predicted)
+        value.backward()
+        optimizer.step()
+        optimizer.zero_grad()
+        n += 1
+        loss_total += value.item()
+        for i, score in enumerate(scores):
+            score_totals[i] += score(true_relevance, predicted).item()
+    return loss_total / n, [t / n for t in score_totals]
+
+
+class _FusedBpr(torch.autograd.Function):
+    """mean(-logsigmoid(<U[u],V[p]> - <U[u],V[n]>)) with the gather fused into the loss kernel and the
+    scatter-add fused into the backward kernel (dense .grad, duplicates accumulate)."""
+
+    @staticmethod
+    def forward(ctx, U, V, u, p, n):
+        pos, neg, loss_sum, auc_sum = _native.bpr_fwd(U, V, u, p, n)
+        ctx.save_for_backward(U, V, u, p, n, pos, neg)
+        ctx.mark_non_differentiable(pos, neg, auc_sum)
+        return loss_sum[0] / u.numel(), pos, neg, auc_sum
+
+    @staticmethod
+    def backward(ctx, g_loss, _gp, _gn, _ga):
+        U, V, u, p, n, pos, neg = ctx.saved_tensors
+        gU, gV = torch.zeros_like(U), torch.zeros_like(V)
+        _native.bpr_bwd(U, V, u, p, n, pos, neg, float(g_loss) / u.numel(), gU, gV)
+        return gU, gV, None, None, None
+
+
+def bpr_step(model: MatrixFactorization, user_id, positive_item_id, negative_item_id):
+    """(loss 0-dim with grad, pos [B], neg [B], auc_sum int32 [1]) for one batch of triples."""
+    U, V = model.user_embeddings.weight, model.item_embeddings.weight
+    dev = U.device
+    to = dict(device=dev, dtype=torch.int64)
+    return _FusedBpr.apply(U, V, user_id.to(**to), positive_item_id.to(**to), negative_item_id.to(**to))
+
+
+def pair_wise_train_loop(dataset: PairWiseDataset, model: RankingModel, loss: PairWiseLoss,
+                         optimizer: torch.optim.Optimizer, scores: Optional[List[PairWiseLoss]] = None,
+                         **loader_params) -> Tuple[float, List[float]]:
+    assert scores is None or all(score.reduce for score in scores)
+    model.train()
+    dev = _model_device(model)
+    scores = scores or []
+    fused = isinstance(model, MatrixFactorization) and type(loss) is LogSigmoidDifferenceLoss
+    n, loss_total, score_totals = 0, 0.0, [0.0] * len(scores)
+    for user_id, pos, neg, user_features, pos_features, neg_features in dataset.loader(**loader_params):
+        if fused:
+            value, positives, negatives, auc_sum = bpr_step(model, user_id, pos, neg)
+        else:
+            user_id = user_id.to(dev)
+            positives = model(user_id, pos.to(dev), user_features, pos_features)
+            negatives = model(user_id, neg.to(dev), user_features, neg_features)
+            value = loss(positives, negatives)
+        value.backward()
+        optimizer.step()
+        optimizer.zero_grad()
+        n += 1
+        loss_total += value.item()
+        for i, score in enumerate(scores):
+            if fused and type(score) is AUCScore and score.reduction == "mean":
+                score_totals[i] += auc_sum.item() / positives.numel()  # free epilogue of the fused forward
+            else:
+                score_totals[i] += score(positives, negatives).item()
+    return loss_total / n, [t / n for t in score_totals]
+
+
+def recommendations_train_loop(dataset: RankingDataset, model: RankingModel, loss: RecommendationsAwareLoss,
+                               number_of_recommendations: int, optimizer: torch.optim.Optimizer,
+                               scores: Optional[List[RecommendationsAwareLoss]] = None) -> Tuple[float, List[float]]:
+    """Kept for import compatibility.  The reference's version (train/utils.py:167-216) cannot run: the
+    recommendations it hands to the loss are integer ids with no path back to the model parameters, so
+    `loss_value.backward()` fails with every shipped loss."""
+    raise NotImplementedError(
+        "recommendations_train_loop is dead code in the reference (no differentiable path from the "
+        "recommended item ids to the model); use pair_wise_train_loop")
+
+
+_host_pipe = {}
+
+
+def host_recommend_and_score(U_host: torch.Tensor, V_host: torch.Tensor, seen_rowptr_host: torch.Tensor,
+                             seen_items_host: torch.Tensor, k: int, device, want_recommendations: bool = True):
+    """The whole evaluation pass from HOST buffers: copy the embedding tables and the seen-item CSR to the
+    device, run score + mask + top-k, ILD and the coverage histogram, and bring the results back to
+    pinned host memory.  Equivalent of recommendations_score_loop(RankingDataset(test, frozen=train),
+    MatrixFactorization, [IntraListDiversityScore, EntropyDiversityScore], k) for a caller whose model and
+    interactions live in host memory.  Returns a dict with host tensors and the bytes moved."""
+    import math
+    dev = torch.device(device)
+    nU, nI = U_host.shape[0], V_host.shape[0]
+    key = (dev.index, nU, nI, U_host.shape[1], k, seen_items_host.numel())
+    st = _host_pipe.get(key)
+    if st is None:
+        st = {
+            "U": torch.empty_like(U_host, device=dev), "V": torch.empty_like(V_host, device=dev),
+            "rp": torch.empty_like(seen_rowptr_host, device=dev), "it": torch.empty_like(seen_items_host, device=dev),
+            "counts": torch.zeros(nI, dtype=torch.int32, device=dev),
+            "recs_h": torch.empty((nU, k), dtype=torch.int64).pin_memory(),
+            "ild_h": torch.empty(nU, dtype=torch.float32).pin_memory(),
+            "counts_h": torch.empty(nI, dtype=torch.int32).pin_memory(),
+            "ent_h": torch.empty(2, dtype=torch.float32).pin_memory(),
+        }
+        _host_pipe.clear()
+        _host_pipe[key] = st
+    h2d = 0
+    for name, src in (("U", U_host), ("V", V_host), ("rp", seen_rowptr_host), ("it", seen_items_host)):
+        st[name].copy_(src, non_blocking=True)
+        h2d += src.numel() * src.element_size()
+    _scores, recs = _native.score_topk(st["U"], st["V"], k, st["rp"], st["it"] if st["it"].numel() else None)
+    ild = _native.ild_cosine(st["V"], recs)
+    st["counts"].zero_()
+    _native.coverage_hist(recs, nI, st["counts"])
+    ent = _native.entropy_from_counts(st["counts"])
+    d2h = 0
+    outs = [("ild_h", ild), ("counts_h", st["counts"]), ("ent_h", ent)]
+    if want_recommendations:
+        outs.append(("recs_h", recs))
+    for name, src in outs:
+        st[name].copy_(src, non_blocking=True)
+        d2h += src.numel() * src.element_size()
+    torch.cuda.current_stream(dev).synchronize()
+    entropy = (float(st["ent_h"][0]) - math.log(k)) / (math.log(nI) - math.log(k))
+    return {"recommendations": st["recs_h"] if want_recommendations else None, "ild_per_user": st["ild_h"],
+            "coverage_counts": st["counts_h"], "entropy_diversity": entropy, "h2d_bytes": h2d, "d2h_bytes": d2h}

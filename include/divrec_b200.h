@@ -59,6 +59,13 @@ const char* divrec_last_error(void);
 /* number of CUDA kernels this library has launched in this process (bench.py "gpu_launches") */
 int64_t divrec_launch_count(void);
 
+/* Measurement aid (bench.py roofline): when on, the library records CUDA events on the launching
+ * stream around its phases; divrec_profile_read waits for them and fills ms_out (host, [n]) with
+ * the last durations in ms, -1 where nothing was recorded.  Slots: 0 operand preparation,
+ * 1 score+filter kernel, 2 select kernel, 3 ILD, 4 coverage histogram.  Host-only calls. */
+void divrec_set_profiling(int on);
+int divrec_profile_read(float* ms_out /*host*/, int n);
+
 /* ---------------------------------------------------------------------------------------
  * score + seen-mask + per-user top-k
  *   replaces: divrec/train/utils.py:53-77 (get_model_recommendations) together with
@@ -155,6 +162,34 @@ int divrec_pair_scores(const float* U, const float* V, const int64_t* user_id,
 int divrec_pair_scores_bwd(const float* U, const float* V, const int64_t* user_id,
                            const int64_t* item_id, const float* g, int64_t L, int d, float* gU,
                            float* gV, void* stream);
+
+/* ILD with the label-equality distance D[i,j] = (labels[i] == labels[j]) without the [I,I] matrix
+ *   replaces: divrec/losses/intra_list_diversity_score.py:45-63 (IntraListBinaryUnfairnessScore) */
+int divrec_ild_labels(const int64_t* labels /*[nI]*/, int64_t nI, const int64_t* recs, int64_t nU, int k,
+                      float* out_per_user, void* stream);
+
+/* coverage counts plus the per-item sum of list positions (avg_rank)
+ *   replaces: divrec/metrics/popularity_rank_correlation_for_items.py:27-41
+ *   counts [nI] int32 and rank_sums [nI] uint64 are caller-zeroed. */
+int divrec_coverage_hist_ranks(const int64_t* recs, int64_t nU, int k, int64_t nI, int32_t* counts,
+                               uint64_t* rank_sums, void* stream);
+
+/* relevance metrics @k against the CSR of each user's positive items
+ *   replaces: divrec/metrics/precision_at_k.py:6-22, recall_at_k.py:6-22,
+ *             average_precision_at_k.py:6-24, normalized_discounted_cumulative_gain.py:6-23
+ *   pos_rowptr [nU+1], pos_items ascending per row; raw_counts [nU] = the number of interaction rows
+ *   of the user (duplicates included: the reference's recall denominator).
+ *   out [4, nU] fp32: precision, recall, average precision, ndcg. */
+int divrec_relevance_metrics(const int64_t* recs, int64_t nU, int k, const int64_t* pos_rowptr,
+                             const int32_t* pos_items, const int32_t* raw_counts, float* out, void* stream);
+
+/* elementwise BPR loss on precomputed scores; loss_values / hits may be NULL
+ *   replaces: divrec/losses/log_sigmoid_difference_loss.py:14 and divrec/metrics/auc_score.py:10
+ *   bwd: gpos[b] = -sigmoid(-(pos[b]-neg[b])) * g[b], gneg[b] = -gpos[b] (autograd of the same line) */
+int divrec_bpr_loss_fwd(const float* pos, const float* neg, int64_t B, float* loss_values, int32_t* hits,
+                        void* stream);
+int divrec_bpr_loss_bwd(const float* pos, const float* neg, const float* g, int64_t B, float* gpos,
+                        float* gneg, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,397 @@
+"""Parity of the CUDA path -- called through the C ABI (ctypes binding divrec._native) -- against the
+oracle and against golden vectors produced by the real reference.
+
+Bars (BASELINE.json north_star): top-k indices and coverage counts bit-exact (ties -> lowest item id);
+scores, ILD and loss within 1e-5 relative in fp32.  "Relative" for a dot product means relative to
+|u| |v| (single scores cancel to ~0).  Two tiers: grid-valued inputs are exact in
+every arithmetic, so everything must be bit-exact; Gaussian inputs must agree within tolerance and
+any index disagreement must sit on a near-tie of the oracle's scores.
+"""
+import math
+
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import divrec_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-5
+
+
+def csr_dev(seen, nU, dev):
+    rowptr, items = O.seen_csr(seen, nU)
+    return rowptr.to(dev), items.to(dev)
+
+
+def check_topk_against_oracle(items, scores, o_items, o_scores, U, V, exact):
+    items, scores = items.cpu(), scores.cpu()
+    if exact:
+        assert torch.equal(items, o_items)
+        assert torch.equal(scores, o_scores)
+        return 0
+    scale = (U.norm(dim=1).max() * V.norm(dim=1).max()).item()
+    tol = REL * scale
+    finite = torch.isfinite(o_scores)
+    assert torch.equal(torch.isfinite(scores), finite)
+    assert (scores[finite] - o_scores[finite]).abs().max().item() <= tol
+    differ = (items != o_items).any(dim=1).nonzero().flatten().tolist()
+    for u in differ:  # every disagreement must be a swap inside a near-tie, or a near-tie at the k boundary
+        pos = (items[u] != o_items[u]).nonzero().flatten()
+        for p in pos.tolist():
+            s_here = o_scores[u, p]
+            j = (o_items[u] == items[u, p]).nonzero().flatten()
+            if j.numel():
+                assert abs(float(o_scores[u, j[0]] - s_here)) <= 2 * tol, (u, p)
+            else:
+                assert abs(float(scores[u, p] - o_scores[u, -1])) <= 2 * tol, (u, p)
+    return len(differ)
+
+
+# ------------------------------------------------------------------------------------------------
+# score + mask + top-k
+# ------------------------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("name,exact", [("cfg1_grid", True), ("cfg1_gauss", False), ("small_k100_gauss", False)])
+def test_score_topk_vs_reference_golden(native, dev, name, exact):
+    g = load_golden(name)
+    k = int(g["k"])
+    nU = g["U"].shape[0]
+    rowptr, items = csr_dev(g["seen"], nU, dev)
+    s, i = native.score_topk(g["U"].to(dev), g["V"].to(dev), k, rowptr, items)
+    if exact:
+        # the reference's order inside exact ties is arbitrary: compare score rows bit for bit and the
+        # canonical order against the oracle
+        assert torch.equal(s.cpu(), g["rec_scores"])
+        o_i, o_s = O.recommendations_dense(g["U"], g["V"], *O.seen_csr(g["seen"], nU), k)
+        assert torch.equal(i.cpu(), o_i)
+    else:
+        n_diff = check_topk_against_oracle(i, s, g["recs"], g["rec_scores"], g["U"], g["V"], False)
+        assert n_diff <= max(1, nU // 100)
+
+
+@pytest.mark.parametrize("nU,nI,d,k,nnz,kind", [
+    (300, 1000, 64, 10, 3000, "grid"),
+    (257, 1300, 128, 100, 20000, "grid"),     # nU, nI not multiples of the 128-wide tiles
+    (129, 127, 32, 16, 500, "grid"),          # fewer items than one tile, d < 64
+    (64, 5000, 100, 128, 10000, "grid"),      # d not a multiple of 64, k = MAX_K
+    (500, 26744, 128, 100, 60000, "gauss"),   # cfg2 catalogue
+    (200, 3000, 48, 7, 0, "gauss"),           # no interactions at all
+    (1, 300, 16, 5, 10, "grid"),              # a single user
+])
+def test_score_topk_vs_oracle(native, dev, nU, nI, d, k, nnz, kind):
+    gen = torch.Generator().manual_seed(nU * 7 + nI)
+    U, V = O.make_embeddings(nU, d, kind, gen), O.make_embeddings(nI, d, kind, gen)
+    seen = O.make_seen(nU, nI, nnz, gen) if nnz else torch.zeros((0, 2), dtype=torch.int64)
+    rowptr, items = O.seen_csr(seen, nU)
+    o_i, o_s = O.recommendations_dense(U, V, rowptr, items, k)
+    s, i = native.score_topk(U.to(dev), V.to(dev), k, rowptr.to(dev), items.to(dev) if nnz else None)
+    check_topk_against_oracle(i, s, o_i, o_s, U, V, kind == "grid")
+
+
+def test_score_topk_without_mask_arguments(native, dev):
+    gen = torch.Generator().manual_seed(11)
+    U, V = O.make_embeddings(150, 64, "grid", gen), O.make_embeddings(700, 64, "grid", gen)
+    o_i, o_s = O.recommendations_dense(U, V, None, None, 20)
+    s, i = native.score_topk(U.to(dev), V.to(dev), 20)
+    assert torch.equal(i.cpu(), o_i) and torch.equal(s.cpu(), o_s)
+
+
+def test_ragged_rows_fewer_candidates_than_k(native, dev):
+    """Users whose unmasked catalogue is smaller than k (the reference itself crashes on ragged lists,
+    train/utils.py:77): padded with (-inf, -1)."""
+    gen = torch.Generator().manual_seed(13)
+    nU, nI, k = 40, 200, 50
+    U, V = O.make_embeddings(nU, 32, "grid", gen), O.make_embeddings(nI, 32, "grid", gen)
+    pairs = []
+    for u in range(nU):
+        n_seen = nI - (u % 60)  # user 0 has nothing left, user 1 one item, ...
+        pairs += [(u, i) for i in torch.randperm(nI, generator=gen)[:n_seen].tolist()]
+    seen = torch.tensor(pairs)
+    rowptr, items = O.seen_csr(seen, nU)
+    o_i, o_s = O.recommendations_dense(U, V, rowptr, items, k)
+    s, i = native.score_topk(U.to(dev), V.to(dev), k, rowptr.to(dev), items.to(dev))
+    assert torch.equal(i.cpu(), o_i) and torch.equal(s.cpu(), o_s)
+    assert (i.cpu()[0] == -1).all() and torch.isinf(s.cpu()[0]).all()
+
+
+def test_all_scores_equal_ties_broken_by_lowest_id(native, dev):
+    U, V = torch.ones(70, 64), torch.ones(900, 64)
+    seen = torch.tensor([[u, i] for u in range(70) for i in range(0, u)])
+    rowptr, items = O.seen_csr(seen, 70)
+    s, i = native.score_topk(U.to(dev), V.to(dev), 10, rowptr.to(dev), items.to(dev))
+    expect = torch.stack([torch.arange(u, u + 10) for u in range(70)])
+    assert torch.equal(i.cpu(), expect) and (s.cpu() == 64.0).all()
+
+
+def test_bf16_tables(native, dev):
+    gen = torch.Generator().manual_seed(17)
+    U = O.make_embeddings(200, 256, "gauss", gen).bfloat16()
+    V = O.make_embeddings(5000, 256, "gauss", gen).bfloat16()
+    o_i, o_s = O.recommendations_dense(U.float(), V.float(), None, None, 100)
+    s, i = native.score_topk(U.to(dev), V.to(dev), 100)
+    check_topk_against_oracle(i, s, o_i, o_s, U.float(), V.float(), False)
+    Ug, Vg = O.make_embeddings(100, 256, "grid", gen), O.make_embeddings(3000, 256, "grid", gen)
+    o_i, o_s = O.recommendations_dense(Ug, Vg, None, None, 100)
+    s, i = native.score_topk(Ug.bfloat16().to(dev), Vg.bfloat16().to(dev), 100)
+    assert torch.equal(i.cpu(), o_i) and torch.equal(s.cpu(), o_s)
+
+
+def test_item_sharded_merge_equals_unsharded(native, dev):
+    """cfg4 in miniature: 8 catalogue shards scored separately (item_id_offset), lists merged by
+    divrec_topk_merge == one unsharded call, bit for bit."""
+    gen = torch.Generator().manual_seed(19)
+    nU, nI, d, k, n_sh = 300, 8000, 64, 100, 8
+    U, V = O.make_embeddings(nU, d, "grid", gen), O.make_embeddings(nI, d, "grid", gen)
+    seen = O.make_seen(nU, nI, 20000, gen)
+    rowptr, items = csr_dev(seen, nU, dev)
+    Ud, Vd = U.to(dev), V.to(dev)
+    full_s, full_i = native.score_topk(Ud, Vd, k, rowptr, items)
+    per = nI // n_sh
+    gs, gi = [], []
+    for sh in range(n_sh):
+        s, i = native.score_topk(Ud, Vd[sh * per:(sh + 1) * per].contiguous(), k, rowptr, items, item_id_offset=sh * per)
+        gs.append(s)
+        gi.append(i)
+    ms, mi = native.topk_merge(torch.stack(gs), torch.stack(gi))
+    assert torch.equal(mi, full_i) and torch.equal(ms, full_s)
+    o_s, o_i = O.topk_merge(torch.stack(gs).cpu(), torch.stack(gi).cpu(), k)
+    assert torch.equal(mi.cpu(), o_i) and torch.equal(ms.cpu(), o_s)
+
+
+# ------------------------------------------------------------------------------------------------
+# ILD / coverage / entropy
+# ------------------------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("name", ["cfg1_gauss", "cfg1_grid", "small_k100_gauss"])
+def test_ild_and_coverage_vs_reference_golden(native, dev, name):
+    g = load_golden(name)
+    n = int(g["ild_users"])
+    V, recs = g["V"].to(dev), g["recs"].to(dev)
+    for mode in (native.ILD_SUMVEC, native.ILD_PAIRWISE):
+        ild = native.ild_cosine(V, recs[:n], mode).cpu()
+        torch.testing.assert_close(ild, g["ild_none"], rtol=REL, atol=1e-7)
+    D = O.cosine_distance_matrix(g["V"]).to(dev)
+    torch.testing.assert_close(native.ild_matrix(D, recs[:n]).cpu(), g["ild_none"], rtol=REL, atol=1e-7)
+    counts = native.coverage_hist(recs, g["V"].shape[0]).cpu()
+    nz = counts.nonzero().flatten()
+    assert torch.equal(nz, g["cov_values"]) and torch.equal(counts[nz].long(), g["cov_counts"])
+    ent = native.entropy_from_counts(counts.to(dev)).cpu()
+    k = recs.shape[1]
+    val = (float(ent[0]) - math.log(k)) / (math.log(g["V"].shape[0]) - math.log(k))
+    assert val == pytest.approx(float(g["entropy"]), rel=REL)
+    assert int(ent[1]) == nz.numel()
+
+
+def test_ild_known_answers_and_padding(native, dev):
+    V = torch.eye(8).repeat(1, 4)  # d = 32, orthogonal rows
+    recs = torch.tensor([[0, 1, 2, 3], [4, 5, 6, 7]])
+    for mode in (native.ILD_SUMVEC, native.ILD_PAIRWISE):
+        out = native.ild_cosine(V.to(dev), recs.to(dev), mode).cpu()
+        torch.testing.assert_close(out, torch.full((2,), 0.5))
+        same = native.ild_cosine(torch.ones(5, 32, device=dev), torch.tensor([[0, 1, 2, 3]], device=dev), mode).cpu()
+        assert abs(float(same[0])) < 1e-6
+    gen = torch.Generator().manual_seed(23)
+    Vg = O.make_embeddings(500, 64, "gauss", gen)
+    r = torch.stack([torch.randperm(500, generator=gen)[:20] for _ in range(33)])
+    r[::3, 15:] = -1  # ragged lists padded with -1
+    ref = O.ild_cosine(r, Vg)
+    for mode in (native.ILD_SUMVEC, native.ILD_PAIRWISE):
+        torch.testing.assert_close(native.ild_cosine(Vg.to(dev), r.to(dev), mode).cpu(), ref, rtol=REL, atol=1e-7)
+
+
+def test_ild_asymmetric_and_integer_matrix(native, dev):
+    gen = torch.Generator().manual_seed(29)
+    D = torch.rand(60, 60, generator=gen)
+    recs = torch.stack([torch.randperm(60, generator=gen)[:9] for _ in range(21)])
+    torch.testing.assert_close(native.ild_matrix(D.to(dev), recs.to(dev)).cpu(), O.ild_matrix(recs, D), rtol=REL, atol=0)
+    torch.testing.assert_close(O.ild_matrix(recs[:4], D), O.ild_matrix_loop(recs[:4], D), rtol=REL, atol=0)
+    labels = torch.randint(0, 3, (60,), generator=gen)
+    Di = (labels[None, :] == labels[:, None]).int()
+    want = O.ild_matrix(recs, Di)
+    torch.testing.assert_close(native.ild_matrix(Di.to(dev), recs.to(dev)).cpu(), want, rtol=0, atol=1e-7)
+    torch.testing.assert_close(native.ild_labels(labels.to(dev), recs.to(dev)).cpu(), want, rtol=0, atol=1e-7)
+
+
+def test_coverage_sharded_accumulation(native, dev):
+    gen = torch.Generator().manual_seed(31)
+    recs = torch.randint(0, 999, (1001, 7), generator=gen)
+    recs[5, 3] = -1
+    counts = torch.zeros(999, dtype=torch.int32, device=dev)
+    for part in recs.to(dev).chunk(3):  # user shards accumulate into one histogram
+        native.coverage_hist(part.contiguous(), 999, counts)
+    assert torch.equal(counts.cpu().long(), O.coverage_counts(recs, 999))
+
+
+# ------------------------------------------------------------------------------------------------
+# BPR
+# ------------------------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("name", ["bpr_small", "bpr_d64"])
+def test_bpr_vs_reference_golden(native, dev, name):
+    g = load_golden(name)
+    U, V = g["U"].to(dev), g["V"].to(dev)
+    u, p, n = g["u"].to(dev), g["p"].to(dev), g["n"].to(dev)
+    B = u.numel()
+    pos, neg, loss_sum, auc_sum = native.bpr_fwd(U, V, u, p, n)
+    scale = float(g["U"].norm(dim=1).max() * g["V"].norm(dim=1).max())
+    assert (pos.cpu() - g["pos"]).abs().max().item() <= REL * scale
+    assert (neg.cpu() - g["neg"]).abs().max().item() <= REL * scale
+    assert float(loss_sum) / B == pytest.approx(float(g["loss"]), rel=REL)
+    assert int(auc_sum) / B == pytest.approx(float(g["auc"]), abs=1.5 / B)
+    gU, gV = torch.zeros_like(U), torch.zeros_like(V)
+    native.bpr_bwd(U, V, u, p, n, pos, neg, 1.0 / B, gU, gV)
+    for got, want in ((gU.cpu(), g["gU"]), (gV.cpu(), g["gV"])):
+        assert (got - want).abs().max().item() <= REL * float(want.abs().max())
+        assert torch.equal(got == 0, want == 0)  # untouched rows stay exactly zero
+    # paired scorer (MatrixFactorization.forward)
+    out = native.pair_scores(U, V, u, p).cpu()
+    assert (out - g["pos"]).abs().max().item() <= REL * scale
+    lv = native.bpr_loss_fwd(pos, neg).cpu()
+    torch.testing.assert_close(lv, -torch.nn.functional.logsigmoid(g["pos"] - g["neg"]), rtol=1e-5, atol=1e-6)
+
+
+def test_bpr_permutation_invariance(native, dev):
+    g = load_golden("bpr_d64")
+    U, V = g["U"].to(dev), g["V"].to(dev)
+    perm = torch.randperm(g["u"].numel(), generator=torch.Generator().manual_seed(1))
+    outs = []
+    for idx in (torch.arange(perm.numel()), perm):
+        u, p, n = g["u"][idx].to(dev), g["p"][idx].to(dev), g["n"][idx].to(dev)
+        pos, neg, _, _ = native.bpr_fwd(U, V, u, p, n)
+        gU, gV = torch.zeros_like(U), torch.zeros_like(V)
+        native.bpr_bwd(U, V, u, p, n, pos, neg, 1.0 / perm.numel(), gU, gV)
+        outs.append((gU.cpu(), gV.cpu()))
+    for a, b in zip(outs[0], outs[1]):
+        assert (a - b).abs().max().item() <= 1e-6 * float(a.abs().max())
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference-facing Python API on top of the C ABI
+# ------------------------------------------------------------------------------------------------
+
+
+def test_shim_end_to_end_matches_reference_golden(native, dev):
+    from divrec.datasets import RankingDataset, UserItemInteractionsDataset
+    from divrec.losses import IntraListDiversityScore, LogSigmoidDifferenceLoss
+    from divrec.metrics import AUCScore, EntropyDiversityScore
+    from divrec.models import MatrixFactorization
+    from divrec.train import bpr_step, get_model_recommendations, recommendations_score_loop
+
+    g = load_golden("cfg1_gauss")
+    nU, nI, d = 943, 1682, 64
+    model = MatrixFactorization(nU, nI, d)
+    model.load_state_dict({"user_embeddings.weight": g["U"], "item_embeddings.weight": g["V"]})
+    model.to(dev)
+    data = UserItemInteractionsDataset(interactions=torch.tensor([[nU - 1, nI - 1]]), number_of_users=nU, number_of_items=nI)
+    frozen = UserItemInteractionsDataset(interactions=g["seen"], number_of_users=nU, number_of_items=nI)
+    ds = RankingDataset(data, frozen=frozen)
+    recs = get_model_recommendations(ds, model, 10)
+    assert recs.dtype == torch.int64 and tuple(recs.shape) == (943, 10)
+    assert (recs.cpu() != g["recs"]).any(dim=1).sum().item() <= 9
+    ild = IntraListDiversityScore(item_embeddings=model.item_embeddings.weight, reduction="mean")
+    ent = EntropyDiversityScore(dataset=data)
+    v_ild, v_ent = recommendations_score_loop(ds, model, [ild, ent], 10)
+    assert float(v_ild) == pytest.approx(float(g["ild_mean"]), rel=1e-4)
+    assert float(v_ent) == pytest.approx(float(g["entropy"]), rel=1e-4)
+    # model.forward + loss + autograd route == reference autograd
+    b = load_golden("bpr_d64")
+    m2 = MatrixFactorization(300, 200, 64)
+    m2.load_state_dict({"user_embeddings.weight": b["U"], "item_embeddings.weight": b["V"]})
+    m2.to(dev)
+    u, p, n = b["u"].to(dev), b["p"].to(dev), b["n"].to(dev)
+    pos, neg = m2(u, p), m2(u, n)
+    loss = LogSigmoidDifferenceLoss()(pos, neg)
+    loss.backward()
+    assert float(loss) == pytest.approx(float(b["loss"]), rel=REL)
+    assert float(AUCScore()(pos, neg)) == pytest.approx(float(b["auc"]), abs=2e-3)
+    gU_generic = m2.user_embeddings.weight.grad.clone()
+    gV_generic = m2.item_embeddings.weight.grad.clone()
+    m2.zero_grad()
+    loss2, _, _, _ = bpr_step(m2, u, p, n)
+    loss2.backward()
+    for got, want in ((gU_generic, b["gU"]), (m2.user_embeddings.weight.grad, b["gU"]),
+                      (gV_generic, b["gV"]), (m2.item_embeddings.weight.grad, b["gV"])):
+        assert (got.cpu() - want).abs().max().item() <= REL * float(want.abs().max())
+
+
+def test_relevance_metrics_vs_reference_formulas(native, dev):
+    """precision / recall / AP / NDCG against a direct restatement of the reference loops
+    (precision_at_k.py:16-22, recall_at_k.py:16-22, average_precision_at_k.py:18-24, ndcg :16-23)."""
+    from divrec.metrics import average_precision_at_k, normalized_discounted_cumulative_gain, precision_at_k, recall_at_k
+    gen = torch.Generator().manual_seed(37)
+    nU, nI, k = 50, 80, 12
+    inter = torch.stack([torch.randint(0, nU, (600,), generator=gen), torch.randint(0, nI, (600,), generator=gen)], 1)
+    inter[:nU, 0] = torch.arange(nU)
+    recs = torch.stack([torch.randperm(nI, generator=gen)[:k] for _ in range(nU)])
+    want = torch.zeros(4, nU)
+    disc = torch.arange(1, k + 1)
+    dlog = torch.log2(torch.arange(2, k + 2))
+    for u in range(nU):
+        positives = inter[inter[:, 0] == u, 1]
+        rel = torch.isin(recs[u], positives).float()
+        want[0, u] = rel.sum() / k
+        want[1, u] = rel.sum() / positives.size(0)
+        want[2, u] = torch.sum(torch.cumsum(rel, 0) / disc) / k
+        want[3, u] = torch.sum(rel / dlog) / torch.sum(1 / dlog)
+    r = recs.to(dev)
+    got = torch.stack([precision_at_k(inter, r), recall_at_k(inter, r), average_precision_at_k(inter, r),
+                       normalized_discounted_cumulative_gain(inter, r)]).cpu()
+    torch.testing.assert_close(got, want, rtol=1e-5, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------
+# full size (BASELINE.json configs[1]): size-independent properties + sampled oracle rows
+# ------------------------------------------------------------------------------------------------
+
+
+def test_cfg2_full_size_properties(native, dev):
+    nU, nI, d, k = 138493, 26744, 128, 100
+    gen = torch.Generator().manual_seed(0)
+    U, V = O.make_embeddings(nU, d, "gauss", gen), O.make_embeddings(nI, d, "gauss", gen)
+    seen = O.make_seen(nU, nI, 2_000_000, gen)
+    rowptr, items = O.seen_csr(seen, nU)
+    Ud, Vd, rp, it = U.to(dev), V.to(dev), rowptr.to(dev), items.to(dev)
+    s, i = native.score_topk(Ud, Vd, k, rp, it)
+    # sortedness in the canonical total order
+    ok = (s[:, :-1] > s[:, 1:]) | ((s[:, :-1] == s[:, 1:]) & (i[:, :-1] < i[:, 1:]))
+    assert bool(ok.all())
+    # no duplicates, ids in range
+    assert bool((i >= 0).all()) and bool((i < nI).all())
+    assert bool((i.sort(dim=1).values.diff(dim=1) > 0).all())
+    # masked items never appear: membership test of (user, item) keys
+    keys = (torch.arange(nU, device=dev)[:, None] * nI + i).flatten()
+    seen_keys = (seen[:, 0] * nI + seen[:, 1]).to(dev)
+    assert not bool(torch.isin(keys, seen_keys).any())
+    # reported scores are the dot products of the reported items (rescoring in fp64)
+    rows = torch.arange(0, nU, 997, device=dev)
+    ref = torch.einsum("ud,ukd->uk", Ud[rows].double(), Vd[i[rows]].double())
+    scale = float(U.norm(dim=1).max() * V.norm(dim=1).max())
+    assert (s[rows].double() - ref).abs().max().item() <= REL * scale
+    # sampled rows against the oracle
+    sample = torch.arange(0, nU, 541)
+    sub_rowptr = torch.zeros(sample.numel() + 1, dtype=torch.int64)
+    sub_items = []
+    for n_, u in enumerate(sample.tolist()):
+        seg = items[rowptr[u]:rowptr[u + 1]]
+        sub_items.append(seg)
+        sub_rowptr[n_ + 1] = sub_rowptr[n_] + seg.numel()
+    o_i, o_s = O.recommendations_dense(U[sample], V, sub_rowptr, torch.cat(sub_items), k)
+    check_topk_against_oracle(i[sample.to(dev)], s[sample.to(dev)], o_i, o_s, U, V, False)
+    # user-sharded == unsharded (checksum of checksums): two halves concatenated give the same lists
+    h = nU // 2
+    s0, i0 = native.score_topk(Ud[:h].contiguous(), Vd, k, rp[:h + 1].contiguous(), it)
+    assert torch.equal(i0, i[:h]) and torch.equal(s0, s[:h])
+    # coverage: counts sum to U k and match a bincount; ILD modes agree and stay in [0, 1]
+    counts = native.coverage_hist(i, nI)
+    assert int(counts.sum()) == nU * k
+    assert torch.equal(counts.long(), torch.bincount(i.flatten(), minlength=nI))
+    a = native.ild_cosine(Vd, i, native.ILD_SUMVEC)
+    b = native.ild_cosine(Vd[:, :], i[:4096].contiguous(), native.ILD_PAIRWISE)
+    torch.testing.assert_close(a[:4096], b, rtol=REL, atol=1e-7)
+    assert bool((a > 0).all()) and bool((a < 1).all())
+    torch.testing.assert_close(a[sample.to(dev)].cpu(), O.ild_cosine(i[sample.to(dev)].cpu(), V), rtol=REL, atol=1e-7)
