@@ -169,11 +169,13 @@ def bench_ours(args):
     launches = N.launch_count() - launches0
     # per-kernel time of the dominant kernel: events recorded by the library around the score+filter
     # launch, on the launching stream; read back per step in a second short loop (same inputs)
-    kern = []
+    kern, phases = [], []
     for _ in range(min(args.steps, 10)):
         step()
         torch.cuda.synchronize()
-        kern.append(N.profile_read()["score_filter_ms"])
+        phases.append(N.profile_read())
+        kern.append(phases[-1]["score_filter_ms"])
+    _s, _i, stats = N.score_topk(Ud, Vd, k, rpd, itd, return_stats=True)
     N.set_profiling(False)
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -225,6 +227,8 @@ def bench_ours(args):
                      "traffic": None, "kernel": "score_filter_kernel", "kernel_ms": kms,
                      "algorithmic_flop_per_launch": flop, "peak_source": pk["source"] + " bf16 sustained (kernel timed inside a long step)"},
         "cpu_baseline": cpu,
+        "phases_ms": {name: sorted(ph[name] for ph in phases)[len(phases) // 2] for name in phases[0]},
+        "rescued_rows_per_step": stats["rescued_rows"],
     }
     print(json.dumps(line))
     if dist is not None:
@@ -292,7 +296,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
-    ap.add_argument("--cpu-sample", type=int, default=4096)
+    ap.add_argument("--cpu-sample", type=int, default=32768)
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU-baseline leg (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":

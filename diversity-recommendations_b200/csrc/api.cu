@@ -26,7 +26,7 @@ static int cuda_fail(cudaError_t e, const char* where) {
 }
 
 // ---- optional per-kernel timing (bench.py roofline): CUDA events on the launching stream ----
-enum ProfSlot { PROF_PREP = 0, PROF_FILTER = 1, PROF_SELECT = 2, PROF_ILD = 3, PROF_COVERAGE = 4, PROF_SLOTS = 5 };
+enum ProfSlot { PROF_PREP = 0, PROF_FILTER = 1, PROF_SELECT = 2, PROF_ILD = 3, PROF_COVERAGE = 4, PROF_RESCUE = 5, PROF_SLOTS = 6 };
 static std::atomic<int> g_prof_on{0};
 static cudaEvent_t g_prof_ev[PROF_SLOTS][2];
 static bool g_prof_made = false;
@@ -62,24 +62,34 @@ static DevInfo device_info() {
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-// workspace layout of score_topk / score_dense
+constexpr int64_t CHUNK_USERS = 148 * 8 * 128;  // users per internal pass: 8 user blocks per SM, bounds the workspace
+
+// workspace layout of score_topk (one chunk of users at a time; the item plane is prepared once)
 struct WsLayout {
   int d_pad, K;
-  bool needA, needB;  // operands have to be rewritten into the workspace
-  size_t offA, offB, offLists, offCounts, offScalars, total;
+  bool convA, convB;  // operands have to be rewritten into the workspace (fp32 -> fp16, or bf16 padding)
+  int64_t chunk;
+  int rescue_grid;
+  size_t offA, offB, offNormU, offListS, offListI, offCounts, offThr, offFail, offScalars, offRescue, total;
 };
 static WsLayout ws_layout(int64_t nU, int64_t nI, int d, int dtype) {
   WsLayout w{};
   w.d_pad = (int)align_up((size_t)d, 64);
-  if (dtype == DIVREC_F32) { w.K = 3 * w.d_pad; w.needA = w.needB = true; }
-  else { w.K = w.d_pad; w.needA = w.needB = (d != w.d_pad); }
+  w.K = w.d_pad;
+  w.convA = w.convB = (dtype == DIVREC_F32) || (d != w.d_pad);
+  w.chunk = nU < CHUNK_USERS ? nU : CHUNK_USERS;
+  const size_t cpad = align_up((size_t)w.chunk, 128);
   size_t off = 0;
-  w.offA = off; if (w.needA) off += align_up((size_t)nU * w.K * 2, 1024);
-  w.offB = off; if (w.needB) off += align_up((size_t)nI * w.K * 2, 1024);
-  const size_t nU_pad = align_up((size_t)nU, 128);
-  w.offLists = off; off += align_up(nU_pad * 2 * LIST_CAP * sizeof(uint2), 1024);
-  w.offCounts = off; off += align_up(nU_pad * 2 * sizeof(int32_t), 1024);
-  w.offScalars = off; off += 1024;  // [0..1] amax bits, [2..3] scale exps
+  w.offA = off; if (w.convA) off += align_up(cpad * w.K * 2, 1024);
+  w.offB = off; if (w.convB) off += align_up((size_t)nI * w.K * 2, 1024);
+  w.offNormU = off; off += align_up(cpad * sizeof(float), 1024);
+  w.offListS = off; off += align_up(cpad * 2 * LIST_CAP * GROUP * sizeof(float), 1024);
+  w.offListI = off; off += align_up(cpad * 2 * LIST_CAP * sizeof(uint32_t), 1024);
+  w.offCounts = off; off += align_up(cpad * 2 * sizeof(int32_t), 1024);
+  w.offThr = off; off += align_up(cpad * sizeof(float), 1024);
+  w.offFail = off; off += align_up(cpad * sizeof(int32_t), 1024);
+  w.offScalars = off; off += 1024;  // u32[0..1] amax bits (U,V), i32[2..3] scale exps, u32[4] max item norm, i32[5] fail count
+  w.offRescue = off; off += align_up(rescue_scratch_bytes(nI, &w.rescue_grid), 1024);
   w.total = off;
   return w;
 }
@@ -88,49 +98,15 @@ static int check_score_args(const void* U, const void* V, int64_t nU, int64_t nI
   if (!U || !V) return fail(DIVREC_ERR_ARG, "score: null embedding table");
   if (nU <= 0 || nI <= 0 || d <= 0) return fail(DIVREC_ERR_ARG, "score: nU, nI, d must be positive");
   if (nI >= (int64_t)1 << 31) return fail(DIVREC_ERR_ARG, "score: nI must be < 2^31");
-  if (dtype == DIVREC_F32) {
-    if (mode != DIVREC_MODE_FP32_PARITY) return fail(DIVREC_ERR_ARG, "score: f32 tables need mode FP32_PARITY");
-    if (d > 128) return fail(DIVREC_ERR_ARG, "score: f32 tables support d <= 128 in this version");
-  } else if (dtype == DIVREC_BF16) {
-    if (mode != DIVREC_MODE_BF16) return fail(DIVREC_ERR_ARG, "score: bf16 tables need mode BF16");
-    if (d > 384) return fail(DIVREC_ERR_ARG, "score: bf16 tables support d <= 384 in this version");
-    if ((reinterpret_cast<uintptr_t>(U) & 15) || (reinterpret_cast<uintptr_t>(V) & 15))
-      return fail(DIVREC_ERR_ARG, "score: bf16 tables must be 16-byte aligned");
-  } else {
-    return fail(DIVREC_ERR_ARG, "score: unknown dtype");
-  }
+  if (dtype != DIVREC_F32 && dtype != DIVREC_BF16) return fail(DIVREC_ERR_ARG, "score: unknown dtype");
+  if (mode != DIVREC_MODE_TENSOR && mode != DIVREC_MODE_SIMT) return fail(DIVREC_ERR_ARG, "score: unknown mode");
+  if (mode == DIVREC_MODE_TENSOR && d > 512) return fail(DIVREC_ERR_ARG, "score: the tensor-core path supports d <= 512 (use DIVREC_MODE_SIMT)");
+  if (d > 8192) return fail(DIVREC_ERR_ARG, "score: d must be <= 8192");
+  if ((reinterpret_cast<uintptr_t>(U) & 15) || (reinterpret_cast<uintptr_t>(V) & 15))
+    return fail(DIVREC_ERR_ARG, "score: embedding tables must be 16-byte aligned");
   DevInfo di = device_info();
   if (!di.ok) return fail(DIVREC_ERR_CUDA, "score: cannot query the CUDA device");
   if (di.cc_major != 10) return fail(DIVREC_ERR_DEVICE, "score: this library only runs on sm_100 (B200)");
-  return DIVREC_OK;
-}
-
-// prepare 16-bit K-major operand planes; returns pointers the TMA descriptors are built on
-static int prepare_operands(const void* U, const void* V, int64_t nU, int64_t nI, int d, int dtype, const WsLayout& w,
-                            uint8_t* ws, cudaStream_t st, const void** A16, const void** B16, int* fmt,
-                            const int32_t** scale_exps) {
-  uint32_t* scal = reinterpret_cast<uint32_t*>(ws + w.offScalars);
-  if (dtype == DIVREC_F32) {
-    cudaError_t e = cudaMemsetAsync(scal, 0, 16, st);
-    if (e != cudaSuccess) return cuda_fail(e, "memset scalars");
-    e = launch_split_f32(reinterpret_cast<const float*>(U), nU, d, w.d_pad, 0, reinterpret_cast<__half*>(ws + w.offA),
-                         scal + 0, reinterpret_cast<int32_t*>(scal + 2), st);
-    if (e != cudaSuccess) return cuda_fail(e, "split user table");
-    e = launch_split_f32(reinterpret_cast<const float*>(V), nI, d, w.d_pad, 1, reinterpret_cast<__half*>(ws + w.offB),
-                         scal + 1, reinterpret_cast<int32_t*>(scal + 3), st);
-    if (e != cudaSuccess) return cuda_fail(e, "split item table");
-    *A16 = ws + w.offA; *B16 = ws + w.offB; *fmt = 0;
-    *scale_exps = reinterpret_cast<const int32_t*>(scal + 2);
-  } else {
-    *A16 = U; *B16 = V; *fmt = 1; *scale_exps = nullptr;
-    if (w.needA) {
-      cudaError_t e = launch_pad_bf16(U, nU, d, w.d_pad, ws + w.offA, st);
-      if (e != cudaSuccess) return cuda_fail(e, "pad user table");
-      e = launch_pad_bf16(V, nI, d, w.d_pad, ws + w.offB, st);
-      if (e != cudaSuccess) return cuda_fail(e, "pad item table");
-      *A16 = ws + w.offA; *B16 = ws + w.offB;
-    }
-  }
   return DIVREC_OK;
 }
 
@@ -178,61 +154,124 @@ int divrec_score_topk(const void* U, const void* V, int64_t nU, int64_t nI, int 
   if (reinterpret_cast<uintptr_t>(workspace) & 1023) return fail(DIVREC_ERR_ARG, "score_topk: workspace must be 1024-byte aligned");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  if (seen_items == nullptr) seen_rowptr = nullptr;
+  const bool tensor = mode == DIVREC_MODE_TENSOR;
+  const size_t esz = dtype == DIVREC_F32 ? 4 : 2;
 
-  const void *A16, *B16;
-  int fmt;
-  const int32_t* scale_exps;
+  uint32_t* scal = reinterpret_cast<uint32_t*>(ws + w.offScalars);
+  uint32_t* amax = scal;                                      // [0] users, [1] items
+  int32_t* sexp = reinterpret_cast<int32_t*>(scal + 2);       // [0] users, [1] items
+  uint32_t* nvmax = scal + 4;
+  int32_t* fail_count = reinterpret_cast<int32_t*>(scal + 5);
+  float* norms_u = reinterpret_cast<float*>(ws + w.offNormU);
+  cudaError_t e = cudaMemsetAsync(scal, 0, 64, st);
+  if (e != cudaSuccess) return cuda_fail(e, "memset scalars");
+
+  // item plane: once per call
+  const void* B16 = V;
   prof_mark(PROF_PREP, 0, st);
-  rc = prepare_operands(U, V, nU, nI, d, dtype, w, ws, st, &A16, &B16, &fmt, &scale_exps);
-  if (rc != DIVREC_OK) return rc;
-  prof_mark(PROF_PREP, 1, st);
+  if (tensor) {
+    if (dtype == DIVREC_F32) {
+      e = launch_prep_f32(reinterpret_cast<const float*>(V), nI, d, w.d_pad, reinterpret_cast<__half*>(ws + w.offB), amax + 1,
+                          sexp + 1, nullptr, nvmax, st);
+      B16 = ws + w.offB;
+    } else {
+      e = launch_prep_bf16(V, nI, d, w.d_pad, w.convB ? ws + w.offB : nullptr, nullptr, nvmax, st);
+      if (w.convB) B16 = ws + w.offB;
+    }
+    if (e != cudaSuccess) return cuda_fail(e, "prepare item table");
+  }
 
-  FilterParams fp{};
-  fp.nU = nU; fp.nI = (int32_t)nI; fp.kblocks = w.K / 64; fp.fmt = fmt; fp.k = k;
-  fp.seen_rowptr = seen_items ? seen_rowptr : nullptr; fp.seen_items = seen_items; fp.item_id_offset = item_id_offset;
-  fp.lists = reinterpret_cast<uint2*>(ws + w.offLists);
-  fp.list_count = reinterpret_cast<int32_t*>(ws + w.offCounts);
-  fp.dump = nullptr; fp.scale_exps = scale_exps;
-  const char* err = "";
-  prof_mark(PROF_FILTER, 0, st);
-  cudaError_t e = launch_score_filter(A16, B16, fp, device_info().sm_count, st, &err);
-  if (e != cudaSuccess) return cuda_fail(e, err[0] ? err : "score_filter launch");
-  prof_mark(PROF_FILTER, 1, st);
+  for (int64_t u0 = 0; u0 < nU; u0 += w.chunk) {
+    const int64_t cu = (nU - u0 < w.chunk) ? nU - u0 : w.chunk;
+    const uint8_t* Uc = reinterpret_cast<const uint8_t*>(U) + (size_t)u0 * d * esz;
+    const int64_t* rp = seen_rowptr ? seen_rowptr + u0 : nullptr;
+    float* outs = out_scores + (size_t)u0 * k;
+    int64_t* outi = out_items + (size_t)u0 * k;
 
-  SelectParams sp{};
-  sp.nU = nU; sp.nI = (int32_t)nI; sp.k = k; sp.lists = fp.lists; sp.list_count = fp.list_count;
-  sp.seen_rowptr = fp.seen_rowptr; sp.seen_items = seen_items; sp.item_id_offset = item_id_offset;
-  sp.scale_exps = scale_exps; sp.out_scores = out_scores; sp.out_items = out_items;
-  prof_mark(PROF_SELECT, 0, st);
-  e = launch_select_topk(sp, st);
-  if (e != cudaSuccess) return cuda_fail(e, "select_topk launch");
-  prof_mark(PROF_SELECT, 1, st);
+    SelectParams sp{};
+    sp.nU = cu; sp.nI = (int32_t)nI; sp.k = k; sp.d = d; sp.dtype = dtype; sp.cap = LIST_CAP;
+    sp.U = Uc; sp.V = V;
+    sp.list_scores = reinterpret_cast<float*>(ws + w.offListS);
+    sp.list_item0 = reinterpret_cast<uint32_t*>(ws + w.offListI);
+    sp.list_count = reinterpret_cast<int32_t*>(ws + w.offCounts);
+    sp.thr = reinterpret_cast<float*>(ws + w.offThr);
+    sp.seen_rowptr = rp; sp.seen_items = seen_items; sp.item_id_offset = item_id_offset;
+    sp.norms_u = norms_u; sp.nvmax_bits = nvmax;
+    sp.out_scores = outs; sp.out_items = outi;
+    sp.fail_rows = reinterpret_cast<int32_t*>(ws + w.offFail); sp.fail_count = fail_count;
+    sp.force_fail = tensor ? 0 : 1;
+
+    if (u0 > 0) {
+      e = cudaMemsetAsync(fail_count, 0, sizeof(int32_t), st);
+      if (e != cudaSuccess) return cuda_fail(e, "memset fail count");
+    }
+    if (tensor) {
+      const void* A16 = Uc;
+      if (u0 > 0) prof_mark(PROF_PREP, 0, st);
+      if (dtype == DIVREC_F32) {
+        e = cudaMemsetAsync(amax, 0, sizeof(uint32_t), st);
+        if (e != cudaSuccess) return cuda_fail(e, "memset amax");
+        e = launch_prep_f32(reinterpret_cast<const float*>(Uc), cu, d, w.d_pad, reinterpret_cast<__half*>(ws + w.offA), amax,
+                            sexp, norms_u, nullptr, st);
+        A16 = ws + w.offA;
+        sp.scale_exps = sexp; sp.amax_bits = amax;
+        sp.c_margin = 1.1f / 1024.0f;
+      } else {
+        e = launch_prep_bf16(Uc, cu, d, w.d_pad, w.convA ? ws + w.offA : nullptr, norms_u, nullptr, st);
+        if (w.convA) A16 = ws + w.offA;
+        sp.scale_exps = nullptr; sp.amax_bits = nullptr;
+        sp.c_margin = 1.0f / 4096.0f;
+      }
+      if (e != cudaSuccess) return cuda_fail(e, "prepare user table");
+      prof_mark(PROF_PREP, 1, st);
+
+      FilterParams fp{};
+      fp.nU = cu; fp.nI = (int32_t)nI; fp.kblocks = w.K / 64; fp.fmt = dtype == DIVREC_F32 ? 0 : 1; fp.k = k;
+      fp.use_hint = 1; fp.cap = LIST_CAP; fp.seen_rowptr = rp;
+      fp.list_scores = reinterpret_cast<float*>(ws + w.offListS);
+      fp.list_item0 = reinterpret_cast<uint32_t*>(ws + w.offListI);
+      fp.list_count = reinterpret_cast<int32_t*>(ws + w.offCounts);
+      fp.thr_out = reinterpret_cast<float*>(ws + w.offThr);
+      const char* err = "";
+      prof_mark(PROF_FILTER, 0, st);
+      e = launch_score_filter(A16, B16, fp, device_info().sm_count, st, &err);
+      if (e != cudaSuccess) return cuda_fail(e, err[0] ? err : "score_filter launch");
+      prof_mark(PROF_FILTER, 1, st);
+    } else {
+      // DIVREC_MODE_SIMT: no candidate lists; select only enqueues every row for the exact kernel
+      e = cudaMemsetAsync(ws + w.offCounts, 0, align_up((size_t)cu, 128) * 2 * sizeof(int32_t), st);
+      if (e != cudaSuccess) return cuda_fail(e, "memset counts");
+    }
+    prof_mark(PROF_SELECT, 0, st);
+    e = launch_select_topk(sp, st);
+    if (e != cudaSuccess) return cuda_fail(e, "select_topk launch");
+    prof_mark(PROF_SELECT, 1, st);
+
+    RescueParams rp2{};
+    rp2.nU = cu; rp2.nI = (int32_t)nI; rp2.k = k; rp2.d = d; rp2.dtype = dtype; rp2.U = Uc; rp2.V = V;
+    rp2.seen_rowptr = rp; rp2.seen_items = seen_items; rp2.item_id_offset = item_id_offset;
+    rp2.fail_rows = sp.fail_rows; rp2.fail_count = fail_count;
+    rp2.scratch = reinterpret_cast<uint32_t*>(ws + w.offRescue); rp2.grid = w.rescue_grid;
+    rp2.out_scores = outs; rp2.out_items = outi;
+    prof_mark(PROF_RESCUE, 0, st);
+    e = launch_rescue(rp2, st);
+    if (e != cudaSuccess) return cuda_fail(e, "rescue launch");
+    prof_mark(PROF_RESCUE, 1, st);
+    e = launch_add_counter(fail_count, reinterpret_cast<int32_t*>(scal) + 6, st);  // statistics: rows re-done exactly
+    if (e != cudaSuccess) return cuda_fail(e, "counter launch");
+  }
   return DIVREC_OK;
 }
 
-int divrec_score_dense(const void* U, const void* V, int64_t nU, int64_t nI, int d, int dtype, int mode, float* out,
-                       void* workspace, size_t ws_bytes, void* stream) {
-  int rc = check_score_args(U, V, nU, nI, d, dtype, mode);
-  if (rc != DIVREC_OK) return rc;
-  if (!out) return fail(DIVREC_ERR_ARG, "score_dense: null output");
+int divrec_score_topk_rescued(const void* workspace, int64_t nU, int64_t nI, int d, int dtype, int32_t* host_out, void* stream) {
+  if (!workspace || !host_out || nU <= 0 || nI <= 0 || d <= 0) return fail(DIVREC_ERR_ARG, "score_topk_rescued: bad argument");
   const WsLayout w = ws_layout(nU, nI, d, dtype);
-  if (!workspace || ws_bytes < w.total) return fail(DIVREC_ERR_WORKSPACE, "score_dense: workspace too small");
-  if (reinterpret_cast<uintptr_t>(workspace) & 1023) return fail(DIVREC_ERR_ARG, "score_dense: workspace must be 1024-byte aligned");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
-  const void *A16, *B16;
-  int fmt;
-  const int32_t* scale_exps;
-  rc = prepare_operands(U, V, nU, nI, d, dtype, w, ws, st, &A16, &B16, &fmt, &scale_exps);
-  if (rc != DIVREC_OK) return rc;
-  FilterParams fp{};
-  fp.nU = nU; fp.nI = (int32_t)nI; fp.kblocks = w.K / 64; fp.fmt = fmt; fp.k = 1;
-  fp.lists = reinterpret_cast<uint2*>(ws + w.offLists);
-  fp.list_count = reinterpret_cast<int32_t*>(ws + w.offCounts);
-  fp.dump = out; fp.scale_exps = scale_exps;
-  const char* err = "";
-  cudaError_t e = launch_score_filter(A16, B16, fp, device_info().sm_count, st, &err);
-  if (e != cudaSuccess) return cuda_fail(e, err[0] ? err : "score_filter launch");
+  cudaError_t e = cudaMemcpyAsync(host_out, reinterpret_cast<const uint8_t*>(workspace) + w.offScalars + 6 * sizeof(int32_t),
+                                  sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return cuda_fail(e, "score_topk_rescued");
   return DIVREC_OK;
 }
 

@@ -7,7 +7,10 @@
 
 namespace divrec {
 
-constexpr int LIST_CAP = 512;  // candidate slots per (user row, column half)
+constexpr int LIST_CAP = 512;        // candidate groups per (user row, column half)
+constexpr int GROUP = 8;             // consecutive item columns appended together
+constexpr int N_SAMPLE = 16;         // item tiles scored first to seed the per-row threshold hint
+constexpr int HINT_MIN_TILES = 32;   // catalogues with fewer 128-item tiles keep every group (no hint)
 constexpr int MAX_K = 128;
 
 void count_launch();
@@ -16,44 +19,78 @@ struct FilterParams {
   int64_t nU;
   int32_t nI;
   int kblocks;  // K / 64
-  int fmt;      // 0 = fp16 planes, 1 = bf16
+  int fmt;      // 0 = fp16 plane, 1 = bf16
   int k;
-  int n_ublocks;
-  int n_tiles;
-  const int64_t* seen_rowptr;  // [nU+1] or null
-  const int32_t* seen_items;   // global item ids, ascending per row
-  int64_t item_id_offset;
-  uint2* lists;                // [nU_pad][2][LIST_CAP]  (score bits, local item id)
-  int32_t* list_count;         // [nU_pad][2]
-  float* dump;                 // dense [nU,nI] output (debug) or null
-  const int32_t* scale_exps;   // device [2]: scores are scaled by 2^(e0+e1); null = unscaled
+  int use_hint;
+  int cap;      // = LIST_CAP
+  // filled by the launcher
+  int n_ublocks, n_tiles, b_stages, n_sample, sample_stride;
+  const int64_t* seen_rowptr;  // [nU+1] or null (only the per-row counts are used here)
+  float* list_scores;          // [nU_pad][2][cap][GROUP]  tensor-core scores (scaled units)
+  uint32_t* list_item0;        // [nU_pad][2][cap]         local id of the first item of each group
+  int32_t* list_count;         // [nU_pad][2]              groups appended; cap + 1 = overflow
+  float* thr_out;              // [nU_pad]                 threshold hint used for the row (scaled units, -inf = none)
 };
 
+int score_filter_b_stages(int kblocks);
 size_t score_filter_smem_bytes(int kblocks);
 cudaError_t launch_score_filter(const void* A16, const void* B16, FilterParams p, int sm_count,
                                 cudaStream_t stream, const char** err);
 
-// fp32 [rows,d] -> fp16 planes [rows, 3*d_pad]; role 0: [hi | hi*2^-11 | lo*2^11], role 1: [hi | lo*2^11 | hi*2^-11]
-// amax_bits / scale_exp are device scalars (amax must be zeroed by the caller before the call).
-cudaError_t launch_split_f32(const float* X, int64_t rows, int d, int d_pad, int role, __half* out,
-                             uint32_t* amax_bits, int32_t* scale_exp, cudaStream_t stream);
-// bf16 [rows,d] -> bf16 [rows,d_pad] zero padded (only when d % 64 != 0)
-cudaError_t launch_pad_bf16(const void* X, int64_t rows, int d, int d_pad, void* out, cudaStream_t stream);
+// fp32 [rows,d] -> one fp16 plane [rows,d_pad] of X * 2^scale_exp (max |x| scaled into [2^13, 2^14)),
+// plus fp32 row norms of X and (optionally) the maximum row norm as float bits.
+// amax_bits must be zeroed by the caller; scale_exp is written.
+cudaError_t launch_prep_f32(const float* X, int64_t rows, int d, int d_pad, __half* out, uint32_t* amax_bits,
+                            int32_t* scale_exp, float* norms, uint32_t* normmax_bits, cudaStream_t stream);
+// bf16 [rows,d]: row norms (+ max); zero-padded copy [rows,d_pad] when out != null
+cudaError_t launch_prep_bf16(const void* X, int64_t rows, int d, int d_pad, void* out, float* norms,
+                             uint32_t* normmax_bits, cudaStream_t stream);
 
 struct SelectParams {
   int64_t nU;
   int32_t nI;
-  int k;
-  const uint2* lists;
+  int k, d, dtype, cap;
+  const void* U;               // original tables (fp32 or bf16) for the exact re-scoring
+  const void* V;
+  const float* list_scores;
+  const uint32_t* list_item0;
   const int32_t* list_count;
+  const float* thr;
   const int64_t* seen_rowptr;
   const int32_t* seen_items;
   int64_t item_id_offset;
-  const int32_t* scale_exps;
-  float* out_scores;    // [nU,k]
-  int64_t* out_items;   // [nU,k]
+  const int32_t* scale_exps;   // device [2] or null: tensor-core scores carry a factor 2^(e0+e1)
+  const float* norms_u;        // [nU]
+  const uint32_t* nvmax_bits;  // device: max item row norm (float bits)
+  const uint32_t* amax_bits;   // device [2]: max |element| of the user / item table (float bits), null for bf16
+  float c_margin;              // delta_u = c_margin * |u| * max|v|
+  float* out_scores;           // [nU,k]
+  int64_t* out_items;          // [nU,k]
+  int32_t* fail_rows;          // [nU] rows the tensor-core path could not certify
+  int32_t* fail_count;         // device counter (zeroed by the caller)
+  int force_fail;              // 1 = send every row to the rescue kernel (DIVREC_MODE_SIMT)
 };
 cudaError_t launch_select_topk(const SelectParams& p, cudaStream_t stream);
+
+struct RescueParams {
+  int64_t nU;
+  int32_t nI;
+  int k, d, dtype;
+  const void* U;
+  const void* V;
+  const int64_t* seen_rowptr;
+  const int32_t* seen_items;
+  int64_t item_id_offset;
+  const int32_t* fail_rows;
+  const int32_t* fail_count;
+  uint32_t* scratch;           // [grid][nI_pad] ordered score keys
+  int grid;
+  float* out_scores;
+  int64_t* out_items;
+};
+size_t rescue_scratch_bytes(int64_t nI, int* grid_out);
+cudaError_t launch_rescue(const RescueParams& p, cudaStream_t stream);
+cudaError_t launch_add_counter(const int32_t* src, int32_t* dst, cudaStream_t stream);
 
 cudaError_t launch_topk_merge(const float* gs, const int64_t* gi, int n_shards, int64_t nU, int k,
                               float* out_scores, int64_t* out_items, cudaStream_t stream);

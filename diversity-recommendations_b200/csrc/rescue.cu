@@ -1,0 +1,189 @@
+// rescue.cu -- exact SIMT scorer + radix-select top-k for single user rows.
+//
+// The safety net of the tensor-core path (and DIVREC_MODE_SIMT as a whole): rows that
+// select_topk.cu could not certify -- threshold hint too high, candidate list overflow (floods of
+// near-ties, e.g. an all-zero user vector or thousands of identical item vectors), more candidates
+// than fit in shared memory -- are re-done here from scratch, in plain fp32, one CTA per row:
+//   1. every item is scored exactly, E = sum_c U[row,c] V[i,c] (the arithmetic of
+//      divrec/models/matrix_factorization.py:26-28), and stored as an ordered integer key;
+//   2. the row's seen items are removed (divrec/datasets/base_datasets.py:143-151);
+//   3. an 8-bit-digit radix select finds the k-th largest key exactly, ties at the k-th key are
+//      resolved towards the lowest item id;
+//   4. the winners are sorted by (E desc, id asc): divrec/train/utils.py:72-76 in canonical tie order.
+// Throughput is irrelevant by design (a handful of rows per call); correctness for ANY input is the point.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace divrec {
+
+namespace {
+
+constexpr int RT = 256;        // threads per CTA
+constexpr int RSORT = 128;     // >= MAX_K
+
+struct RescueSmem {
+  unsigned int hist[256];
+  unsigned int warp_tot[RT / 32];
+  unsigned int prefix, kmask, k_rem, n_win, tie_base;
+  unsigned long long srt[RSORT];
+};
+
+__device__ __forceinline__ float rd(const void* T, int dtype, int64_t idx) {
+  if (dtype == 0) return __ldg(reinterpret_cast<const float*>(T) + idx);
+  return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(T)[idx]);
+}
+
+__global__ void __launch_bounds__(RT)
+rescue_kernel(const RescueParams p) {
+  extern __shared__ __align__(16) float u_s[];  // [d] the user row
+  __shared__ RescueSmem sm;
+  const int tid = threadIdx.x;
+  const uint32_t lane = lane_id();
+  const int warp = tid >> 5;
+  const int n_fail = *p.fail_count;
+  const int d = p.d, k = p.k;
+  const int64_t nI = p.nI;
+  uint32_t* keys = p.scratch + (size_t)blockIdx.x * (size_t)((nI + 31) & ~(int64_t)31);
+
+  for (int f = blockIdx.x; f < n_fail; f += gridDim.x) {
+    const int64_t row = p.fail_rows[f];
+    __syncthreads();
+    for (int c = tid; c < d; c += RT) u_s[c] = rd(p.U, p.dtype, row * d + c);
+    __syncthreads();
+    // 1. exact scores -> ordered keys (0 is reserved for "not recommendable")
+    const bool vec = p.dtype == 0 && (d & 3) == 0;
+    for (int64_t i = tid; i < nI; i += RT) {
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      if (vec) {
+        const float4* v = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.V) + i * d);
+        for (int c = 0; c < (d >> 2); ++c) {
+          const float4 x = __ldg(v + c);
+          const float4 y = *reinterpret_cast<const float4*>(u_s + 4 * c);
+          s0 = fmaf(x.x, y.x, s0); s1 = fmaf(x.y, y.y, s1); s2 = fmaf(x.z, y.z, s2); s3 = fmaf(x.w, y.w, s3);
+        }
+      } else {
+        for (int c = 0; c < d; ++c) s0 = fmaf(rd(p.V, p.dtype, i * d + c), u_s[c], s0);
+      }
+      const float s = (s0 + s1) + (s2 + s3);
+      uint32_t kk = f32_to_key(__float_as_uint(s + 0.0f));
+      if (kk <= KEY_NEG_INF || !(s == s)) kk = 0;
+      keys[i] = kk;
+    }
+    __syncthreads();
+    // 2. seen-item mask
+    if (p.seen_rowptr != nullptr) {
+      const int64_t s0 = p.seen_rowptr[row], s1 = p.seen_rowptr[row + 1];
+      for (int64_t s = s0 + tid; s < s1; s += RT) {
+        const int64_t li = (int64_t)p.seen_items[s] - p.item_id_offset;
+        if (li >= 0 && li < nI) keys[li] = 0;
+      }
+    }
+    __syncthreads();
+    // 3. radix select of the k-th largest non-zero key, most significant digit first
+    if (tid == 0) { sm.prefix = 0; sm.kmask = 0; sm.k_rem = (unsigned)k; }
+    bool have_k = true;
+    for (int pass = 3; pass >= 0; --pass) {
+      sm.hist[tid] = 0;  // RT == 256 bins
+      __syncthreads();
+      const unsigned prefix = sm.prefix, kmask = sm.kmask;
+      for (int64_t i = tid; i < nI; i += RT) {
+        const uint32_t kk = keys[i];
+        if (kk != 0 && (kk & kmask) == prefix) atomicAdd(&sm.hist[(kk >> (8 * pass)) & 255u], 1u);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        unsigned rem = sm.k_rem, acc = 0;
+        int bin = 255;
+        for (; bin >= 0; --bin) {
+          if (acc + sm.hist[bin] >= rem) break;
+          acc += sm.hist[bin];
+        }
+        if (bin < 0) {
+          sm.k_rem = 0xffffffffu;  // fewer than k recommendable items: take them all
+        } else {
+          sm.k_rem = rem - acc;
+          sm.prefix = prefix | ((unsigned)bin << (8 * pass));
+          sm.kmask = kmask | (255u << (8 * pass));
+        }
+      }
+      __syncthreads();
+      if (sm.k_rem == 0xffffffffu) { have_k = false; break; }
+    }
+    const uint32_t T = have_k ? sm.prefix : 1u;             // keep keys > T, and `quota` keys == T (lowest ids)
+    const unsigned quota = have_k ? sm.k_rem : 0xffffffffu;  // no limit when everything is taken
+    // 4. gather winners in id order (ties ranked by a block-wide ordered scan), then sort
+    for (int i = tid; i < RSORT; i += RT) sm.srt[i] = 0ull;
+    if (tid == 0) { sm.n_win = 0; sm.tie_base = 0; }
+    __syncthreads();
+    for (int64_t base = 0; base < nI; base += RT) {
+      const int64_t i = base + tid;
+      const uint32_t kk = i < nI ? keys[i] : 0;
+      const bool gt = kk != 0 && (have_k ? kk > T : true);
+      const bool eq = have_k && kk == T;
+      const uint32_t eb = __ballot_sync(0xffffffffu, eq);
+      if (lane == 0) sm.warp_tot[warp] = __popc(eb);
+      __syncthreads();
+      unsigned before = sm.tie_base;
+      for (int w2 = 0; w2 < warp; ++w2) before += sm.warp_tot[w2];
+      const unsigned my_rank = before + __popc(eb & lanemask_lt());
+      const bool keep = gt || (eq && my_rank < quota);
+      if (keep) {
+        const unsigned slot = atomicAdd(&sm.n_win, 1u);
+        if (slot < RSORT) sm.srt[slot] = ((unsigned long long)kk << 32) | (unsigned long long)(~(uint32_t)i);
+      }
+      __syncthreads();
+      if (tid == 0) { unsigned t = 0; for (int w2 = 0; w2 < RT / 32; ++w2) t += sm.warp_tot[w2]; sm.tie_base += t; }
+      __syncthreads();
+    }
+    // bitonic sort (descending) of RSORT composites by the whole block
+    for (int size = 2; size <= RSORT; size <<= 1) {
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        if (tid < RSORT / 2) {
+          const int a = ((tid & ~(stride - 1)) << 1) | (tid & (stride - 1));
+          const int b = a | stride;
+          const bool desc = (a & size) == 0;
+          const unsigned long long x = sm.srt[a], y = sm.srt[b];
+          if (desc ? (x < y) : (x > y)) { sm.srt[a] = y; sm.srt[b] = x; }
+        }
+        __syncthreads();
+      }
+    }
+    for (int r = tid; r < k; r += RT) {
+      const unsigned long long c = sm.srt[r];
+      const uint32_t kk = (uint32_t)(c >> 32);
+      float sc = -INFINITY;
+      int64_t it = -1;
+      if (kk != 0) { sc = __uint_as_float(key_to_f32(kk)); it = (int64_t)(~(uint32_t)c) + p.item_id_offset; }
+      p.out_scores[row * k + r] = sc;
+      p.out_items[row * k + r] = it;
+    }
+  }
+}
+
+__global__ void add_counter_kernel(const int32_t* __restrict__ src, int32_t* __restrict__ dst) { *dst += *src; }
+
+}  // namespace
+
+cudaError_t launch_add_counter(const int32_t* src, int32_t* dst, cudaStream_t stream) {
+  add_counter_kernel<<<1, 1, 0, stream>>>(src, dst);
+  count_launch();
+  return cudaGetLastError();
+}
+
+size_t rescue_scratch_bytes(int64_t nI, int* grid_out) {
+  const size_t per = (size_t)((nI + 31) & ~(int64_t)31) * sizeof(uint32_t);
+  int64_t g = (int64_t)((size_t)256 << 20) / (int64_t)per;  // at most 256 MB of scratch
+  if (g > 296) g = 296;
+  if (g < 4) g = 4;
+  if (grid_out) *grid_out = (int)g;
+  return per * (size_t)g;
+}
+
+cudaError_t launch_rescue(const RescueParams& p, cudaStream_t stream) {
+  const size_t smem = (size_t)p.d * sizeof(float);
+  rescue_kernel<<<p.grid, RT, smem, stream>>>(p);
+  count_launch();
+  return cudaGetLastError();
+}
+
+}  // namespace divrec

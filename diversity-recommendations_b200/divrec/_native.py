@@ -17,7 +17,7 @@ _PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB_PATH = os.path.join(_PKG_DIR, "libdivrec_b200.so")
 
 DIVREC_F32, DIVREC_BF16 = 0, 1
-MODE_FP32_PARITY, MODE_BF16 = 0, 1
+MODE_TENSOR, MODE_SIMT = 0, 2
 ILD_SUMVEC, ILD_PAIRWISE = 0, 1
 MAX_K = 128
 
@@ -33,7 +33,7 @@ SIGNATURES = {
     "divrec_profile_read": (_i32, [_c.POINTER(_c.c_float), _i32]),
     "divrec_score_topk_workspace": (_sz, [_i64, _i64, _i32, _i32, _i32]),
     "divrec_score_topk": (_i32, [_vp, _vp, _i64, _i64, _i32, _i32, _i32, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _sz, _vp]),
-    "divrec_score_dense": (_i32, [_vp, _vp, _i64, _i64, _i32, _i32, _i32, _vp, _vp, _sz, _vp]),
+    "divrec_score_topk_rescued": (_i32, [_vp, _i64, _i64, _i32, _i32, _c.POINTER(_c.c_int32), _vp]),
     "divrec_topk_merge": (_i32, [_vp, _vp, _i32, _i64, _i32, _vp, _vp, _vp]),
     "divrec_ild_cosine": (_i32, [_vp, _i64, _i32, _i32, _vp, _i64, _i32, _i32, _vp, _vp, _vp]),
     "divrec_ild_matrix": (_i32, [_vp, _i32, _i64, _vp, _i64, _i32, _vp, _vp]),
@@ -120,7 +120,7 @@ def set_profiling(on: bool) -> None:
     load_library().divrec_set_profiling(1 if on else 0)
 
 
-PROFILE_SLOTS = ("prep_ms", "score_filter_ms", "select_ms", "ild_ms", "coverage_ms")
+PROFILE_SLOTS = ("prep_ms", "score_filter_ms", "select_ms", "ild_ms", "coverage_ms", "rescue_ms")
 
 
 def profile_read() -> dict:
@@ -147,8 +147,10 @@ def _workspace(nbytes: int, dev) -> torch.Tensor:
 
 
 def score_topk(U: torch.Tensor, V: torch.Tensor, k: int, seen_rowptr: Optional[torch.Tensor] = None,
-               seen_items: Optional[torch.Tensor] = None, item_id_offset: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
-    """(scores [nU,k] fp32, items [nU,k] int64): the k best unmasked items per user, (score desc, id asc)."""
+               seen_items: Optional[torch.Tensor] = None, item_id_offset: int = 0, mode: int = MODE_TENSOR,
+               return_stats: bool = False):
+    """(scores [nU,k] fp32, items [nU,k] int64): the k best unmasked items per user, (score desc, id asc).
+    With return_stats=True a third value {"rescued_rows": n} is returned (synchronises the stream)."""
     lib = load_library()
     U = _cuda(U, "U")
     V = _cuda(V, "V", U.dtype)
@@ -170,28 +172,14 @@ def score_topk(U: torch.Tensor, V: torch.Tensor, k: int, seen_rowptr: Optional[t
         ws = _workspace(ws_bytes, U.device)
         out_s = torch.empty((nU, k), dtype=torch.float32, device=U.device)
         out_i = torch.empty((nU, k), dtype=torch.int64, device=U.device)
-        mode = MODE_FP32_PARITY if dt == DIVREC_F32 else MODE_BF16
         rc = lib.divrec_score_topk(_ptr(U), _ptr(V), nU, nI, d, dt, mode, _ptr(seen_rowptr), _ptr(seen_items),
                                    item_id_offset, k, _ptr(out_s), _ptr(out_i), _ptr(ws), ws_bytes, _stream(U.device))
-    _check(rc, "divrec_score_topk")
+        _check(rc, "divrec_score_topk")
+        if return_stats:
+            n = _c.c_int32(0)
+            _check(lib.divrec_score_topk_rescued(_ptr(ws), nU, nI, d, dt, _c.byref(n), _stream(U.device)), "divrec_score_topk_rescued")
+            return out_s, out_i, {"rescued_rows": int(n.value)}
     return out_s, out_i
-
-
-def score_dense(U: torch.Tensor, V: torch.Tensor) -> torch.Tensor:
-    lib = load_library()
-    U = _cuda(U, "U")
-    V = _cuda(V, "V", U.dtype)
-    dt = _table_dtype(U)
-    nU, d = U.shape
-    nI = V.shape[0]
-    with torch.cuda.device(U.device):
-        ws_bytes = lib.divrec_score_topk_workspace(nU, nI, d, dt, 1)
-        ws = _workspace(ws_bytes, U.device)
-        out = torch.empty((nU, nI), dtype=torch.float32, device=U.device)
-        mode = MODE_FP32_PARITY if dt == DIVREC_F32 else MODE_BF16
-        rc = lib.divrec_score_dense(_ptr(U), _ptr(V), nU, nI, d, dt, mode, _ptr(out), _ptr(ws), ws_bytes, _stream(U.device))
-    _check(rc, "divrec_score_dense")
-    return out
 
 
 def topk_merge(gathered_scores: torch.Tensor, gathered_items: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:

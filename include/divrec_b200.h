@@ -42,11 +42,14 @@ typedef enum divrec_dtype {
 } divrec_dtype;
 
 typedef enum divrec_score_mode {
-  /* fp32 tables are split into three fp16 planes (hi, hi*2^-11, lo*2^11) so that one fp16
-   * tensor-core pass over K = 3*d reproduces the fp32 dot product to ~3*2^-22 relative. */
-  DIVREC_MODE_FP32_PARITY = 0,
-  /* single pass over the table as stored (bf16 tables), fp32 accumulation */
-  DIVREC_MODE_BF16 = 1
+  /* tensor-core filter + exact fp32 re-scoring: the tables are rounded to ONE 16-bit plane (fp16 with a
+   * power-of-two scale for fp32 tables; bf16 tables as stored), S = U V^T runs on tcgen05 with fp32
+   * accumulation and is used only to FILTER; every candidate within 2*delta of the k-th best filter
+   * score is re-scored exactly in fp32 from the original tables, so the reported top-k and scores are
+   * those of the exact dot products.  Rows the filter cannot certify are re-done by the SIMT kernel. */
+  DIVREC_MODE_TENSOR = 0,
+  /* exact fp32 SIMT scoring + radix select for every row (no tensor cores; any d <= 8192) */
+  DIVREC_MODE_SIMT = 2
 } divrec_score_mode;
 
 typedef enum divrec_ild_mode {
@@ -62,7 +65,7 @@ int64_t divrec_launch_count(void);
 /* Measurement aid (bench.py roofline): when on, the library records CUDA events on the launching
  * stream around its phases; divrec_profile_read waits for them and fills ms_out (host, [n]) with
  * the last durations in ms, -1 where nothing was recorded.  Slots: 0 operand preparation,
- * 1 score+filter kernel, 2 select kernel, 3 ILD, 4 coverage histogram.  Host-only calls. */
+ * 1 score+filter kernel, 2 select kernel, 3 ILD, 4 coverage histogram, 5 rescue kernel.  Host-only calls. */
 void divrec_set_profiling(int on);
 int divrec_profile_read(float* ms_out /*host*/, int n);
 
@@ -78,7 +81,10 @@ int divrec_profile_read(float* ms_out /*host*/, int n);
  *   reported (global) item ids and subtracted from seen_items (item-sharded catalogue).
  *   Output row u = the k best unmasked items by (score desc, item id asc); rows with fewer
  *   than k unmasked items are padded with score -inf / item -1.
- *   Limits of this version: k <= 128; d <= 128 (f32) or d <= 384 (bf16); nI < 2^31.
+ *   Limits of this version: k <= 128; d <= 512 in DIVREC_MODE_TENSOR; nI < 2^31; tables 16-byte aligned;
+ *   finite inputs.  Users are processed in internal passes of <= 151 552 rows, which bounds the workspace.
+ *   divrec_score_topk_rescued: (host call, synchronises `stream`) how many rows of the last call on this
+ *   workspace were re-done by the exact SIMT kernel.
  * ------------------------------------------------------------------------------------- */
 size_t divrec_score_topk_workspace(int64_t nU, int64_t nI, int d, int dtype, int k);
 
@@ -88,11 +94,8 @@ int divrec_score_topk(const void* U, const void* V, int64_t nU, int64_t nI, int 
                       int64_t* out_items /*[nU,k]*/, void* workspace, size_t ws_bytes,
                       void* stream);
 
-/* Debug/validation aid: the raw tensor-core score matrix S = U V^T (no mask, no top-k),
- * written densely to out [nU,nI] fp32 by the same kernel that feeds the top-k filter. */
-int divrec_score_dense(const void* U, const void* V, int64_t nU, int64_t nI, int d, int dtype,
-                       int mode, float* out /*[nU,nI]*/, void* workspace, size_t ws_bytes,
-                       void* stream);
+int divrec_score_topk_rescued(const void* workspace, int64_t nU, int64_t nI, int d, int dtype,
+                                int32_t* host_out /*host*/, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * merge per-shard top-k lists after the all-gather (item-sharded catalogue)

@@ -126,6 +126,62 @@ def test_all_scores_equal_ties_broken_by_lowest_id(native, dev):
     assert torch.equal(i.cpu(), expect) and (s.cpu() == 64.0).all()
 
 
+@pytest.mark.parametrize("kind", ["grid", "gauss"])
+def test_simt_mode_equals_oracle(native, dev, kind):
+    """DIVREC_MODE_SIMT: every row through the exact SIMT scorer + radix select (the rescue kernel)."""
+    gen = torch.Generator().manual_seed(41)
+    nU, nI, d, k = 77, 3001, 72, 33
+    U, V = O.make_embeddings(nU, d, kind, gen), O.make_embeddings(nI, d, kind, gen)
+    seen = O.make_seen(nU, nI, 5000, gen)
+    rowptr, items = O.seen_csr(seen, nU)
+    o_i, o_s = O.recommendations_dense(U, V, rowptr, items, k)
+    s, i, st = native.score_topk(U.to(dev), V.to(dev), k, rowptr.to(dev), items.to(dev), mode=native.MODE_SIMT, return_stats=True)
+    assert st["rescued_rows"] == nU
+    check_topk_against_oracle(i, s, o_i, o_s, U, V, kind == "grid")
+
+
+def test_degenerate_rows_are_rescued_exactly(native, dev):
+    """Zero user vectors (every score ties at 0), duplicated item vectors and users that have seen almost
+    everything: the tensor-core filter cannot certify these rows, the exact kernel must take over."""
+    gen = torch.Generator().manual_seed(43)
+    nU, nI, d, k = 200, 9000, 64, 50
+    U, V = O.make_embeddings(nU, d, "gauss", gen), O.make_embeddings(nI, d, "gauss", gen)
+    U[::7] = 0.0                       # untrained users
+    V[1000:6000] = V[999]              # 5000 identical (cold-start) items
+    pairs = [O.make_seen(nU, nI, 20000, gen)]
+    heavy = torch.arange(3, nU, 50)
+    for u in heavy.tolist():           # users who have seen all but 30 items
+        keep = torch.randperm(nI, generator=gen)[: nI - 30]
+        pairs.append(torch.stack([torch.full_like(keep, u), keep], 1))
+    seen = torch.cat(pairs)
+    rowptr, items = O.seen_csr(seen, nU)
+    o_i, o_s = O.recommendations_dense(U, V, rowptr, items, k)
+    s, i, st = native.score_topk(U.to(dev), V.to(dev), k, rowptr.to(dev), items.to(dev), return_stats=True)
+    assert st["rescued_rows"] >= 29    # at least the zero rows
+    check_topk_against_oracle(i, s, o_i, o_s, U, V, False)
+    z = torch.arange(0, nU, 7)
+    assert (s.cpu()[z][torch.isfinite(o_s[z])] == 0).all() and torch.equal(i.cpu()[z], o_i[z])
+
+
+def test_hint_path_rarely_needs_the_rescue_kernel(native, dev):
+    gen = torch.Generator().manual_seed(47)
+    nU, nI, d, k = 4096, 26744, 128, 100
+    U, V = O.make_embeddings(nU, d, "gauss", gen), O.make_embeddings(nI, d, "gauss", gen)
+    seen = O.make_seen(nU, nI, 600000, gen)
+    rowptr, items = O.seen_csr(seen, nU)
+    s, i, st = native.score_topk(U.to(dev), V.to(dev), k, rowptr.to(dev), items.to(dev), return_stats=True)
+    assert st["rescued_rows"] <= nU // 50
+    sample = torch.arange(0, nU, 16)
+    sub_rp = torch.zeros(sample.numel() + 1, dtype=torch.int64)
+    segs = []
+    for n_, u in enumerate(sample.tolist()):
+        seg = items[rowptr[u]:rowptr[u + 1]]
+        segs.append(seg)
+        sub_rp[n_ + 1] = sub_rp[n_] + seg.numel()
+    o_i, o_s = O.recommendations_dense(U[sample], V, sub_rp, torch.cat(segs), k)
+    check_topk_against_oracle(i[sample.to(dev)], s[sample.to(dev)], o_i, o_s, U, V, False)
+
+
 def test_bf16_tables(native, dev):
     gen = torch.Generator().manual_seed(17)
     U = O.make_embeddings(200, 256, "gauss", gen).bfloat16()
