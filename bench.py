@@ -104,11 +104,10 @@ class ClockSampler:
 
 
 def run_step_device(N, model_U, V, rowptr, items, k, nI, counts):
-    """One pass with everything resident: fused score+mask+top-k, ILD, coverage histogram."""
-    s, i = N.score_topk(model_U, V, k, rowptr, items)
-    ild = N.ild_cosine(V, i, N.ILD_SUMVEC)
+    """One pass with everything resident: score + mask + top-k with the cosine ILD and the coverage
+    histogram fused into the selection kernel (divrec_score_topk_metrics)."""
     counts.zero_()
-    N.coverage_hist(i, nI, counts)
+    s, i, ild, _ = N.score_topk_metrics(model_U, V, k, rowptr, items, counts=counts)
     return s, i, ild
 
 

@@ -140,11 +140,16 @@ size_t divrec_score_topk_workspace(int64_t nU, int64_t nI, int d, int dtype, int
   return ws_layout(nU, nI, d, dtype).total;
 }
 
-int divrec_score_topk(const void* U, const void* V, int64_t nU, int64_t nI, int d, int dtype, int mode,
-                      const int64_t* seen_rowptr, const int32_t* seen_items, int64_t item_id_offset, int k,
-                      float* out_scores, int64_t* out_items, void* workspace, size_t ws_bytes, void* stream) {
+static int score_topk_impl(const void* U, const void* V, int64_t nU, int64_t nI, int d, int dtype, int mode,
+                           const int64_t* seen_rowptr, const int32_t* seen_items, int64_t item_id_offset, int k,
+                           float* out_scores, int64_t* out_items, float* out_ild, int32_t* coverage, void* workspace,
+                           size_t ws_bytes, void* stream) {
   int rc = check_score_args(U, V, nU, nI, d, dtype, mode);
   if (rc != DIVREC_OK) return rc;
+  if (out_ild != nullptr && ((d & 3) != 0 || d > 256 || k < 2))
+    return fail(DIVREC_ERR_ARG, "score_topk_metrics: the fused ILD needs d % 4 == 0, d <= 256 and k >= 2");
+  if ((out_ild != nullptr || coverage != nullptr) && item_id_offset != 0)
+    return fail(DIVREC_ERR_ARG, "score_topk_metrics: fused metrics need the whole catalogue (item_id_offset == 0)");
   if (k <= 0 || k > MAX_K) return fail(DIVREC_ERR_ARG, "score_topk: k must be in [1,128]");
   if (!out_scores || !out_items) return fail(DIVREC_ERR_ARG, "score_topk: null output");
   if (seen_rowptr == nullptr && seen_items != nullptr)
@@ -201,6 +206,7 @@ int divrec_score_topk(const void* U, const void* V, int64_t nU, int64_t nI, int 
     sp.out_scores = outs; sp.out_items = outi;
     sp.fail_rows = reinterpret_cast<int32_t*>(ws + w.offFail); sp.fail_count = fail_count;
     sp.force_fail = tensor ? 0 : 1;
+    sp.out_ild = out_ild ? out_ild + u0 : nullptr; sp.coverage = coverage;
 
     if (u0 > 0) {
       e = cudaMemsetAsync(fail_count, 0, sizeof(int32_t), st);
@@ -253,7 +259,7 @@ int divrec_score_topk(const void* U, const void* V, int64_t nU, int64_t nI, int 
     rp2.seen_rowptr = rp; rp2.seen_items = seen_items; rp2.item_id_offset = item_id_offset;
     rp2.fail_rows = sp.fail_rows; rp2.fail_count = fail_count;
     rp2.scratch = reinterpret_cast<uint32_t*>(ws + w.offRescue); rp2.grid = w.rescue_grid;
-    rp2.out_scores = outs; rp2.out_items = outi;
+    rp2.out_scores = outs; rp2.out_items = outi; rp2.out_ild = sp.out_ild; rp2.coverage = coverage;
     prof_mark(PROF_RESCUE, 0, st);
     e = launch_rescue(rp2, st);
     if (e != cudaSuccess) return cuda_fail(e, "rescue launch");
@@ -262,6 +268,21 @@ int divrec_score_topk(const void* U, const void* V, int64_t nU, int64_t nI, int 
     if (e != cudaSuccess) return cuda_fail(e, "counter launch");
   }
   return DIVREC_OK;
+}
+
+int divrec_score_topk(const void* U, const void* V, int64_t nU, int64_t nI, int d, int dtype, int mode,
+                      const int64_t* seen_rowptr, const int32_t* seen_items, int64_t item_id_offset, int k,
+                      float* out_scores, int64_t* out_items, void* workspace, size_t ws_bytes, void* stream) {
+  return score_topk_impl(U, V, nU, nI, d, dtype, mode, seen_rowptr, seen_items, item_id_offset, k, out_scores, out_items,
+                         nullptr, nullptr, workspace, ws_bytes, stream);
+}
+
+int divrec_score_topk_metrics(const void* U, const void* V, int64_t nU, int64_t nI, int d, int dtype, int mode,
+                              const int64_t* seen_rowptr, const int32_t* seen_items, int k, float* out_scores,
+                              int64_t* out_items, float* out_ild, int32_t* coverage_counts, void* workspace,
+                              size_t ws_bytes, void* stream) {
+  return score_topk_impl(U, V, nU, nI, d, dtype, mode, seen_rowptr, seen_items, 0, k, out_scores, out_items, out_ild,
+                         coverage_counts, workspace, ws_bytes, stream);
 }
 
 int divrec_score_topk_rescued(const void* workspace, int64_t nU, int64_t nI, int d, int dtype, int32_t* host_out, void* stream) {

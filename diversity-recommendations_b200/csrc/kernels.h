@@ -69,6 +69,8 @@ struct SelectParams {
   int32_t* fail_rows;          // [nU] rows the tensor-core path could not certify
   int32_t* fail_count;         // device counter (zeroed by the caller)
   int force_fail;              // 1 = send every row to the rescue kernel (DIVREC_MODE_SIMT)
+  float* out_ild;              // [nU] fused cosine ILD of the row's top-k (null = off; needs d % 4 == 0, d <= 512)
+  int32_t* coverage;           // [>= nI + offset] fused coverage histogram over global item ids (null = off)
 };
 cudaError_t launch_select_topk(const SelectParams& p, cudaStream_t stream);
 
@@ -87,6 +89,8 @@ struct RescueParams {
   int grid;
   float* out_scores;
   int64_t* out_items;
+  float* out_ild;              // fused metrics for the rows re-done here (null = off)
+  int32_t* coverage;
 };
 size_t rescue_scratch_bytes(int64_t nI, int* grid_out);
 cudaError_t launch_rescue(const RescueParams& p, cudaStream_t stream);

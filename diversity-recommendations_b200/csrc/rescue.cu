@@ -26,6 +26,8 @@ struct RescueSmem {
   unsigned int warp_tot[RT / 32];
   unsigned int prefix, kmask, k_rem, n_win, tie_base;
   unsigned long long srt[RSORT];
+  float inv[RSORT];
+  float red[RT / 32];
 };
 
 __device__ __forceinline__ float rd(const void* T, int dtype, int64_t idx) {
@@ -156,6 +158,34 @@ rescue_kernel(const RescueParams p) {
       if (kk != 0) { sc = __uint_as_float(key_to_f32(kk)); it = (int64_t)(~(uint32_t)c) + p.item_id_offset; }
       p.out_scores[row * k + r] = sc;
       p.out_items[row * k + r] = it;
+      if (kk != 0 && p.coverage != nullptr) atomicAdd(p.coverage + it, 1);
+    }
+    if (p.out_ild != nullptr) {
+      // cosine ILD of the winners: sum_{a<b} cos = (|sum e|^2 - kv) / 2  (same formula as metrics.cu / select_topk.cu)
+      const int n_win = min((int)sm.n_win, k);
+      for (int wdx = warp; wdx < n_win; wdx += RT / 32) {
+        const int64_t it = (int64_t)(~(uint32_t)sm.srt[wdx]);
+        float q = 0.f;
+        for (int c = lane; c < d; c += 32) { const float v = rd(p.V, p.dtype, it * d + c); q = fmaf(v, v, q); }
+        q = warp_sum(q);
+        if (lane == 0) sm.inv[wdx] = 1.0f / sqrtf(q);
+      }
+      __syncthreads();
+      float part = 0.f;
+      for (int c = tid; c < d; c += RT) {
+        float sc = 0.f;
+        for (int wdx = 0; wdx < n_win; ++wdx) sc = fmaf(rd(p.V, p.dtype, (int64_t)(~(uint32_t)sm.srt[wdx]) * d + c), sm.inv[wdx], sc);
+        part = fmaf(sc, sc, part);
+      }
+      part = warp_sum(part);
+      if (lane == 0) sm.red[warp] = part;
+      __syncthreads();
+      if (tid == 0) {
+        float ssum = 0.f;
+        for (int w2 = 0; w2 < RT / 32; ++w2) ssum += sm.red[w2];
+        const float kvf = (float)n_win;
+        p.out_ild[row] = (0.5f * kvf * (kvf - 1.0f) - 0.5f * (ssum - kvf)) / ((float)k * (float)(k - 1));
+      }
     }
   }
 }

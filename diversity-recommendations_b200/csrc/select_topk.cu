@@ -25,15 +25,16 @@ namespace {
 
 constexpr int SEL_WARPS = 4;
 constexpr int SEL_CAP = 1024;             // candidate elements per row held in shared memory
-constexpr int SEL_SLOTS = SEL_CAP / 32;
+constexpr int SEEN_CAP = 512;             // seen items of the row staged in shared memory (longer lists stay in global)
 constexpr int SORT_N = 128;               // >= MAX_K, power of two
-constexpr int MAX_UCH = 8;                // user row kept in registers: d <= 128 * MAX_UCH
+constexpr int LOAD_B = 4;                 // candidate groups fetched per lane per batch (memory-level parallelism)
 
 struct SelSmem {
   uint32_t key[SEL_WARPS][SEL_CAP];
   uint32_t id[SEL_WARPS][SEL_CAP];
-  uint32_t tie_id[SEL_WARPS][SEL_CAP];
-  unsigned long long srt[SEL_WARPS][SORT_N];
+  int32_t seen[SEL_WARPS][SEEN_CAP];
+  unsigned long long top[SEL_WARPS][SORT_N];   // running top list, sorted descending
+  unsigned long long chunk[SEL_WARPS][SORT_N];
 };
 
 // descending bitonic sort of 128 64-bit keys held in shared memory by one warp
@@ -56,6 +57,21 @@ __device__ __forceinline__ void warp_bitonic_desc_128(unsigned long long* a, uin
     }
   }
 }
+// `a` is bitonic (first descending then ascending, or any rotation): make it descending
+__device__ __forceinline__ void warp_bitonic_merge_desc_128(unsigned long long* a, uint32_t lane) {
+#pragma unroll 1
+  for (int stride = SORT_N >> 1; stride > 0; stride >>= 1) {
+#pragma unroll
+    for (int r = 0; r < SORT_N / 64; ++r) {
+      const int t = r * 32 + lane;
+      const int i = ((t & ~(stride - 1)) << 1) | (t & (stride - 1));
+      const int j = i | stride;
+      const unsigned long long x = a[i], y = a[j];
+      if (x < y) { a[i] = y; a[j] = x; }
+    }
+    __syncwarp();
+  }
+}
 
 __device__ __forceinline__ float4 ld4(const void* T, int dtype, int64_t row, int d, int c4) {
   if (dtype == 0) {
@@ -70,6 +86,16 @@ __device__ __forceinline__ float ld1(const void* T, int dtype, int64_t row, int 
   if (dtype == 0) return __ldg(reinterpret_cast<const float*>(T) + row * d + c);
   return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(T)[row * d + c]);
 }
+__device__ __forceinline__ float dot4(const float4& a, const float4& b, float s) {
+  s = fmaf(a.x, b.x, s); s = fmaf(a.y, b.y, s); s = fmaf(a.z, b.z, s); return fmaf(a.w, b.w, s);
+}
+// sum over the 8 lanes of a sub-group (lanes that share lane >> 3)
+__device__ __forceinline__ float sum8(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  return v;
+}
 
 struct GroupRef { const float* s; uint32_t item0; };
 __device__ __forceinline__ GroupRef group_at(const SelectParams& p, int64_t row, int n0, int g) {
@@ -79,60 +105,69 @@ __device__ __forceinline__ GroupRef group_at(const SelectParams& p, int64_t row,
   return GroupRef{p.list_scores + base * GROUP, p.list_item0[base]};
 }
 
-// number of captured elements of the row with ordered key >= kmin (and a real item id)
-__device__ __forceinline__ int count_ge(const SelectParams& p, int64_t row, int n0, int ng, uint32_t kmin, uint32_t lane) {
-  int c = 0;
-  for (int g = lane; g < ng; g += 32) {
-    const GroupRef gr = group_at(p, row, n0, g);
-    const float4 a = *reinterpret_cast<const float4*>(gr.s), b = *reinterpret_cast<const float4*>(gr.s + 4);
-    const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      c += (f32_to_key(__float_as_uint(v[j] + 0.0f)) >= kmin && gr.item0 + j < (uint32_t)p.nI) ? 1 : 0;
-  }
-  return __reduce_add_sync(0xffffffffu, c);
-}
-
-// enumerate elements with key >= kmin into shared memory (at most SEL_CAP are stored); returns the total
-__device__ __forceinline__ int enumerate_ge(const SelectParams& p, int64_t row, int n0, int ng, uint32_t kmin,
-                                            uint32_t* key, uint32_t* id, uint32_t lane) {
-  const uint32_t lt = lanemask_lt();
+// One pass over the row's captured groups, LOAD_B groups per lane in flight.
+//   STORE: elements with ordered key >= kmin are written to key[] / id[] (at most SEL_CAP), any order;
+//   returns how many there are in total.
+template <bool STORE>
+__device__ __forceinline__ int scan_groups(const SelectParams& p, int64_t row, int n0, int ng, uint32_t kmin,
+                                           uint32_t* key, uint32_t* id, uint32_t lane) {
   int total = 0;
-  for (int g0 = 0; g0 < ng; g0 += 32) {
-    const int g = g0 + lane;
-    uint32_t kk[8];
-    uint32_t item0 = 0;
-    uint32_t m = 0;
-    if (g < ng) {
-      const GroupRef gr = group_at(p, row, n0, g);
-      item0 = gr.item0;
-      const float4 a = *reinterpret_cast<const float4*>(gr.s), b = *reinterpret_cast<const float4*>(gr.s + 4);
-      const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  for (int g0 = 0; g0 < ng; g0 += 32 * LOAD_B) {
+    float4 a[LOAD_B], b[LOAD_B];
+    uint32_t item0[LOAD_B];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        kk[j] = f32_to_key(__float_as_uint(v[j] + 0.0f));
-        if (kk[j] >= kmin && kk[j] > KEY_NEG_INF && item0 + j < (uint32_t)p.nI) m |= 1u << j;
+    for (int j = 0; j < LOAD_B; ++j) {
+      const int g = g0 + j * 32 + lane;
+      item0[j] = 0xffffffffu;
+      if (g < ng) {
+        const GroupRef gr = group_at(p, row, n0, g);
+        item0[j] = gr.item0;
+        a[j] = *reinterpret_cast<const float4*>(gr.s);
+        b[j] = *reinterpret_cast<const float4*>(gr.s + 4);
       }
     }
-    // exclusive prefix sum of popc(m) over the warp
-    const int mine = __popc(m);
-    int incl = mine;
+    uint32_t m[LOAD_B];
+    int mine = 0;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, incl, o);
-      if ((int)lane >= o) incl += t;
+    for (int j = 0; j < LOAD_B; ++j) {
+      m[j] = 0;
+      if (item0[j] != 0xffffffffu) {
+        const float v[8] = {a[j].x, a[j].y, a[j].z, a[j].w, b[j].x, b[j].y, b[j].z, b[j].w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const uint32_t kk = f32_to_key(__float_as_uint(v[e] + 0.0f));
+          if (kk >= kmin && kk > KEY_NEG_INF && item0[j] + e < (uint32_t)p.nI) m[j] |= 1u << e;
+        }
+      }
+      mine += __popc(m[j]);
     }
-    int pos = total + incl - mine;
-    total += __shfl_sync(0xffffffffu, incl, 31);
+    if (!STORE) {
+      total += mine;
+    } else {
+      int incl = mine;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      if (m & (1u << j)) {
-        if (pos < SEL_CAP) { key[pos] = kk[j]; id[pos] = item0 + j; }
-        ++pos;
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((int)lane >= o) incl += t;
+      }
+      int pos = total + incl - mine;
+      total += __shfl_sync(0xffffffffu, incl, 31);
+#pragma unroll
+      for (int j = 0; j < LOAD_B; ++j) {
+        if (m[j]) {
+          const float v[8] = {a[j].x, a[j].y, a[j].z, a[j].w, b[j].x, b[j].y, b[j].z, b[j].w};
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            if (m[j] & (1u << e)) {
+              if (pos < SEL_CAP) { key[pos] = f32_to_key(__float_as_uint(v[e] + 0.0f)); id[pos] = item0[j] + e; }
+              ++pos;
+            }
+          }
+        }
       }
     }
-    (void)lt;
   }
+  if (!STORE) total = __reduce_add_sync(0xffffffffu, total);
   __syncwarp();
   return total;
 }
@@ -144,6 +179,9 @@ __device__ __forceinline__ void report_fail(const SelectParams& p, int64_t row, 
   }
 }
 
+// NJ = float4 chunks of a table row per lane of an 8-lane sub-group: vector path for d <= 32 * NJ, d % 4 == 0.
+// NJ == 0: scalar path for any d (no fused metrics).
+template <int NJ>
 __global__ void __launch_bounds__(SEL_WARPS * 32)
 select_topk_kernel(const SelectParams p) {
   extern __shared__ __align__(16) uint8_t sel_smem_raw[];
@@ -155,8 +193,9 @@ select_topk_kernel(const SelectParams p) {
   if (row >= p.nU) return;
   uint32_t* key = sm->key[w];
   uint32_t* id = sm->id[w];
-  unsigned long long* srt = sm->srt[w];
-  uint32_t* tie_id = sm->tie_id[w];
+  int32_t* seen_s = sm->seen[w];
+  unsigned long long* top = sm->top[w];
+  unsigned long long* chunk = sm->chunk[w];
   const int k = p.k;
 
   const int n0 = p.list_count[row * 2 + 0];
@@ -167,10 +206,13 @@ select_topk_kernel(const SelectParams p) {
   int64_t s0 = 0, s1 = 0;
   if (p.seen_rowptr != nullptr) { s0 = p.seen_rowptr[row]; s1 = p.seen_rowptr[row + 1]; }
   const int64_t seen_u = s1 - s0;
+  const bool seen_in_smem = seen_u <= SEEN_CAP;
+  if (seen_in_smem)
+    for (int i = lane; i < (int)seen_u; i += 32) seen_s[i] = __ldg(p.seen_items + s0 + i);
 
   // 2 delta in the (scaled) units of the tensor-core scores
-  int e = 0;
-  if (p.scale_exps != nullptr) e = p.scale_exps[0] + p.scale_exps[1];
+  int e2 = 0;
+  if (p.scale_exps != nullptr) e2 = p.scale_exps[0] + p.scale_exps[1];
   const float nu = p.norms_u[row], nvmax = __uint_as_float(*p.nvmax_bits);
   float delta = p.c_margin * nu * nvmax;
   if (p.amax_bits != nullptr) {
@@ -179,13 +221,13 @@ select_topk_kernel(const SelectParams p) {
     const float au = __uint_as_float(p.amax_bits[0]), av = __uint_as_float(p.amax_bits[1]);
     delta += 3.64e-12f * sqrtf((float)p.d) * (nu * av + nvmax * au);
   }
-  const float margin2 = ldexpf(2.0f * delta, e) * 1.0001f;
+  const float margin2 = ldexpf(2.0f * delta, e2) * 1.0001f;
 
   const float thr = p.thr[row];
   uint32_t thr_key = (thr == -INFINITY) ? 0u : f32_to_key(__float_as_uint(thr + 0.0f));  // effective capture threshold
 
   // ---- A: enumerate ----
-  int ne = enumerate_ge(p, row, n0, ng, thr_key, key, id, lane);
+  int ne = scan_groups<true>(p, row, n0, ng, thr_key, key, id, lane);
   if (ne > SEL_CAP) {
     // coarse cut: X = the need-th largest captured score, need = k + seen_u  =>  k-th best unmasked >= X
     const int64_t need64 = (int64_t)k + seen_u;
@@ -194,7 +236,7 @@ select_topk_kernel(const SelectParams p) {
     uint32_t lo = thr_key > KEY_NEG_INF ? thr_key : KEY_NEG_INF + 1, hi = 0xff800000u;  // hi: above every finite key
     while (hi - lo > 1) {
       const uint32_t mid = lo + ((hi - lo) >> 1);
-      const int c = count_ge(p, row, n0, ng, mid, lane);
+      const int c = scan_groups<false>(p, row, n0, ng, mid, key, id, lane);
       if (c >= need) lo = mid; else hi = mid;
       if (c >= need && c <= need + need / 8) break;  // close enough
     }
@@ -202,34 +244,37 @@ select_topk_kernel(const SelectParams p) {
     const uint32_t cut_key = f32_to_key(__float_as_uint((X - margin2) + 0.0f));
     if (cut_key <= thr_key) { report_fail(p, row, lane); return; }
     thr_key = cut_key;
-    ne = enumerate_ge(p, row, n0, ng, thr_key, key, id, lane);
+    ne = scan_groups<true>(p, row, n0, ng, thr_key, key, id, lane);
     if (ne > SEL_CAP) { report_fail(p, row, lane); return; }
   }
 
-  // ---- B: seen-item mask ----
+  // ---- B: seen-item mask (each candidate looked up in the row's sorted seen list) ----
   if (seen_u > 0) {
     for (int i = lane; i < ne; i += 32) {
       const int64_t gid = (int64_t)id[i] + p.item_id_offset;
-      int64_t lo = s0, hi = s1;
-      while (lo < hi) {
-        const int64_t mid = (lo + hi) >> 1;
-        if ((int64_t)__ldg(p.seen_items + mid) < gid) lo = mid + 1; else hi = mid;
+      int64_t lo = 0, hi = seen_u;
+      if (seen_in_smem) {
+        while (lo < hi) {
+          const int64_t mid = (lo + hi) >> 1;
+          if ((int64_t)seen_s[mid] < gid) lo = mid + 1; else hi = mid;
+        }
+        if (lo < seen_u && (int64_t)seen_s[lo] == gid) key[i] = 0;
+      } else {
+        while (lo < hi) {
+          const int64_t mid = (lo + hi) >> 1;
+          if ((int64_t)__ldg(p.seen_items + s0 + mid) < gid) lo = mid + 1; else hi = mid;
+        }
+        if (lo < seen_u && (int64_t)__ldg(p.seen_items + s0 + lo) == gid) key[i] = 0;
       }
-      if (lo < s1 && (int64_t)__ldg(p.seen_items + lo) == gid) key[i] = 0;
     }
   }
   __syncwarp();
 
-  // ---- C: lower bound T of the k-th best unmasked tensor-core score ----
-  uint32_t rk[SEL_SLOTS], rid[SEL_SLOTS];
+  // ---- C: a lower bound T of the k-th best unmasked tensor-core score (count(>= T) in [k, k + k/8]) ----
   int nv_local = 0;
   uint32_t kmin = 0xffffffffu, kmax = 0;
-#pragma unroll
-  for (int s = 0; s < SEL_SLOTS; ++s) {
-    const int idx = s * 32 + lane;
-    const uint32_t kk = idx < ne ? key[idx] : 0;
-    rk[s] = kk;
-    rid[s] = idx < ne ? id[idx] : 0;
+  for (int i = lane; i < ne; i += 32) {
+    const uint32_t kk = key[i];
     if (kk) { nv_local++; kmin = min(kmin, kk); kmax = max(kmax, kk); }
   }
   const int nv = __reduce_add_sync(0xffffffffu, nv_local);
@@ -239,11 +284,11 @@ select_topk_kernel(const SelectParams p) {
   if (nv >= k) {
     uint32_t lo = kmin, hi = kmax + 1;
     int c_lo = nv;
-    while (hi - lo > 1 && c_lo != k) {
+    const int c_ok = k + (k >> 3);
+    while (hi - lo > 1 && c_lo > c_ok) {
       const uint32_t mid = lo + ((hi - lo) >> 1);
       int c = 0;
-#pragma unroll
-      for (int s = 0; s < SEL_SLOTS; ++s) c += (rk[s] >= mid) ? 1 : 0;
+      for (int i = lane; i < ne; i += 32) c += (key[i] >= mid) ? 1 : 0;
       c = __reduce_add_sync(0xffffffffu, c);
       if (c >= k) { lo = mid; c_lo = c; } else { hi = mid; }
     }
@@ -254,46 +299,70 @@ select_topk_kernel(const SelectParams p) {
     report_fail(p, row, lane);  // fewer than k unmasked candidates captured above a threshold
     return;
   }
-  // ---- D: compact the candidates to re-score, then exact fp32 scores ----
-  __syncwarp();
+
+  // ---- D: compact the candidates to re-score (in place), then exact fp32 scores ----
   int nr = 0;
-#pragma unroll
-  for (int s = 0; s < SEL_SLOTS; ++s) {
-    const bool keep = rk[s] != 0 && rk[s] >= cut;
+  for (int base = 0; base < ne; base += 32) {
+    const int i = base + lane;
+    const uint32_t kk = i < ne ? key[i] : 0;
+    const uint32_t ii = i < ne ? id[i] : 0;
+    const bool keep = kk != 0 && kk >= cut;
     const uint32_t kb = __ballot_sync(0xffffffffu, keep);
-    if (keep) id[nr + __popc(kb & lt)] = rid[s];
+    __syncwarp();
+    if (keep) id[nr + __popc(kb & lt)] = ii;
     nr += __popc(kb);
   }
   __syncwarp();
   const int d = p.d;
-  const bool vec = ((d & 3) == 0) && d <= 128 * MAX_UCH;
-  if (vec) {
+  const bool want_ild = NJ > 0 && p.out_ild != nullptr;
+  float4 acc[NJ > 0 ? NJ : 1];  // sum of the normalised rows of every re-scored candidate (fused ILD)
+  if (NJ > 0) {
     const int nvec = d >> 2;
-    float4 ur[MAX_UCH];
+    const int sub = lane & 7, grp = lane >> 3;
+    float4 ur[NJ > 0 ? NJ : 1];
 #pragma unroll
-    for (int c = 0; c < MAX_UCH; ++c) {
-      const int c4 = c * 32 + lane;
-      ur[c] = c4 < nvec ? ld4(p.U, p.dtype, row, d, c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < NJ; ++j) {
+      const int c4 = sub + 8 * j;
+      ur[j] = c4 < nvec ? ld4(p.U, p.dtype, row, d, c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    for (int r = 0; r < nr; r += 2) {
-      const uint32_t ia = id[r], ib = id[min(r + 1, nr - 1)];
-      float sa = 0.f, sb = 0.f;
+    for (int r0 = 0; r0 < nr; r0 += 8) {
+      const int ra = r0 + grp, rb = r0 + 4 + grp;
+      const uint32_t ia = id[min(ra, nr - 1)], ib = id[min(rb, nr - 1)];
+      float4 va[NJ > 0 ? NJ : 1], vb[NJ > 0 ? NJ : 1];
 #pragma unroll
-      for (int c = 0; c < MAX_UCH; ++c) {
-        const int c4 = c * 32 + lane;
-        if (c * 32 < nvec) {
-          if (c4 < nvec) {
-            const float4 va = ld4(p.V, p.dtype, ia, d, c4), vb = ld4(p.V, p.dtype, ib, d, c4);
-            sa = fmaf(ur[c].x, va.x, sa); sa = fmaf(ur[c].y, va.y, sa); sa = fmaf(ur[c].z, va.z, sa); sa = fmaf(ur[c].w, va.w, sa);
-            sb = fmaf(ur[c].x, vb.x, sb); sb = fmaf(ur[c].y, vb.y, sb); sb = fmaf(ur[c].z, vb.z, sb); sb = fmaf(ur[c].w, vb.w, sb);
+      for (int j = 0; j < NJ; ++j) {
+        const int c4 = sub + 8 * j;
+        if (8 * j < nvec) {
+          va[j] = c4 < nvec ? ld4(p.V, p.dtype, ia, d, c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          vb[j] = c4 < nvec ? ld4(p.V, p.dtype, ib, d, c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      float sa = 0.f, sb = 0.f, qa = 0.f, qb = 0.f;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        if (8 * j < nvec) {
+          sa = dot4(ur[j], va[j], sa); sb = dot4(ur[j], vb[j], sb);
+          if (want_ild) { qa = dot4(va[j], va[j], qa); qb = dot4(vb[j], vb[j], qb); }
+        }
+      }
+      sa = sum8(sa); sb = sum8(sb);
+      if (want_ild) {
+        qa = sum8(qa); qb = sum8(qb);
+        const float ia_n = ra < nr ? 1.0f / sqrtf(qa) : 0.f, ib_n = rb < nr ? 1.0f / sqrtf(qb) : 0.f;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          if (8 * j < nvec) {
+            acc[j].x = fmaf(va[j].x, ia_n, acc[j].x); acc[j].y = fmaf(va[j].y, ia_n, acc[j].y);
+            acc[j].z = fmaf(va[j].z, ia_n, acc[j].z); acc[j].w = fmaf(va[j].w, ia_n, acc[j].w);
+            acc[j].x = fmaf(vb[j].x, ib_n, acc[j].x); acc[j].y = fmaf(vb[j].y, ib_n, acc[j].y);
+            acc[j].z = fmaf(vb[j].z, ib_n, acc[j].z); acc[j].w = fmaf(vb[j].w, ib_n, acc[j].w);
           }
         }
       }
-      sa = warp_sum(sa);
-      sb = warp_sum(sb);
-      if (lane == 0) {
-        key[r] = f32_to_key(__float_as_uint(sa + 0.0f));
-        if (r + 1 < nr) key[r + 1] = f32_to_key(__float_as_uint(sb + 0.0f));
+      if (sub == 0) {
+        if (ra < nr) key[ra] = f32_to_key(__float_as_uint(sa + 0.0f));
+        if (rb < nr) key[rb] = f32_to_key(__float_as_uint(sb + 0.0f));
       }
     }
   } else {
@@ -307,83 +376,97 @@ select_topk_kernel(const SelectParams p) {
   }
   __syncwarp();
 
-  // ---- E: exact top-k by (E desc, id asc) ----
-  nv_local = 0; kmin = 0xffffffffu; kmax = 0;
-#pragma unroll
-  for (int s = 0; s < SEL_SLOTS; ++s) {
-    const int idx = s * 32 + lane;
-    uint32_t kk = idx < nr ? key[idx] : 0;
-    if (kk <= KEY_NEG_INF) kk = 0;  // -inf / NaN scores are not recommendable
-    rk[s] = kk;
-    rid[s] = idx < nr ? id[idx] : 0;
-    if (kk) { nv_local++; kmin = min(kmin, kk); kmax = max(kmax, kk); }
-  }
-  const int nv2 = __reduce_add_sync(0xffffffffu, nv_local);
-  kmin = __reduce_min_sync(0xffffffffu, kmin);
-  kmax = __reduce_max_sync(0xffffffffu, kmax);
-  uint32_t T = 0;
-  int quota = 0x7fffffff;
-  if (nv2 > k) {
-    uint32_t lo = kmin, hi = kmax + 1;
-    int c_lo = nv2, c_hi = 0;
-    while (hi - lo > 1 && c_lo != k) {
-      const uint32_t mid = lo + ((hi - lo) >> 1);
-      int c = 0;
-#pragma unroll
-      for (int s = 0; s < SEL_SLOTS; ++s) c += (rk[s] >= mid) ? 1 : 0;
-      c = __reduce_add_sync(0xffffffffu, c);
-      if (c >= k) { lo = mid; c_lo = c; } else { hi = mid; c_hi = c; }
-    }
-    T = lo;
-    if (c_lo != k) quota = k - c_hi;  // hi == lo + 1: T is the exact k-th key, ties trimmed by id
-  }
-  // ties on the k-th score: keep the `quota` lowest item ids among them
-  uint32_t id_cut = 0xffffffffu;
-  if (quota != 0x7fffffff) {
-    int nt = 0;
-#pragma unroll
-    for (int s = 0; s < SEL_SLOTS; ++s) {
-      const bool eq = rk[s] == T && rk[s] != 0;
-      const uint32_t eb = __ballot_sync(0xffffffffu, eq);
-      if (eq) tie_id[nt + __popc(eb & lt)] = rid[s];
-      nt += __popc(eb);
+  // ---- E: exact top-k by (E desc, id asc): composite keys are unique, sort chunks of 128 and merge ----
+  for (int c0 = 0; c0 < nr || c0 == 0; c0 += SORT_N) {
+    unsigned long long* dst = c0 == 0 ? top : chunk;
+    for (int i = lane; i < SORT_N; i += 32) {
+      const int r = c0 + i;
+      unsigned long long c = 0ull;
+      if (r < nr) {
+        uint32_t kk = key[r];
+        if (kk > KEY_NEG_INF && kk < 0xff800000u) c = ((unsigned long long)kk << 32) | (unsigned long long)(~id[r]);
+      }
+      dst[i] = c;
     }
     __syncwarp();
-    for (int i = lane; i < nt; i += 32) {
-      const uint32_t me = tie_id[i];
-      int r = 0;
-      for (int j = 0; j < nt; ++j) r += (tie_id[j] < me) ? 1 : 0;
-      if (r == quota - 1) id_cut = me;
+    warp_bitonic_desc_128(dst, lane);
+    if (c0 > 0) {
+      for (int i = lane; i < SORT_N; i += 32) {
+        const unsigned long long a = top[i], b = chunk[SORT_N - 1 - i];
+        top[i] = a > b ? a : b;
+      }
+      __syncwarp();
+      warp_bitonic_merge_desc_128(top, lane);
     }
-    id_cut = __reduce_min_sync(0xffffffffu, id_cut);
   }
-  for (int i = lane; i < SORT_N; i += 32) srt[i] = 0ull;
-  __syncwarp();
-  int outn = 0;
-#pragma unroll
-  for (int s = 0; s < SEL_SLOTS; ++s) {
-    const uint32_t kk = rk[s];
-    const bool keep = kk != 0 && (kk > T || (kk == T && rid[s] <= id_cut));
-    const uint32_t kb = __ballot_sync(0xffffffffu, keep);
-    if (keep) {
-      const int pos = outn + __popc(kb & lt);
-      if (pos < SORT_N) srt[pos] = ((unsigned long long)kk << 32) | (unsigned long long)(~rid[s]);
-    }
-    outn += __popc(kb);
-  }
-  __syncwarp();
-  warp_bitonic_desc_128(srt, lane);
+  int kv = 0;  // valid results of the row
   for (int r = lane; r < k; r += 32) {
-    const unsigned long long c = srt[r];
+    const unsigned long long c = top[r];
     const uint32_t kk = (uint32_t)(c >> 32);
     float sc = -INFINITY;
     int64_t it = -1;
     if (kk != 0) {
       sc = __uint_as_float(key_to_f32(kk));
       it = (int64_t)(~(uint32_t)c) + p.item_id_offset;
+      kv++;
+      if (p.coverage != nullptr) atomicAdd(p.coverage + it, 1);
     }
     p.out_scores[row * k + r] = sc;
     p.out_items[row * k + r] = it;
+  }
+  if (NJ > 0 && want_ild) {
+    // fused cosine ILD: sum_{a<b} cos = (|sum e|^2 - kv) / 2 over the winners.  acc holds the sum over ALL
+    // re-scored candidates; subtract the few that did not make the top-k.
+    kv = __reduce_add_sync(0xffffffffu, kv);
+    const unsigned long long kth = k <= SORT_N ? top[k - 1] : 0ull;  // smallest winning composite (0 when fewer than k)
+    const int nvec = d >> 2;
+    const int sub = lane & 7, grp = lane >> 3;
+    for (int r0 = 0; r0 < nr; r0 += 4) {
+      const int r = r0 + grp;
+      bool loser = false;
+      uint32_t ia = 0;
+      if (r < nr) {
+        ia = id[r];
+        const uint32_t kk = key[r];
+        unsigned long long c = 0ull;
+        if (kk > KEY_NEG_INF && kk < 0xff800000u) c = ((unsigned long long)kk << 32) | (unsigned long long)(~ia);
+        loser = c < kth || c == 0ull;
+      }
+      if (__ballot_sync(0xffffffffu, loser) == 0) continue;
+      float4 va[NJ > 0 ? NJ : 1];
+      float qa = 0.f;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const int c4 = sub + 8 * j;
+        va[j] = (loser && c4 < nvec) ? ld4(p.V, p.dtype, ia, d, c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        qa = dot4(va[j], va[j], qa);
+      }
+      qa = sum8(qa);
+      const float inv = loser ? 1.0f / sqrtf(qa) : 0.f;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        acc[j].x = fmaf(-va[j].x, inv, acc[j].x); acc[j].y = fmaf(-va[j].y, inv, acc[j].y);
+        acc[j].z = fmaf(-va[j].z, inv, acc[j].z); acc[j].w = fmaf(-va[j].w, inv, acc[j].w);
+      }
+    }
+    // combine the four sub-groups' partial sums (same `sub` => same columns), then |sum e|^2
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      float4 t = acc[j];
+      t.x += __shfl_xor_sync(0xffffffffu, t.x, 8); t.y += __shfl_xor_sync(0xffffffffu, t.y, 8);
+      t.z += __shfl_xor_sync(0xffffffffu, t.z, 8); t.w += __shfl_xor_sync(0xffffffffu, t.w, 8);
+      t.x += __shfl_xor_sync(0xffffffffu, t.x, 16); t.y += __shfl_xor_sync(0xffffffffu, t.y, 16);
+      t.z += __shfl_xor_sync(0xffffffffu, t.z, 16); t.w += __shfl_xor_sync(0xffffffffu, t.w, 16);
+      s = dot4(t, t, s);
+    }
+    s = sum8(s);  // lanes 0..7 hold the distinct column chunks
+    if (lane == 0) {
+      const float kvf = (float)kv;
+      const float sum_cos = 0.5f * (s - kvf);
+      const float pairs = 0.5f * kvf * (kvf - 1.0f);
+      p.out_ild[row] = (pairs - sum_cos) / ((float)k * (float)(k - 1));
+    }
   }
 }
 
@@ -430,10 +513,19 @@ topk_merge_kernel(const float* __restrict__ gs, const int64_t* __restrict__ gi, 
 
 cudaError_t launch_select_topk(const SelectParams& p, cudaStream_t stream) {
   const size_t smem = sizeof(SelSmem);
-  cudaError_t e = cudaFuncSetAttribute(select_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
   const int64_t grid = (p.nU + SEL_WARPS - 1) / SEL_WARPS;
-  select_topk_kernel<<<(unsigned)grid, SEL_WARPS * 32, smem, stream>>>(p);
+  const bool vec = (p.d & 3) == 0 && p.d <= 256;  // wider rows take the scalar path (no fused metrics)
+  cudaError_t e;
+#define DIVREC_LAUNCH_SELECT(NJ)                                                                                   \
+  do {                                                                                                             \
+    e = cudaFuncSetAttribute(select_topk_kernel<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
+    if (e != cudaSuccess) return e;                                                                                \
+    select_topk_kernel<NJ><<<(unsigned)grid, SEL_WARPS * 32, smem, stream>>>(p);                                   \
+  } while (0)
+  if (!vec) DIVREC_LAUNCH_SELECT(0);
+  else if (p.d <= 128) DIVREC_LAUNCH_SELECT(4);
+  else DIVREC_LAUNCH_SELECT(8);
+#undef DIVREC_LAUNCH_SELECT
   count_launch();
   return cudaGetLastError();
 }

@@ -33,6 +33,7 @@ SIGNATURES = {
     "divrec_profile_read": (_i32, [_c.POINTER(_c.c_float), _i32]),
     "divrec_score_topk_workspace": (_sz, [_i64, _i64, _i32, _i32, _i32]),
     "divrec_score_topk": (_i32, [_vp, _vp, _i64, _i64, _i32, _i32, _i32, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _sz, _vp]),
+    "divrec_score_topk_metrics": (_i32, [_vp, _vp, _i64, _i64, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "divrec_score_topk_rescued": (_i32, [_vp, _i64, _i64, _i32, _i32, _c.POINTER(_c.c_int32), _vp]),
     "divrec_topk_merge": (_i32, [_vp, _vp, _i32, _i64, _i32, _vp, _vp, _vp]),
     "divrec_ild_cosine": (_i32, [_vp, _i64, _i32, _i32, _vp, _i64, _i32, _i32, _vp, _vp, _vp]),
@@ -180,6 +181,38 @@ def score_topk(U: torch.Tensor, V: torch.Tensor, k: int, seen_rowptr: Optional[t
             _check(lib.divrec_score_topk_rescued(_ptr(ws), nU, nI, d, dt, _c.byref(n), _stream(U.device)), "divrec_score_topk_rescued")
             return out_s, out_i, {"rescued_rows": int(n.value)}
     return out_s, out_i
+
+
+def score_topk_metrics(U: torch.Tensor, V: torch.Tensor, k: int, seen_rowptr: Optional[torch.Tensor] = None,
+                       seen_items: Optional[torch.Tensor] = None, counts: Optional[torch.Tensor] = None,
+                       want_ild: bool = True, want_coverage: bool = True, mode: int = MODE_TENSOR):
+    """score + mask + top-k with the cosine ILD and the coverage histogram fused into the selection kernel.
+    Returns (scores [nU,k], items [nU,k], ild [nU] or None, counts int32 [nI] or None)."""
+    lib = load_library()
+    U = _cuda(U, "U")
+    V = _cuda(V, "V", U.dtype)
+    dt = _table_dtype(U)
+    nU, d = U.shape
+    nI = V.shape[0]
+    if seen_rowptr is not None:
+        seen_rowptr = _cuda(seen_rowptr, "seen_rowptr", torch.int64)
+        if seen_items is not None:
+            seen_items = _cuda(seen_items, "seen_items", torch.int32)
+            if seen_items.numel() == 0:
+                seen_items = None
+    with torch.cuda.device(U.device):
+        ws_bytes = lib.divrec_score_topk_workspace(nU, nI, d, dt, k)
+        ws = _workspace(ws_bytes, U.device)
+        out_s = torch.empty((nU, k), dtype=torch.float32, device=U.device)
+        out_i = torch.empty((nU, k), dtype=torch.int64, device=U.device)
+        ild = torch.empty(nU, dtype=torch.float32, device=U.device) if want_ild else None
+        if want_coverage and counts is None:
+            counts = torch.zeros(nI, dtype=torch.int32, device=U.device)
+        rc = lib.divrec_score_topk_metrics(_ptr(U), _ptr(V), nU, nI, d, dt, mode, _ptr(seen_rowptr), _ptr(seen_items), k,
+                                           _ptr(out_s), _ptr(out_i), _ptr(ild), _ptr(counts) if want_coverage else None,
+                                           _ptr(ws), ws_bytes, _stream(U.device))
+    _check(rc, "divrec_score_topk_metrics")
+    return out_s, out_i, ild, (counts if want_coverage else None)
 
 
 def topk_merge(gathered_scores: torch.Tensor, gathered_items: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:

@@ -203,10 +203,9 @@ def host_recommend_and_score(U_host: torch.Tensor, V_host: torch.Tensor, seen_ro
     for name, src in (("U", U_host), ("V", V_host), ("rp", seen_rowptr_host), ("it", seen_items_host)):
         st[name].copy_(src, non_blocking=True)
         h2d += src.numel() * src.element_size()
-    _scores, recs = _native.score_topk(st["U"], st["V"], k, st["rp"], st["it"] if st["it"].numel() else None)
-    ild = _native.ild_cosine(st["V"], recs)
     st["counts"].zero_()
-    _native.coverage_hist(recs, nI, st["counts"])
+    _scores, recs, ild, _ = _native.score_topk_metrics(st["U"], st["V"], k, st["rp"], st["it"] if st["it"].numel() else None,
+                                                       counts=st["counts"])
     ent = _native.entropy_from_counts(st["counts"])
     d2h = 0
     outs = [("ild_h", ild), ("counts_h", st["counts"]), ("ent_h", ent)]

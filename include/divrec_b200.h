@@ -94,6 +94,19 @@ int divrec_score_topk(const void* U, const void* V, int64_t nU, int64_t nI, int 
                       int64_t* out_items /*[nU,k]*/, void* workspace, size_t ws_bytes,
                       void* stream);
 
+/* The same pass with the list metrics fused into the selection kernel (the top-k item rows are already
+ * in flight there for the exact re-scoring, so the ILD costs no second gather):
+ *   out_ild [nU] (or NULL)          per-user cosine ILD of the row's top-k over the item table V, the value of
+ *                                   divrec_ild_cosine on out_items (replaces
+ *                                   divrec/losses/intra_list_diversity_score.py:20-42 with D = 1 - cos)
+ *   coverage_counts [nI] (or NULL)  += histogram of the recommended ids, caller-zeroed (replaces torch.unique at
+ *                                   divrec/metrics/entropy_diversity_score.py:22)
+ * Whole catalogue only (no item_id_offset); the fused ILD needs d % 4 == 0, d <= 256, k >= 2. */
+int divrec_score_topk_metrics(const void* U, const void* V, int64_t nU, int64_t nI, int d, int dtype,
+                              int mode, const int64_t* seen_rowptr, const int32_t* seen_items, int k,
+                              float* out_scores, int64_t* out_items, float* out_ild,
+                              int32_t* coverage_counts, void* workspace, size_t ws_bytes, void* stream);
+
 int divrec_score_topk_rescued(const void* workspace, int64_t nU, int64_t nI, int d, int dtype,
                                 int32_t* host_out /*host*/, void* stream);
 

@@ -182,6 +182,28 @@ def test_hint_path_rarely_needs_the_rescue_kernel(native, dev):
     check_topk_against_oracle(i[sample.to(dev)], s[sample.to(dev)], o_i, o_s, U, V, False)
 
 
+@pytest.mark.parametrize("nU,nI,d,k,kind,dt", [
+    (943, 1682, 64, 10, "gauss", torch.float32),
+    (600, 26744, 128, 100, "gauss", torch.float32),
+    (300, 9000, 256, 100, "gauss", torch.bfloat16),
+    (257, 5000, 100, 37, "grid", torch.float32),
+])
+def test_fused_metrics_equal_the_separate_kernels_and_the_oracle(native, dev, nU, nI, d, k, kind, dt):
+    gen = torch.Generator().manual_seed(nU + nI + d)
+    U, V = O.make_embeddings(nU, d, kind, gen).to(dt), O.make_embeddings(nI, d, kind, gen).to(dt)
+    U[5] = 0  # a row that has to go through the rescue kernel (fused metrics must cover it too)
+    seen = O.make_seen(nU, nI, 8 * nU, gen)
+    rowptr, items = O.seen_csr(seen, nU)
+    Ud, Vd, rp, it = U.to(dev), V.to(dev), rowptr.to(dev), items.to(dev)
+    s0, i0 = native.score_topk(Ud, Vd, k, rp, it)
+    s1, i1, ild, counts = native.score_topk_metrics(Ud, Vd, k, rp, it)
+    assert torch.equal(i0, i1) and torch.equal(s0, s1)
+    torch.testing.assert_close(ild, native.ild_cosine(Vd, i1, native.ILD_SUMVEC), rtol=REL, atol=1e-7)
+    torch.testing.assert_close(ild.cpu(), O.ild_cosine(i1.cpu(), V.float()), rtol=REL, atol=1e-7)
+    assert torch.equal(counts, native.coverage_hist(i1, nI))
+    assert torch.equal(counts.cpu().long(), O.coverage_counts(i1.cpu(), nI))
+
+
 def test_bf16_tables(native, dev):
     gen = torch.Generator().manual_seed(17)
     U = O.make_embeddings(200, 256, "gauss", gen).bfloat16()
