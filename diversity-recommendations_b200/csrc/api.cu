@@ -70,7 +70,7 @@ struct WsLayout {
   bool convA, convB;  // operands have to be rewritten into the workspace (fp32 -> fp16, or bf16 padding)
   int64_t chunk;
   int rescue_grid;
-  size_t offA, offB, offNormU, offListS, offListI, offCounts, offThr, offFail, offScalars, offRescue, total;
+  size_t offA, offB, offNormU, offInvV, offListS, offListI, offCounts, offThr, offFail, offScalars, offRescue, total;
 };
 static WsLayout ws_layout(int64_t nU, int64_t nI, int d, int dtype) {
   WsLayout w{};
@@ -83,6 +83,7 @@ static WsLayout ws_layout(int64_t nU, int64_t nI, int d, int dtype) {
   w.offA = off; if (w.convA) off += align_up(cpad * w.K * 2, 1024);
   w.offB = off; if (w.convB) off += align_up((size_t)nI * w.K * 2, 1024);
   w.offNormU = off; off += align_up(cpad * sizeof(float), 1024);
+  w.offInvV = off; off += align_up((size_t)nI * sizeof(float), 1024);
   w.offListS = off; off += align_up(cpad * 2 * LIST_CAP * GROUP * sizeof(float), 1024);
   w.offListI = off; off += align_up(cpad * 2 * LIST_CAP * sizeof(uint32_t), 1024);
   w.offCounts = off; off += align_up(cpad * 2 * sizeof(int32_t), 1024);
@@ -169,6 +170,7 @@ static int score_topk_impl(const void* U, const void* V, int64_t nU, int64_t nI,
   uint32_t* nvmax = scal + 4;
   int32_t* fail_count = reinterpret_cast<int32_t*>(scal + 5);
   float* norms_u = reinterpret_cast<float*>(ws + w.offNormU);
+  float* inv_v = reinterpret_cast<float*>(ws + w.offInvV);
   cudaError_t e = cudaMemsetAsync(scal, 0, 64, st);
   if (e != cudaSuccess) return cuda_fail(e, "memset scalars");
 
@@ -178,10 +180,10 @@ static int score_topk_impl(const void* U, const void* V, int64_t nU, int64_t nI,
   if (tensor) {
     if (dtype == DIVREC_F32) {
       e = launch_prep_f32(reinterpret_cast<const float*>(V), nI, d, w.d_pad, reinterpret_cast<__half*>(ws + w.offB), amax + 1,
-                          sexp + 1, nullptr, nvmax, st);
+                          sexp + 1, nullptr, inv_v, nvmax, st);
       B16 = ws + w.offB;
     } else {
-      e = launch_prep_bf16(V, nI, d, w.d_pad, w.convB ? ws + w.offB : nullptr, nullptr, nvmax, st);
+      e = launch_prep_bf16(V, nI, d, w.d_pad, w.convB ? ws + w.offB : nullptr, nullptr, inv_v, nvmax, st);
       if (w.convB) B16 = ws + w.offB;
     }
     if (e != cudaSuccess) return cuda_fail(e, "prepare item table");
@@ -202,7 +204,7 @@ static int score_topk_impl(const void* U, const void* V, int64_t nU, int64_t nI,
     sp.list_count = reinterpret_cast<int32_t*>(ws + w.offCounts);
     sp.thr = reinterpret_cast<float*>(ws + w.offThr);
     sp.seen_rowptr = rp; sp.seen_items = seen_items; sp.item_id_offset = item_id_offset;
-    sp.norms_u = norms_u; sp.nvmax_bits = nvmax;
+    sp.norms_u = norms_u; sp.nvmax_bits = nvmax; sp.inv_norm_v = inv_v;
     sp.out_scores = outs; sp.out_items = outi;
     sp.fail_rows = reinterpret_cast<int32_t*>(ws + w.offFail); sp.fail_count = fail_count;
     sp.force_fail = tensor ? 0 : 1;
@@ -219,12 +221,12 @@ static int score_topk_impl(const void* U, const void* V, int64_t nU, int64_t nI,
         e = cudaMemsetAsync(amax, 0, sizeof(uint32_t), st);
         if (e != cudaSuccess) return cuda_fail(e, "memset amax");
         e = launch_prep_f32(reinterpret_cast<const float*>(Uc), cu, d, w.d_pad, reinterpret_cast<__half*>(ws + w.offA), amax,
-                            sexp, norms_u, nullptr, st);
+                            sexp, norms_u, nullptr, nullptr, st);
         A16 = ws + w.offA;
         sp.scale_exps = sexp; sp.amax_bits = amax;
         sp.c_margin = 1.1f / 1024.0f;
       } else {
-        e = launch_prep_bf16(Uc, cu, d, w.d_pad, w.convA ? ws + w.offA : nullptr, norms_u, nullptr, st);
+        e = launch_prep_bf16(Uc, cu, d, w.d_pad, w.convA ? ws + w.offA : nullptr, norms_u, nullptr, nullptr, st);
         if (w.convA) A16 = ws + w.offA;
         sp.scale_exps = nullptr; sp.amax_bits = nullptr;
         sp.c_margin = 1.0f / 4096.0f;

@@ -41,9 +41,9 @@ cudaError_t launch_score_filter(const void* A16, const void* B16, FilterParams p
 // plus fp32 row norms of X and (optionally) the maximum row norm as float bits.
 // amax_bits must be zeroed by the caller; scale_exp is written.
 cudaError_t launch_prep_f32(const float* X, int64_t rows, int d, int d_pad, __half* out, uint32_t* amax_bits,
-                            int32_t* scale_exp, float* norms, uint32_t* normmax_bits, cudaStream_t stream);
+                            int32_t* scale_exp, float* norms, float* inv_norms, uint32_t* normmax_bits, cudaStream_t stream);
 // bf16 [rows,d]: row norms (+ max); zero-padded copy [rows,d_pad] when out != null
-cudaError_t launch_prep_bf16(const void* X, int64_t rows, int d, int d_pad, void* out, float* norms,
+cudaError_t launch_prep_bf16(const void* X, int64_t rows, int d, int d_pad, void* out, float* norms, float* inv_norms,
                              uint32_t* normmax_bits, cudaStream_t stream);
 
 struct SelectParams {
@@ -62,6 +62,7 @@ struct SelectParams {
   const int32_t* scale_exps;   // device [2] or null: tensor-core scores carry a factor 2^(e0+e1)
   const float* norms_u;        // [nU]
   const uint32_t* nvmax_bits;  // device: max item row norm (float bits)
+  const float* inv_norm_v;     // [nI] 1 / |V_i| (fused ILD)
   const uint32_t* amax_bits;   // device [2]: max |element| of the user / item table (float bits), null for bf16
   float c_margin;              // delta_u = c_margin * |u| * max|v|
   float* out_scores;           // [nU,k]

@@ -42,7 +42,8 @@ __global__ void scale_exp_kernel(const uint32_t* __restrict__ amax_bits, int32_t
 // one warp per row: scaled fp16 copy (zero padded to d_pad) + fp32 row norm (+ global max norm)
 __global__ void __launch_bounds__(256)
 convert_f32_kernel(const float* __restrict__ X, int64_t rows, int d, int d_pad, __half* __restrict__ out,
-                   const int32_t* __restrict__ scale_exp, float* __restrict__ norms, uint32_t* __restrict__ normmax_bits) {
+                   const int32_t* __restrict__ scale_exp, float* __restrict__ norms, float* __restrict__ inv_norms,
+                   uint32_t* __restrict__ normmax_bits) {
   const uint32_t lane = lane_id();
   const int e = *scale_exp;
   const bool vec = ((d & 3) == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
@@ -71,6 +72,7 @@ convert_f32_kernel(const float* __restrict__ X, int64_t rows, int d, int d_pad, 
     ss = warp_sum(ss);
     const float nrm = sqrtf(ss) * 1.000001f;  // round up: the norm feeds an error BOUND
     if (lane == 0 && norms) norms[r] = nrm;
+    if (lane == 0 && inv_norms) inv_norms[r] = 1.0f / sqrtf(ss);
     wmax = fmaxf(wmax, nrm);
   }
   if (normmax_bits && lane == 0 && wmax > 0.f && wmax < INFINITY) atomicMax(normmax_bits, __float_as_uint(wmax));
@@ -78,7 +80,7 @@ convert_f32_kernel(const float* __restrict__ X, int64_t rows, int d, int d_pad, 
 
 __global__ void __launch_bounds__(256)
 prep_bf16_kernel(const __nv_bfloat16* __restrict__ X, int64_t rows, int d, int d_pad, __nv_bfloat16* __restrict__ out,
-                 float* __restrict__ norms, uint32_t* __restrict__ normmax_bits) {
+                 float* __restrict__ norms, float* __restrict__ inv_norms, uint32_t* __restrict__ normmax_bits) {
   const uint32_t lane = lane_id();
   float wmax = 0.f;
   for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < rows; r += ((int64_t)gridDim.x * blockDim.x) >> 5) {
@@ -93,6 +95,7 @@ prep_bf16_kernel(const __nv_bfloat16* __restrict__ X, int64_t rows, int d, int d
     ss = warp_sum(ss);
     const float nrm = sqrtf(ss) * 1.000001f;
     if (lane == 0 && norms) norms[r] = nrm;
+    if (lane == 0 && inv_norms) inv_norms[r] = 1.0f / sqrtf(ss);
     wmax = fmaxf(wmax, nrm);
   }
   if (normmax_bits && lane == 0 && wmax > 0.f && wmax < INFINITY) atomicMax(normmax_bits, __float_as_uint(wmax));
@@ -108,7 +111,7 @@ inline unsigned grid_for(int64_t work, int threads) {
 }  // namespace
 
 cudaError_t launch_prep_f32(const float* X, int64_t rows, int d, int d_pad, __half* out, uint32_t* amax_bits,
-                            int32_t* scale_exp, float* norms, uint32_t* normmax_bits, cudaStream_t stream) {
+                            int32_t* scale_exp, float* norms, float* inv_norms, uint32_t* normmax_bits, cudaStream_t stream) {
   const int64_t n = rows * d;
   const bool al16 = (reinterpret_cast<uintptr_t>(X) & 15) == 0;
   const int64_t n4 = al16 ? n / 4 : 0;
@@ -116,15 +119,15 @@ cudaError_t launch_prep_f32(const float* X, int64_t rows, int d, int d_pad, __ha
   count_launch();
   scale_exp_kernel<<<1, 1, 0, stream>>>(amax_bits, scale_exp);
   count_launch();
-  convert_f32_kernel<<<grid_for(rows * 32, 256), 256, 0, stream>>>(X, rows, d, d_pad, out, scale_exp, norms, normmax_bits);
+  convert_f32_kernel<<<grid_for(rows * 32, 256), 256, 0, stream>>>(X, rows, d, d_pad, out, scale_exp, norms, inv_norms, normmax_bits);
   count_launch();
   return cudaGetLastError();
 }
 
-cudaError_t launch_prep_bf16(const void* X, int64_t rows, int d, int d_pad, void* out, float* norms,
+cudaError_t launch_prep_bf16(const void* X, int64_t rows, int d, int d_pad, void* out, float* norms, float* inv_norms,
                              uint32_t* normmax_bits, cudaStream_t stream) {
   prep_bf16_kernel<<<grid_for(rows * 32, 256), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(X), rows, d, d_pad,
-                                                                 reinterpret_cast<__nv_bfloat16*>(out), norms, normmax_bits);
+                                                                 reinterpret_cast<__nv_bfloat16*>(out), norms, inv_norms, normmax_bits);
   count_launch();
   return cudaGetLastError();
 }

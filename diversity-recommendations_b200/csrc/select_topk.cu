@@ -73,8 +73,9 @@ __device__ __forceinline__ void warp_bitonic_merge_desc_128(unsigned long long* 
   }
 }
 
-__device__ __forceinline__ float4 ld4(const void* T, int dtype, int64_t row, int d, int c4) {
-  if (dtype == 0) {
+template <int DT>
+__device__ __forceinline__ float4 ld4(const void* T, int64_t row, int d, int c4) {
+  if (DT == 0) {
     return __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(T) + row * d) + c4);
   } else {
     const uint2 raw = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(T) + row * d) + c4);
@@ -106,12 +107,13 @@ __device__ __forceinline__ GroupRef group_at(const SelectParams& p, int64_t row,
 }
 
 // One pass over the row's captured groups, LOAD_B groups per lane in flight.
-//   STORE: elements with ordered key >= kmin are written to key[] / id[] (at most SEL_CAP), any order;
-//   returns how many there are in total.
+//   STORE: elements with score >= fmin are written to key[] / id[] (at most SEL_CAP), any order;
+//   returns how many there are in total.  Scores are compared as floats; -inf never qualifies.
 template <bool STORE>
-__device__ __forceinline__ int scan_groups(const SelectParams& p, int64_t row, int n0, int ng, uint32_t kmin,
+__device__ __forceinline__ int scan_groups(const SelectParams& p, int64_t row, int n0, int ng, float fmin,
                                            uint32_t* key, uint32_t* id, uint32_t lane) {
   int total = 0;
+  const float lim = fmaxf(fmin, -3.0e38f);
   for (int g0 = 0; g0 < ng; g0 += 32 * LOAD_B) {
     float4 a[LOAD_B], b[LOAD_B];
     uint32_t item0[LOAD_B];
@@ -132,12 +134,11 @@ __device__ __forceinline__ int scan_groups(const SelectParams& p, int64_t row, i
     for (int j = 0; j < LOAD_B; ++j) {
       m[j] = 0;
       if (item0[j] != 0xffffffffu) {
-        const float v[8] = {a[j].x, a[j].y, a[j].z, a[j].w, b[j].x, b[j].y, b[j].z, b[j].w};
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const uint32_t kk = f32_to_key(__float_as_uint(v[e] + 0.0f));
-          if (kk >= kmin && kk > KEY_NEG_INF && item0[j] + e < (uint32_t)p.nI) m[j] |= 1u << e;
-        }
+        m[j] = (a[j].x >= lim ? 1u : 0u) | (a[j].y >= lim ? 2u : 0u) | (a[j].z >= lim ? 4u : 0u) | (a[j].w >= lim ? 8u : 0u) |
+               (b[j].x >= lim ? 16u : 0u) | (b[j].y >= lim ? 32u : 0u) | (b[j].z >= lim ? 64u : 0u) | (b[j].w >= lim ? 128u : 0u);
+        // only the last tile's groups can run past the catalogue (zero-filled operand rows score 0)
+        if (item0[j] >= (uint32_t)p.nI) m[j] = 0;
+        else if ((uint32_t)p.nI - item0[j] < 8u) m[j] &= (1u << ((uint32_t)p.nI - item0[j])) - 1u;
       }
       mine += __popc(m[j]);
     }
@@ -154,15 +155,14 @@ __device__ __forceinline__ int scan_groups(const SelectParams& p, int64_t row, i
       total += __shfl_sync(0xffffffffu, incl, 31);
 #pragma unroll
       for (int j = 0; j < LOAD_B; ++j) {
-        if (m[j]) {
-          const float v[8] = {a[j].x, a[j].y, a[j].z, a[j].w, b[j].x, b[j].y, b[j].z, b[j].w};
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            if (m[j] & (1u << e)) {
-              if (pos < SEL_CAP) { key[pos] = f32_to_key(__float_as_uint(v[e] + 0.0f)); id[pos] = item0[j] + e; }
-              ++pos;
-            }
-          }
+        uint32_t mm = m[j];
+        while (mm) {
+          const int e = __ffs(mm) - 1;
+          mm &= mm - 1;
+          const float v = e < 4 ? (e == 0 ? a[j].x : e == 1 ? a[j].y : e == 2 ? a[j].z : a[j].w)
+                                : (e == 4 ? b[j].x : e == 5 ? b[j].y : e == 6 ? b[j].z : b[j].w);
+          if (pos < SEL_CAP) { key[pos] = f32_to_key(__float_as_uint(v + 0.0f)); id[pos] = item0[j] + e; }
+          ++pos;
         }
       }
     }
@@ -181,7 +181,7 @@ __device__ __forceinline__ void report_fail(const SelectParams& p, int64_t row, 
 
 // NJ = float4 chunks of a table row per lane of an 8-lane sub-group: vector path for d <= 32 * NJ, d % 4 == 0.
 // NJ == 0: scalar path for any d (no fused metrics).
-template <int NJ>
+template <int NJ, int DT>
 __global__ void __launch_bounds__(SEL_WARPS * 32)
 select_topk_kernel(const SelectParams p) {
   extern __shared__ __align__(16) uint8_t sel_smem_raw[];
@@ -227,7 +227,7 @@ select_topk_kernel(const SelectParams p) {
   uint32_t thr_key = (thr == -INFINITY) ? 0u : f32_to_key(__float_as_uint(thr + 0.0f));  // effective capture threshold
 
   // ---- A: enumerate ----
-  int ne = scan_groups<true>(p, row, n0, ng, thr_key, key, id, lane);
+  int ne = scan_groups<true>(p, row, n0, ng, thr, key, id, lane);
   if (ne > SEL_CAP) {
     // coarse cut: X = the need-th largest captured score, need = k + seen_u  =>  k-th best unmasked >= X
     const int64_t need64 = (int64_t)k + seen_u;
@@ -236,7 +236,7 @@ select_topk_kernel(const SelectParams p) {
     uint32_t lo = thr_key > KEY_NEG_INF ? thr_key : KEY_NEG_INF + 1, hi = 0xff800000u;  // hi: above every finite key
     while (hi - lo > 1) {
       const uint32_t mid = lo + ((hi - lo) >> 1);
-      const int c = scan_groups<false>(p, row, n0, ng, mid, key, id, lane);
+      const int c = scan_groups<false>(p, row, n0, ng, __uint_as_float(key_to_f32(mid)), key, id, lane);
       if (c >= need) lo = mid; else hi = mid;
       if (c >= need && c <= need + need / 8) break;  // close enough
     }
@@ -244,7 +244,7 @@ select_topk_kernel(const SelectParams p) {
     const uint32_t cut_key = f32_to_key(__float_as_uint((X - margin2) + 0.0f));
     if (cut_key <= thr_key) { report_fail(p, row, lane); return; }
     thr_key = cut_key;
-    ne = scan_groups<true>(p, row, n0, ng, thr_key, key, id, lane);
+    ne = scan_groups<true>(p, row, n0, ng, __uint_as_float(key_to_f32(thr_key)), key, id, lane);
     if (ne > SEL_CAP) { report_fail(p, row, lane); return; }
   }
 
@@ -252,14 +252,16 @@ select_topk_kernel(const SelectParams p) {
   if (seen_u > 0) {
     for (int i = lane; i < ne; i += 32) {
       const int64_t gid = (int64_t)id[i] + p.item_id_offset;
-      int64_t lo = 0, hi = seen_u;
       if (seen_in_smem) {
+        const int32_t g32 = (int32_t)gid;  // seen ids are int32
+        int lo = 0, hi = (int)seen_u;
         while (lo < hi) {
-          const int64_t mid = (lo + hi) >> 1;
-          if ((int64_t)seen_s[mid] < gid) lo = mid + 1; else hi = mid;
+          const int mid = (lo + hi) >> 1;
+          if (seen_s[mid] < g32) lo = mid + 1; else hi = mid;
         }
-        if (lo < seen_u && (int64_t)seen_s[lo] == gid) key[i] = 0;
+        if (lo < (int)seen_u && seen_s[lo] == g32 && gid <= 0x7fffffffLL) key[i] = 0;
       } else {
+        int64_t lo = 0, hi = seen_u;
         while (lo < hi) {
           const int64_t mid = (lo + hi) >> 1;
           if ((int64_t)__ldg(p.seen_items + s0 + mid) < gid) lo = mid + 1; else hi = mid;
@@ -284,7 +286,7 @@ select_topk_kernel(const SelectParams p) {
   if (nv >= k) {
     uint32_t lo = kmin, hi = kmax + 1;
     int c_lo = nv;
-    const int c_ok = k + (k >> 3);
+    const int c_ok = k + max(2, k >> 4);
     while (hi - lo > 1 && c_lo > c_ok) {
       const uint32_t mid = lo + ((hi - lo) >> 1);
       int c = 0;
@@ -323,7 +325,7 @@ select_topk_kernel(const SelectParams p) {
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
       const int c4 = sub + 8 * j;
-      ur[j] = c4 < nvec ? ld4(p.U, p.dtype, row, d, c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      ur[j] = c4 < nvec ? ld4<DT>(p.U, row, d, c4) : make_float4(0.f, 0.f, 0.f, 0.f);
       acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     for (int r0 = 0; r0 < nr; r0 += 8) {
@@ -334,22 +336,18 @@ select_topk_kernel(const SelectParams p) {
       for (int j = 0; j < NJ; ++j) {
         const int c4 = sub + 8 * j;
         if (8 * j < nvec) {
-          va[j] = c4 < nvec ? ld4(p.V, p.dtype, ia, d, c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-          vb[j] = c4 < nvec ? ld4(p.V, p.dtype, ib, d, c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          va[j] = c4 < nvec ? ld4<DT>(p.V, ia, d, c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          vb[j] = c4 < nvec ? ld4<DT>(p.V, ib, d, c4) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
-      float sa = 0.f, sb = 0.f, qa = 0.f, qb = 0.f;
+      float sa = 0.f, sb = 0.f;
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
-        if (8 * j < nvec) {
-          sa = dot4(ur[j], va[j], sa); sb = dot4(ur[j], vb[j], sb);
-          if (want_ild) { qa = dot4(va[j], va[j], qa); qb = dot4(vb[j], vb[j], qb); }
-        }
+        if (8 * j < nvec) { sa = dot4(ur[j], va[j], sa); sb = dot4(ur[j], vb[j], sb); }
       }
       sa = sum8(sa); sb = sum8(sb);
       if (want_ild) {
-        qa = sum8(qa); qb = sum8(qb);
-        const float ia_n = ra < nr ? 1.0f / sqrtf(qa) : 0.f, ib_n = rb < nr ? 1.0f / sqrtf(qb) : 0.f;
+        const float ia_n = ra < nr ? __ldg(p.inv_norm_v + ia) : 0.f, ib_n = rb < nr ? __ldg(p.inv_norm_v + ib) : 0.f;
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
           if (8 * j < nvec) {
@@ -434,15 +432,12 @@ select_topk_kernel(const SelectParams p) {
       }
       if (__ballot_sync(0xffffffffu, loser) == 0) continue;
       float4 va[NJ > 0 ? NJ : 1];
-      float qa = 0.f;
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
         const int c4 = sub + 8 * j;
-        va[j] = (loser && c4 < nvec) ? ld4(p.V, p.dtype, ia, d, c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        qa = dot4(va[j], va[j], qa);
+        va[j] = (loser && c4 < nvec) ? ld4<DT>(p.V, ia, d, c4) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      qa = sum8(qa);
-      const float inv = loser ? 1.0f / sqrtf(qa) : 0.f;
+      const float inv = loser ? __ldg(p.inv_norm_v + ia) : 0.f;
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
         acc[j].x = fmaf(-va[j].x, inv, acc[j].x); acc[j].y = fmaf(-va[j].y, inv, acc[j].y);
@@ -516,15 +511,17 @@ cudaError_t launch_select_topk(const SelectParams& p, cudaStream_t stream) {
   const int64_t grid = (p.nU + SEL_WARPS - 1) / SEL_WARPS;
   const bool vec = (p.d & 3) == 0 && p.d <= 256;  // wider rows take the scalar path (no fused metrics)
   cudaError_t e;
-#define DIVREC_LAUNCH_SELECT(NJ)                                                                                   \
+#define DIVREC_LAUNCH_SELECT(NJ, DT)                                                                               \
   do {                                                                                                             \
-    e = cudaFuncSetAttribute(select_topk_kernel<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
+    e = cudaFuncSetAttribute(select_topk_kernel<NJ, DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
     if (e != cudaSuccess) return e;                                                                                \
-    select_topk_kernel<NJ><<<(unsigned)grid, SEL_WARPS * 32, smem, stream>>>(p);                                   \
+    select_topk_kernel<NJ, DT><<<(unsigned)grid, SEL_WARPS * 32, smem, stream>>>(p);                               \
   } while (0)
-  if (!vec) DIVREC_LAUNCH_SELECT(0);
-  else if (p.d <= 128) DIVREC_LAUNCH_SELECT(4);
-  else DIVREC_LAUNCH_SELECT(8);
+  if (!vec) DIVREC_LAUNCH_SELECT(0, 0);
+  else if (p.dtype == 0 && p.d <= 128) DIVREC_LAUNCH_SELECT(4, 0);
+  else if (p.dtype == 0) DIVREC_LAUNCH_SELECT(8, 0);
+  else if (p.d <= 128) DIVREC_LAUNCH_SELECT(4, 1);
+  else DIVREC_LAUNCH_SELECT(8, 1);
 #undef DIVREC_LAUNCH_SELECT
   count_launch();
   return cudaGetLastError();
