@@ -139,7 +139,7 @@ def bench_ours(args):
     def step():
         s, i, ild = run_step_device(N, Ud, Vd, rpd, itd, k, nI, counts)
         ild_sum.copy_(ild.sum(dtype=torch.float64).reshape(1))
-        if dist is not None:  # the path's only exchange: metric reductions
+        if dist is not None:  # the path's only exchange: the metric reductions (as divrec.parallel.recommend_user_sharded)
             dist.all_reduce(counts)
             dist.all_reduce(ild_sum)
         return s, i, ild

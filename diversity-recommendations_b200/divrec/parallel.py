@@ -1,0 +1,92 @@
+"""Multi-GPU host logic: one process per GPU, torch.distributed (NCCL over NVLink) for the plumbing.
+
+The path shards two ways:
+  * users sharded, item table replicated -- no data-path collective; the metric reductions are one all_reduce
+    of the [I] coverage histogram and one of the (ILD sum, user count) pair;
+  * item table sharded (large catalogues) -- every rank scores all query users against its slice, one
+    all_gather of the per-shard [U,k] (score, id) lists, then the n-way merge kernel;
+  * BPR -- triples partitioned by user shard (user gradients stay local), item gradient all_reduce.
+
+`kernels` is the compute backend (default: the ctypes binding of libdivrec_b200.so).  It is a parameter only
+so that the sharding / collective logic can be exercised on CPU with the gloo backend in tests; the product
+path never substitutes it.
+"""
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def _kernels(kernels):
+    if kernels is not None:
+        return kernels
+    from . import _native
+    return _native
+
+
+def _world(group) -> Tuple[int, int]:
+    if not (dist.is_available() and dist.is_initialized()):
+        return 0, 1
+    return dist.get_rank(group), dist.get_world_size(group)
+
+
+def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous balanced ranges: the first n % world shards get one extra element."""
+    base, extra = divmod(n, world)
+    a = rank * base + min(rank, extra)
+    return a, a + base + (1 if rank < extra else 0)
+
+
+def recommend_user_sharded(U: torch.Tensor, V: torch.Tensor, seen_rowptr: Optional[torch.Tensor],
+                           seen_items: Optional[torch.Tensor], k: int, group=None, kernels=None):
+    """Score this rank's contiguous range of users against the replicated item table.
+    Returns (items [n_local,k], scores [n_local,k], ild_local [n_local], ild_mean_global, coverage_counts_global, (a,b))."""
+    K = _kernels(kernels)
+    rank, world = _world(group)
+    nU = U.shape[0]
+    a, b = shard_range(nU, rank, world)
+    rp = None
+    if seen_rowptr is not None:
+        rp = seen_rowptr[a:b + 1].contiguous()  # absolute offsets into the (replicated) seen_items array
+    scores, items, ild, counts = K.score_topk_metrics(U[a:b].contiguous(), V, k, rp, seen_items)
+    stat = torch.stack([ild.sum(dtype=torch.float64), torch.tensor(float(b - a), dtype=torch.float64, device=ild.device)])
+    if world > 1:
+        dist.all_reduce(counts, group=group)
+        dist.all_reduce(stat, group=group)
+    return items, scores, ild, (stat[0] / stat[1]).to(torch.float32), counts, (a, b)
+
+
+def recommend_item_sharded(U: torch.Tensor, V_shard: torch.Tensor, shard_offset: int, k: int,
+                           seen_rowptr: Optional[torch.Tensor] = None, seen_items: Optional[torch.Tensor] = None,
+                           group=None, kernels=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Every rank holds items [shard_offset, shard_offset + len(V_shard)) and all query users.
+    Local top-k with global ids -> all_gather -> merge (ties -> lowest id; deterministic because the merge
+    uses the total order (score desc, id asc)).  Returns the global (scores [U,k], items [U,k]) on every rank."""
+    K = _kernels(kernels)
+    rank, world = _world(group)
+    s, i = K.score_topk(U, V_shard, k, seen_rowptr, seen_items, item_id_offset=shard_offset)
+    if world == 1:
+        return s, i
+    gs = [torch.empty_like(s) for _ in range(world)]
+    gi = [torch.empty_like(i) for _ in range(world)]
+    dist.all_gather(gs, s.contiguous(), group=group)
+    dist.all_gather(gi, i.contiguous(), group=group)
+    return K.topk_merge(torch.stack(gs), torch.stack(gi))
+
+
+def bpr_step_sharded(U: torch.Tensor, V: torch.Tensor, u: torch.Tensor, p: torch.Tensor, n: torch.Tensor,
+                     global_batch: int, group=None, kernels=None):
+    """One BPR forward/backward on this rank's triples (its users only).  Gradients are those of the GLOBAL
+    mean loss: every rank scales by 1 / global_batch, the item-table gradient is summed over ranks, the user
+    gradient needs no communication because a user's triples live on one rank.
+    Returns (loss_global, auc_global, gU_local_rows_dense, gV_global)."""
+    K = _kernels(kernels)
+    rank, world = _world(group)
+    pos, neg, loss_sum, auc_sum = K.bpr_fwd(U, V, u, p, n)
+    gU, gV = torch.zeros_like(U), torch.zeros_like(V)
+    K.bpr_bwd(U, V, u, p, n, pos, neg, 1.0 / global_batch, gU, gV)
+    stat = torch.stack([loss_sum.reshape(()).to(torch.float64), auc_sum.reshape(()).to(torch.float64)])
+    if world > 1:
+        dist.all_reduce(gV, group=group)
+        dist.all_reduce(stat, group=group)
+    return (stat[0] / global_batch).to(torch.float32), (stat[1] / global_batch).to(torch.float32), gU, gV

@@ -1,0 +1,126 @@
+"""The N > 1 host logic (sharding, collectives, merge order) with 2 ranks over gloo on CPU.  The compute
+backend is substituted by the oracle HERE ONLY (tests may use the oracle); the collectives, shard ranges and
+result layout are the product code in divrec/parallel.py."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import divrec_oracle as O
+
+
+class OracleKernels:
+    """CPU stand-in with the signatures of divrec._native used by divrec.parallel."""
+
+    @staticmethod
+    def score_topk(U, V, k, seen_rowptr=None, seen_items=None, item_id_offset=0):
+        rp, it = seen_rowptr, seen_items
+        if rp is not None and it is not None:
+            # keep only the seen items that fall into this shard, re-based to local ids
+            rp = rp - rp[0]
+            lo, hi = int(seen_rowptr[0]), int(seen_rowptr[-1])
+            seg = it[lo:hi].long() - item_id_offset
+            rows = torch.repeat_interleave(torch.arange(U.shape[0]), (rp[1:] - rp[:-1]))
+            ok = (seg >= 0) & (seg < V.shape[0])
+            cnt = torch.bincount(rows[ok], minlength=U.shape[0])
+            rp = torch.zeros(U.shape[0] + 1, dtype=torch.int64)
+            rp[1:] = torch.cumsum(cnt, 0)
+            it = seg[ok].int()
+        i, s = O.recommendations_dense(U, V, rp, it, k)
+        return s, torch.where(i >= 0, i + item_id_offset, i)
+
+    @staticmethod
+    def score_topk_metrics(U, V, k, seen_rowptr=None, seen_items=None):
+        rp = None if seen_rowptr is None else seen_rowptr - seen_rowptr[0]
+        it = None if seen_items is None else seen_items[int(seen_rowptr[0]):int(seen_rowptr[-1])]
+        i, s = O.recommendations_dense(U, V, rp, it, k)
+        return s, i, O.ild_cosine(i, V), O.coverage_counts(i, V.shape[0]).int()
+
+    @staticmethod
+    def topk_merge(gs, gi):
+        return O.topk_merge(gs, gi, gs.shape[2])
+
+    @staticmethod
+    def bpr_fwd(U, V, u, p, n):
+        pos, neg, loss, auc = O.bpr_forward(U, V, u, p, n)
+        B = u.numel()
+        return pos, neg, (loss * B).reshape(1), (auc * B).round().int().reshape(1)
+
+    @staticmethod
+    def bpr_bwd(U, V, u, p, n, pos, neg, scale, gU, gV):
+        a, b = O.bpr_backward(U, V, u, p, n, upstream=scale * u.numel())
+        gU += a
+        gV += b
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from divrec import parallel
+    gen = torch.Generator().manual_seed(0)
+    nU, nI, d, k = 101, 600, 32, 20
+    U, V = O.make_embeddings(nU, d, "grid", gen), O.make_embeddings(nI, d, "grid", gen)
+    seen = O.make_seen(nU, nI, 3000, gen)
+    rowptr, items = O.seen_csr(seen, nU)
+    full_i, full_s = O.recommendations_dense(U, V, rowptr, items, k)
+    K = OracleKernels()
+    # users sharded
+    it, sc, ild, ild_mean, counts, (a, b) = parallel.recommend_user_sharded(U, V, rowptr, items, k, kernels=K)
+    assert (a, b) == parallel.shard_range(nU, rank, world)
+    assert torch.equal(it, full_i[a:b]) and torch.equal(sc, full_s[a:b])
+    assert torch.equal(counts.long(), O.coverage_counts(full_i, nI))          # all-reduced histogram = global
+    assert abs(float(ild_mean) - float(O.ild_cosine(full_i, V).double().mean())) < 1e-6
+    # items sharded
+    ia, ib = parallel.shard_range(nI, rank, world)
+    ms, mi = parallel.recommend_item_sharded(U, V[ia:ib].contiguous(), ia, k, rowptr, items, kernels=K)
+    assert torch.equal(mi, full_i) and torch.equal(ms, full_s)
+    # BPR: triples partitioned by user shard
+    B = 400
+    u = torch.randint(0, nU, (B,), generator=gen); p = torch.randint(0, nI, (B,), generator=gen); n = torch.randint(0, nI, (B,), generator=gen)
+    mine = (u >= a) & (u < b)
+    Ug = O.make_embeddings(nU, d, "gauss", gen); Vg = O.make_embeddings(nI, d, "gauss", gen)
+    loss, auc, gU, gV = parallel.bpr_step_sharded(Ug, Vg, u[mine], p[mine], n[mine], B, kernels=K)
+    _, _, o_loss, o_auc = O.bpr_forward(Ug, Vg, u, p, n)
+    o_gU, o_gV = O.bpr_backward(Ug, Vg, u, p, n)
+    assert abs(float(loss) - float(o_loss)) < 1e-5 * abs(float(o_loss)) and abs(float(auc) - float(o_auc)) < 1e-6
+    torch.testing.assert_close(gV, o_gV, rtol=0, atol=1e-6 * float(o_gV.abs().max()))
+    torch.testing.assert_close(gU[a:b], o_gU[a:b], rtol=0, atol=1e-6 * float(o_gU.abs().max()))
+    assert float(gU[:a].abs().sum()) == 0 and float(gU[b:].abs().sum()) == 0    # other shards' users untouched
+    dist.barrier()
+    dist.destroy_process_group()
+    out.put(rank)
+
+
+def test_two_rank_sharding_over_gloo():
+    world = 2
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, out)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    for pr in procs:
+        pr.join(120)
+    assert all(pr.exitcode == 0 for pr in procs), [pr.exitcode for pr in procs]
+    assert sorted(out.get(timeout=5) for _ in range(world)) == [0, 1]
+
+
+def test_shard_range_covers_everything():
+    from divrec.parallel import shard_range
+    for n in (0, 1, 7, 100, 138493):
+        for w in (1, 2, 3, 8):
+            edges = [shard_range(n, r, w) for r in range(w)]
+            assert edges[0][0] == 0 and edges[-1][1] == n
+            assert all(edges[i][1] == edges[i + 1][0] for i in range(w - 1))
+            sizes = [b - a for a, b in edges]
+            assert max(sizes) - min(sizes) <= 1
