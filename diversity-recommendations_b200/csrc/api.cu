@@ -84,9 +84,9 @@ static WsLayout ws_layout(int64_t nU, int64_t nI, int d, int dtype) {
   w.offB = off; if (w.convB) off += align_up((size_t)nI * w.K * 2, 1024);
   w.offNormU = off; off += align_up(cpad * sizeof(float), 1024);
   w.offInvV = off; off += align_up((size_t)nI * sizeof(float), 1024);
-  w.offListS = off; off += align_up(cpad * 2 * LIST_CAP * GROUP * sizeof(float), 1024);
-  w.offListI = off; off += align_up(cpad * 2 * LIST_CAP * sizeof(uint32_t), 1024);
-  w.offCounts = off; off += align_up(cpad * 2 * sizeof(int32_t), 1024);
+  w.offListS = off; off += align_up(cpad * LISTS_PER_ROW * LIST_CAP * GROUP * sizeof(float), 1024);
+  w.offListI = off; off += align_up(cpad * LISTS_PER_ROW * LIST_CAP * sizeof(uint32_t), 1024);
+  w.offCounts = off; off += align_up(cpad * LISTS_PER_ROW * sizeof(int32_t), 1024);
   w.offThr = off; off += align_up(cpad * sizeof(float), 1024);
   w.offFail = off; off += align_up(cpad * sizeof(int32_t), 1024);
   w.offScalars = off; off += 1024;  // u32[0..1] amax bits (U,V), i32[2..3] scale exps, u32[4] max item norm, i32[5] fail count
@@ -248,7 +248,7 @@ static int score_topk_impl(const void* U, const void* V, int64_t nU, int64_t nI,
       prof_mark(PROF_FILTER, 1, st);
     } else {
       // DIVREC_MODE_SIMT: no candidate lists; select only enqueues every row for the exact kernel
-      e = cudaMemsetAsync(ws + w.offCounts, 0, align_up((size_t)cu, 128) * 2 * sizeof(int32_t), st);
+      e = cudaMemsetAsync(ws + w.offCounts, 0, align_up((size_t)cu, 128) * LISTS_PER_ROW * sizeof(int32_t), st);
       if (e != cudaSuccess) return cuda_fail(e, "memset counts");
     }
     prof_mark(PROF_SELECT, 0, st);

@@ -7,7 +7,8 @@
 
 namespace divrec {
 
-constexpr int LIST_CAP = 512;        // candidate groups per (user row, column half)
+constexpr int LIST_CAP = 256;        // candidate groups per list; a user row owns LISTS_PER_ROW lists
+constexpr int LISTS_PER_ROW = 4;     // (column half of a tile) x (tile parity)
 constexpr int GROUP = 8;             // consecutive item columns appended together
 constexpr int N_SAMPLE = 16;         // item tiles scored first to seed the per-row threshold hint
 constexpr int HINT_MIN_TILES = 32;   // catalogues with fewer 128-item tiles keep every group (no hint)
@@ -26,9 +27,9 @@ struct FilterParams {
   // filled by the launcher
   int n_ublocks, n_tiles, b_stages, n_sample, sample_stride;
   const int64_t* seen_rowptr;  // [nU+1] or null (only the per-row counts are used here)
-  float* list_scores;          // [nU_pad][2][cap][GROUP]  tensor-core scores (scaled units)
-  uint32_t* list_item0;        // [nU_pad][2][cap]         local id of the first item of each group
-  int32_t* list_count;         // [nU_pad][2]              groups appended; cap + 1 = overflow
+  float* list_scores;          // [nU_pad][4][cap][GROUP]  tensor-core scores (scaled units)
+  uint32_t* list_item0;        // [nU_pad][4][cap]         local id of the first item of each group
+  int32_t* list_count;         // [nU_pad][4]              groups appended; cap + 1 = overflow
   float* thr_out;              // [nU_pad]                 threshold hint used for the row (scaled units, -inf = none)
 };
 

@@ -25,11 +25,14 @@
 // overflowed, to the exact SIMT kernel in rescue.cu.  Small catalogues (< HINT_MIN_TILES tiles) skip
 // phase 1 and keep every group.
 //
-// Block roles (384 threads, 1 CTA / SM, persistent over user blocks):
-//   warps 0-7  epilogue: warp w reads TMEM lanes 32*(w%4).. and columns 64*(w/4).. of every tile
-//   warp  8    TMA producer (one lane): A block once per user block, B k-blocks through a ring
-//   warp  9    MMA issuer (one lane): tcgen05.mma kind::f16, M=128 N=128 K=16, fp32 accum in TMEM
-//   warp  10   TMEM allocator
+// Block roles (608 threads, 1 CTA / SM, persistent over user blocks):
+//   warps 0-15 epilogue in two sets of 8: set s = w/8 takes the item tiles of parity s, so four warps per
+//              scheduler partition hide each other's TMEM-load and store latency; inside a set warp w reads
+//              TMEM lanes 32*(w%4).. and columns 64*((w/4)%2).. of its tiles.  A user row therefore owns four
+//              candidate lists (column half x tile parity).
+//   warp  16   TMA producer (one lane): A block once per user block, B k-blocks through a ring
+//   warp  17   MMA issuer (one lane): tcgen05.mma kind::f16, M=128 N=128 K=16, fp32 accum in TMEM
+//   warp  18   TMEM allocator
 #include "common.cuh"
 #include "kernels.h"
 
@@ -43,9 +46,11 @@ constexpr int BK = 64;             // 16-bit elements per k-block = one 128-byte
 constexpr int UMMA_K = 16;         // K per tcgen05.mma for 16-bit inputs
 constexpr int SLAB_BYTES = BM * BK * 2;  // 16 KB: 128 rows x 128 B
 constexpr int ACC_STAGES = 4;      // 4 x 128 fp32 columns = all 512 TMEM columns
-constexpr int EPI_WARPS = 8;
+constexpr int EPI_WARPS = 8;       // warps that consume one tile (one set)
+constexpr int EPI_SETS = 2;
 constexpr int EPI_THREADS = EPI_WARPS * 32;
-constexpr int NUM_THREADS = 384;
+constexpr int W_TMA = EPI_WARPS * EPI_SETS, W_MMA = W_TMA + 1, W_ALLOC = W_TMA + 2;
+constexpr int NUM_THREADS = (W_ALLOC + 1) * 32;
 constexpr int COLS_PER_THREAD = BN / 2;
 constexpr int GROUPS_PER_TILE = COLS_PER_THREAD / GROUP;  // 8 groups of 8 columns per thread per tile
 constexpr int HS = 2 * N_SAMPLE;   // 32-column group maxima per thread in the hint phase
@@ -104,8 +109,8 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     mbar_init(smem_u32(&sm->a_empty), 1);
     fence_mbar_init();
   }
-  if (warp == 8 && lane == 0) { tma_prefetch_desc(&tmap_a); tma_prefetch_desc(&tmap_b); }
-  if (warp == 10) { tmem_alloc(smem_u32(&sm->tmem_base), ACC_STAGES * BN); tmem_relinquish(); }
+  if (warp == W_TMA && lane == 0) { tma_prefetch_desc(&tmap_a); tma_prefetch_desc(&tmap_b); }
+  if (warp == W_ALLOC) { tmem_alloc(smem_u32(&sm->tmem_base), ACC_STAGES * BN); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -115,7 +120,7 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const int n_sample = p.n_sample;
   const int n_sched = n_sample + p.n_tiles;
 
-  if (warp == 8) {
+  if (warp == W_TMA) {
     // ================= TMA producer =================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0, a_phase = 0;
@@ -140,7 +145,7 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == W_MMA) {
     // ================= MMA issuer =================
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_f16(p.fmt, BM, BN);
@@ -172,60 +177,64 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         umma_commit(smem_u32(&sm->a_empty));
       }
     }
-  } else if (warp < EPI_WARPS) {
+  } else if (warp < EPI_WARPS * EPI_SETS) {
     // ================= epilogue =================
-    const int q = warp & 3;   // TMEM lane quarter
-    const int h = warp >> 2;  // column half of every tile
+    const int q = warp & 3;          // TMEM lane quarter
+    const int h = (warp >> 2) & 1;   // column half of a tile
+    const int pset = warp >> 3;      // tile parity this warp consumes
     const int row_local = q * 32 + lane;
-    const int et = threadIdx.x;  // 0..255
-    uint32_t acc = 0, acc_phase = 0;
-    for (int ub = blockIdx.x; ub < p.n_ublocks; ub += gridDim.x) {
+    const int et = (warp & 7) * 32 + lane;  // 0..255 inside the set
+    uint32_t base_seq = 0;                   // tiles issued before this user block (all sets count every tile)
+    for (int ub = blockIdx.x; ub < p.n_ublocks; ub += gridDim.x, base_seq += (uint32_t)n_sched) {
       const int64_t row = (int64_t)ub * BM + row_local;
       const bool valid_row = row < p.nU;
       float thr = valid_row ? -INFINITY : INFINITY;
 
-      // ---------------- phase 1: threshold hint from sampled tiles ----------------
+      // ---------------- phase 1: threshold hint from sampled tiles (set 0 scores them, both sets use the result) ----------------
       if (n_sample > 0) {
-        float hs[HS];
+        if (pset == 0) {
+          float hs[HS];
 #pragma unroll
-        for (int s = 0; s < N_SAMPLE; ++s) {
-          mbar_wait(smem_u32(&sm->acc_full[acc]), acc_phase);
-          tc_fence_after();
-          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + h * COLS_PER_THREAD;
-          uint32_t v0[32], v1[32];
-          tmem_ld_32x32b_x32(taddr, v0);
-          tmem_ld_32x32b_x32(taddr + 32, v1);
-          tmem_wait_ld();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(&sm->acc_empty[acc]));
-          if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
-          hs[2 * s] = max32(v0);
-          hs[2 * s + 1] = max32(v1);
-        }
-        // bitonic sort, descending, fully unrolled in registers
+          for (int s = 0; s < N_SAMPLE; ++s) {
+            const uint32_t seq = base_seq + s, acc = seq & (ACC_STAGES - 1), acc_phase = (seq / ACC_STAGES) & 1;
+            mbar_wait(smem_u32(&sm->acc_full[acc]), acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + h * COLS_PER_THREAD;
+            uint32_t v0[32];
+            tmem_ld_32x32b_x32(taddr, v0);
+            tmem_wait_ld();
+            hs[2 * s] = max32(v0);
+            tmem_ld_32x32b_x32(taddr + 32, v0);
+            tmem_wait_ld();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&sm->acc_empty[acc]));
+            hs[2 * s + 1] = max32(v0);
+          }
+          // bitonic sort, descending, fully unrolled in registers
 #pragma unroll
-        for (int size = 2; size <= HS; size <<= 1) {
+          for (int size = 2; size <= HS; size <<= 1) {
 #pragma unroll
-          for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
 #pragma unroll
-            for (int i = 0; i < HS; ++i) {
-              const int j = i ^ stride;
-              if (j > i) {
-                const bool desc = (i & size) == 0;
-                const float a = hs[i], b = hs[j];
-                const float mx = fmaxf(a, b), mn = fminf(a, b);
-                hs[i] = desc ? mx : mn;
-                hs[j] = desc ? mn : mx;
+              for (int i = 0; i < HS; ++i) {
+                const int j = i ^ stride;
+                if (j > i) {
+                  const bool desc = (i & size) == 0;
+                  const float a = hs[i], b = hs[j];
+                  const float mx = fmaxf(a, b), mn = fminf(a, b);
+                  hs[i] = desc ? mx : mn;
+                  hs[j] = desc ? mn : mx;
+                }
               }
             }
           }
-        }
 #pragma unroll
-        for (int i = 0; i < HS; ++i) sm->sorted[i][et] = hs[i];
-        asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+          for (int i = 0; i < HS; ++i) sm->sorted[i][et] = hs[i];
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS * EPI_SETS) : "memory");
         if (valid_row) {
-          // r-th largest of the row's 2*HS group maxima (this thread's and its partner's in the other half)
+          // r-th largest of the row's 2*HS group maxima (both column halves)
           int64_t seen_u = 0;
           if (p.seen_rowptr != nullptr) seen_u = p.seen_rowptr[row + 1] - p.seen_rowptr[row];
           const float f0 = ((float)p.k + (float)seen_u + 8.0f) / (float)p.nI;  // needed fraction of the catalogue
@@ -236,26 +245,29 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             r = (int)ceilf(n * pg + 3.0f * sqrtf(n * pg * (1.0f - pg))) + 1;
           }
           if (r <= 2 * HS - 4) {
-            const int partner = et ^ 128;
+            const int ea = row_local, eb = row_local + 128;  // the row's two column halves in `sorted`
             int i = 0, j = 0;
             float pick = INFINITY;
             for (int c = 0; c < r; ++c) {
-              const float a = i < HS ? sm->sorted[i][et] : -INFINITY;
-              const float b = j < HS ? sm->sorted[j][partner] : -INFINITY;
+              const float a = i < HS ? sm->sorted[i][ea] : -INFINITY;
+              const float b = j < HS ? sm->sorted[j][eb] : -INFINITY;
               if (a >= b) { pick = a; ++i; } else { pick = b; ++j; }
             }
             thr = pick;
           }
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");  // sorted[] is reused by the next block
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS * EPI_SETS) : "memory");  // sorted[] is reused by the next block
       }
 
-      // ---------------- phase 2: fixed-threshold group filter ----------------
-      float* Ls = p.list_scores + ((size_t)row * 2 + h) * ((size_t)p.cap * GROUP);
-      uint32_t* Li = p.list_item0 + ((size_t)row * 2 + h) * (size_t)p.cap;
-      int cnt = 0;
-      const int cap_lim = p.cap - GROUPS_PER_TILE;
-      for (int t = 0; t < p.n_tiles; ++t) {
+      // ---------------- phase 2: fixed-threshold group filter over this set's tiles ----------------
+      // block-relative 32-bit offsets (a user block's lists span 128 * 4 * cap groups) on uniform 64-bit bases
+      float* const Ls_blk = p.list_scores + (size_t)ub * (BM * 4) * ((size_t)p.cap * GROUP);
+      uint32_t* const Li_blk = p.list_item0 + (size_t)ub * (BM * 4) * (size_t)p.cap;
+      const uint32_t goff = (uint32_t)((row_local * 4 + h * 2 + pset) * p.cap);
+      uint32_t cnt = 0;
+      const uint32_t cap_lim = (uint32_t)(p.cap - GROUPS_PER_TILE);
+      for (int t = pset; t < p.n_tiles; t += EPI_SETS) {
+        const uint32_t seq = base_seq + (uint32_t)(n_sample + t), acc = seq & (ACC_STAGES - 1), acc_phase = (seq / ACC_STAGES) & 1;
         mbar_wait(smem_u32(&sm->acc_full[acc]), acc_phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + h * COLS_PER_THREAD;
@@ -266,34 +278,33 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&sm->acc_empty[acc]));
-        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
 
-        if (cnt > cap_lim) { thr = INFINITY; cnt = p.cap + 1; }  // overflow: stop, the row goes to the rescue kernel
+        if (cnt > cap_lim) { thr = INFINITY; cnt = (uint32_t)p.cap + 1; }  // overflow: stop, the row goes to the rescue kernel
         const uint32_t item0 = (uint32_t)(t * BN + h * COLS_PER_THREAD);
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          if (max8(&v0[8 * g]) >= thr) {
-            float4* dst = reinterpret_cast<float4*>(Ls + (size_t)cnt * GROUP);
-            dst[0] = make_float4(__uint_as_float(v0[8 * g + 0]), __uint_as_float(v0[8 * g + 1]), __uint_as_float(v0[8 * g + 2]), __uint_as_float(v0[8 * g + 3]));
-            dst[1] = make_float4(__uint_as_float(v0[8 * g + 4]), __uint_as_float(v0[8 * g + 5]), __uint_as_float(v0[8 * g + 6]), __uint_as_float(v0[8 * g + 7]));
-            Li[cnt] = item0 + 8 * g;
-            ++cnt;
-          }
-        }
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          if (max8(&v1[8 * g]) >= thr) {
-            float4* dst = reinterpret_cast<float4*>(Ls + (size_t)cnt * GROUP);
-            dst[0] = make_float4(__uint_as_float(v1[8 * g + 0]), __uint_as_float(v1[8 * g + 1]), __uint_as_float(v1[8 * g + 2]), __uint_as_float(v1[8 * g + 3]));
-            dst[1] = make_float4(__uint_as_float(v1[8 * g + 4]), __uint_as_float(v1[8 * g + 5]), __uint_as_float(v1[8 * g + 6]), __uint_as_float(v1[8 * g + 7]));
-            Li[cnt] = item0 + 32 + 8 * g;
-            ++cnt;
-          }
+        for (int g = 0; g < GROUPS_PER_TILE; ++g) {
+          const uint32_t* v = g < 4 ? &v0[8 * g] : &v1[8 * (g - 4)];
+          const float m = max8(v);
+          float* dst = Ls_blk + (size_t)(goff + cnt) * GROUP;
+          uint32_t* idst = Li_blk + (goff + cnt);
+          // branch-free append: predicated 128-bit stores of the whole group + its first item id
+          asm volatile(
+              "{\n"
+              ".reg .pred p;\n"
+              "setp.ge.f32 p, %0, %1;\n"
+              "@p st.global.v4.b32 [%2], {%4, %5, %6, %7};\n"
+              "@p st.global.v4.b32 [%2+16], {%8, %9, %10, %11};\n"
+              "@p st.global.b32 [%3], %12;\n"
+              "}\n"
+              ::"f"(m), "f"(thr), "l"(dst), "l"(idst), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]),
+                "r"(v[6]), "r"(v[7]), "r"(item0 + 8 * g)
+              : "memory");
+          cnt += (m >= thr) ? 1u : 0u;
         }
       }
       if (valid_row) {
-        p.list_count[row * 2 + h] = cnt;  // cap + 1 = overflowed
-        if (h == 0) p.thr_out[row] = thr;  // both halves computed the same hint (an overflowed half reports via its count)
+        p.list_count[row * 4 + h * 2 + pset] = (int32_t)cnt;  // cap + 1 = overflowed
+        if (h == 0 && pset == 0) p.thr_out[row] = thr;         // every owner of the row computed the same hint
       }
     }
   }
@@ -301,7 +312,7 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   // ---- teardown ----
   tc_fence_before();
   __syncthreads();
-  if (warp == 10) { tc_fence_after(); tmem_dealloc(tmem_base, ACC_STAGES * BN); }
+  if (warp == W_ALLOC) { tc_fence_after(); tmem_dealloc(tmem_base, ACC_STAGES * BN); }
 }
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

@@ -99,10 +99,11 @@ __device__ __forceinline__ float sum8(float v) {
 }
 
 struct GroupRef { const float* s; uint32_t item0; };
-__device__ __forceinline__ GroupRef group_at(const SelectParams& p, int64_t row, int n0, int g) {
-  const int h = g < n0 ? 0 : 1;
-  const int idx = g - (h ? n0 : 0);
-  const size_t base = ((size_t)row * 2 + h) * (size_t)p.cap + idx;
+// the row's LISTS_PER_ROW lists as one virtual sequence; e1/e2/e3 = end offsets of lists 0/1/2 in it
+__device__ __forceinline__ GroupRef group_at(const SelectParams& p, int64_t row, int e1, int e2, int e3, int g) {
+  const int l = (g >= e1) + (g >= e2) + (g >= e3);
+  const int idx = g - (l == 0 ? 0 : l == 1 ? e1 : l == 2 ? e2 : e3);
+  const size_t base = ((size_t)row * LISTS_PER_ROW + l) * (size_t)p.cap + idx;
   return GroupRef{p.list_scores + base * GROUP, p.list_item0[base]};
 }
 
@@ -110,7 +111,7 @@ __device__ __forceinline__ GroupRef group_at(const SelectParams& p, int64_t row,
 //   STORE: elements with score >= fmin are written to key[] / id[] (at most SEL_CAP), any order;
 //   returns how many there are in total.  Scores are compared as floats; -inf never qualifies.
 template <bool STORE>
-__device__ __forceinline__ int scan_groups(const SelectParams& p, int64_t row, int n0, int ng, float fmin,
+__device__ __forceinline__ int scan_groups(const SelectParams& p, int64_t row, int e1, int e2, int e3, int ng, float fmin,
                                            uint32_t* key, uint32_t* id, uint32_t lane) {
   int total = 0;
   const float lim = fmaxf(fmin, -3.0e38f);
@@ -122,7 +123,7 @@ __device__ __forceinline__ int scan_groups(const SelectParams& p, int64_t row, i
       const int g = g0 + j * 32 + lane;
       item0[j] = 0xffffffffu;
       if (g < ng) {
-        const GroupRef gr = group_at(p, row, n0, g);
+        const GroupRef gr = group_at(p, row, e1, e2, e3, g);
         item0[j] = gr.item0;
         a[j] = *reinterpret_cast<const float4*>(gr.s);
         b[j] = *reinterpret_cast<const float4*>(gr.s + 4);
@@ -198,10 +199,9 @@ select_topk_kernel(const SelectParams p) {
   unsigned long long* chunk = sm->chunk[w];
   const int k = p.k;
 
-  const int n0 = p.list_count[row * 2 + 0];
-  const int n1 = p.list_count[row * 2 + 1];
-  if (p.force_fail || n0 > p.cap || n1 > p.cap) { report_fail(p, row, lane); return; }
-  const int ng = n0 + n1;
+  const int4 nl = *reinterpret_cast<const int4*>(p.list_count + row * LISTS_PER_ROW);
+  if (p.force_fail || nl.x > p.cap || nl.y > p.cap || nl.z > p.cap || nl.w > p.cap) { report_fail(p, row, lane); return; }
+  const int le1 = nl.x, le2 = le1 + nl.y, le3 = le2 + nl.z, ng = le3 + nl.w;
 
   int64_t s0 = 0, s1 = 0;
   if (p.seen_rowptr != nullptr) { s0 = p.seen_rowptr[row]; s1 = p.seen_rowptr[row + 1]; }
@@ -227,7 +227,7 @@ select_topk_kernel(const SelectParams p) {
   uint32_t thr_key = (thr == -INFINITY) ? 0u : f32_to_key(__float_as_uint(thr + 0.0f));  // effective capture threshold
 
   // ---- A: enumerate ----
-  int ne = scan_groups<true>(p, row, n0, ng, thr, key, id, lane);
+  int ne = scan_groups<true>(p, row, le1, le2, le3, ng, thr, key, id, lane);
   if (ne > SEL_CAP) {
     // coarse cut: X = the need-th largest captured score, need = k + seen_u  =>  k-th best unmasked >= X
     const int64_t need64 = (int64_t)k + seen_u;
@@ -236,7 +236,7 @@ select_topk_kernel(const SelectParams p) {
     uint32_t lo = thr_key > KEY_NEG_INF ? thr_key : KEY_NEG_INF + 1, hi = 0xff800000u;  // hi: above every finite key
     while (hi - lo > 1) {
       const uint32_t mid = lo + ((hi - lo) >> 1);
-      const int c = scan_groups<false>(p, row, n0, ng, __uint_as_float(key_to_f32(mid)), key, id, lane);
+      const int c = scan_groups<false>(p, row, le1, le2, le3, ng, __uint_as_float(key_to_f32(mid)), key, id, lane);
       if (c >= need) lo = mid; else hi = mid;
       if (c >= need && c <= need + need / 8) break;  // close enough
     }
@@ -244,7 +244,7 @@ select_topk_kernel(const SelectParams p) {
     const uint32_t cut_key = f32_to_key(__float_as_uint((X - margin2) + 0.0f));
     if (cut_key <= thr_key) { report_fail(p, row, lane); return; }
     thr_key = cut_key;
-    ne = scan_groups<true>(p, row, n0, ng, __uint_as_float(key_to_f32(thr_key)), key, id, lane);
+    ne = scan_groups<true>(p, row, le1, le2, le3, ng, __uint_as_float(key_to_f32(thr_key)), key, id, lane);
     if (ne > SEL_CAP) { report_fail(p, row, lane); return; }
   }
 
