@@ -28,6 +28,8 @@ static int cuda_fail(cudaError_t e, const char* where) {
 // ---- optional per-kernel timing (bench.py roofline): CUDA events on the launching stream ----
 enum ProfSlot { PROF_PREP = 0, PROF_FILTER = 1, PROF_SELECT = 2, PROF_ILD = 3, PROF_COVERAGE = 4, PROF_RESCUE = 5, PROF_SLOTS = 6 };
 static std::atomic<int> g_prof_on{0};
+static std::atomic<int> g_debug_mode{0};
+static std::atomic<long long*> g_filter_stats{nullptr};
 static cudaEvent_t g_prof_ev[PROF_SLOTS][2];
 static bool g_prof_made = false;
 static bool g_prof_set[PROF_SLOTS];
@@ -122,6 +124,8 @@ const char* divrec_last_error(void) { return g_err; }
 int64_t divrec_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 void divrec_set_profiling(int on) { g_prof_on.store(on ? 1 : 0); }
+void divrec_debug_filter_mode(int mode) { g_debug_mode.store(mode); }
+void divrec_debug_filter_stats(void* dev_buf) { g_filter_stats.store(reinterpret_cast<long long*>(dev_buf)); }
 
 int divrec_profile_read(float* ms_out, int n) {
   if (!ms_out || n <= 0) return fail(DIVREC_ERR_ARG, "profile_read: bad argument");
@@ -236,7 +240,7 @@ static int score_topk_impl(const void* U, const void* V, int64_t nU, int64_t nI,
 
       FilterParams fp{};
       fp.nU = cu; fp.nI = (int32_t)nI; fp.kblocks = w.K / 64; fp.fmt = dtype == DIVREC_F32 ? 0 : 1; fp.k = k;
-      fp.use_hint = 1; fp.cap = LIST_CAP; fp.seen_rowptr = rp;
+      fp.use_hint = 1; fp.cap = LIST_CAP; fp.seen_rowptr = rp; fp.debug_mode = g_debug_mode.load(); fp.stats = g_filter_stats.load();
       fp.list_scores = reinterpret_cast<float*>(ws + w.offListS);
       fp.list_item0 = reinterpret_cast<uint32_t*>(ws + w.offListI);
       fp.list_count = reinterpret_cast<int32_t*>(ws + w.offCounts);

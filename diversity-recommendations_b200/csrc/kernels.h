@@ -23,9 +23,12 @@ struct FilterParams {
   int fmt;      // 0 = fp16 plane, 1 = bf16
   int k;
   int use_hint;
+  int debug_mode;  // 0 = normal; 1 = skip the filter (pipeline timing); 2 = filter without stores
   int cap;      // = LIST_CAP
   // filled by the launcher
-  int n_ublocks, n_tiles, b_stages, n_sample, sample_stride;
+  int n_ublocks, n_tiles, b_stages, acc_stages, n_sample, sample_stride;
+  const void* a16;             // [nU, K] 16-bit user plane (read row-wise into TMEM)
+  long long* stats;            // [grid][4] MMA-issuer cycles: total, blocked on A, on accumulators, on B (null = off)
   const int64_t* seen_rowptr;  // [nU+1] or null (only the per-row counts are used here)
   float* list_scores;          // [nU_pad][4][cap][GROUP]  tensor-core scores (scaled units)
   uint32_t* list_item0;        // [nU_pad][4][cap]         local id of the first item of each group

@@ -45,7 +45,7 @@ constexpr int BN = 128;            // items per tile   (TMEM columns per accumul
 constexpr int BK = 64;             // 16-bit elements per k-block = one 128-byte swizzle row
 constexpr int UMMA_K = 16;         // K per tcgen05.mma for 16-bit inputs
 constexpr int SLAB_BYTES = BM * BK * 2;  // 16 KB: 128 rows x 128 B
-constexpr int ACC_STAGES = 4;      // 4 x 128 fp32 columns = all 512 TMEM columns
+constexpr int TMEM_COLS = 512;     // accumulator stages (128 fp32 columns each) from column 0, the A operand at the top
 constexpr int EPI_WARPS = 8;       // warps that consume one tile (one set)
 constexpr int EPI_SETS = 2;
 constexpr int EPI_THREADS = EPI_WARPS * 32;
@@ -58,8 +58,8 @@ constexpr int HS = 2 * N_SAMPLE;   // 32-column group maxima per thread in the h
 struct Smem {
   uint64_t b_full[16];
   uint64_t b_empty[16];
-  uint64_t acc_full[ACC_STAGES];
-  uint64_t acc_empty[ACC_STAGES];
+  uint64_t acc_full[4];
+  uint64_t acc_empty[4];
   uint64_t a_full;
   uint64_t a_empty;
   uint32_t tmem_base;
@@ -89,13 +89,11 @@ __device__ __forceinline__ int sched_tile(int s, int n_sample, int stride) {
 }
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-score_filter_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                    const FilterParams p) {
+score_filter_kernel(const __grid_constant__ CUtensorMap tmap_b, const FilterParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // dynamic smem: [A slabs: kblocks x 16 KB][B ring: b_stages x 16 KB][Smem control block]
+  // dynamic smem: [B ring: b_stages x 16 KB][Smem control block]; the A operand of the user block lives in TMEM
   uint8_t* smem_base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* a_slabs = smem_base;
-  uint8_t* b_ring = smem_base + (size_t)p.kblocks * SLAB_BYTES;
+  uint8_t* b_ring = smem_base;
   Smem* sm = reinterpret_cast<Smem*>(b_ring + (size_t)p.b_stages * SLAB_BYTES);
 
   const int warp = threadIdx.x >> 5;
@@ -104,13 +102,13 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < b_stages; ++i) { mbar_init(smem_u32(&sm->b_full[i]), 1); mbar_init(smem_u32(&sm->b_empty[i]), 1); }
-    for (int i = 0; i < ACC_STAGES; ++i) { mbar_init(smem_u32(&sm->acc_full[i]), 1); mbar_init(smem_u32(&sm->acc_empty[i]), EPI_WARPS); }
-    mbar_init(smem_u32(&sm->a_full), 1);
+    for (int i = 0; i < 4; ++i) { mbar_init(smem_u32(&sm->acc_full[i]), 1); mbar_init(smem_u32(&sm->acc_empty[i]), EPI_WARPS); }
+    mbar_init(smem_u32(&sm->a_full), EPI_WARPS);  // the eight set-0 warps that write A into TMEM
     mbar_init(smem_u32(&sm->a_empty), 1);
     fence_mbar_init();
   }
-  if (warp == W_TMA && lane == 0) { tma_prefetch_desc(&tmap_a); tma_prefetch_desc(&tmap_b); }
-  if (warp == W_ALLOC) { tmem_alloc(smem_u32(&sm->tmem_base), ACC_STAGES * BN); tmem_relinquish(); }
+  if (warp == W_TMA && lane == 0) tma_prefetch_desc(&tmap_b);
+  if (warp == W_ALLOC) { tmem_alloc(smem_u32(&sm->tmem_base), TMEM_COLS); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -119,20 +117,15 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const int kblocks = p.kblocks;
   const int n_sample = p.n_sample;
   const int n_sched = n_sample + p.n_tiles;
+  const uint32_t acc_stages = (uint32_t)p.acc_stages;            // (512 - K/2) / 128: 3 for K <= 256, 2 up to K = 512
+  const uint32_t a_col = TMEM_COLS - (uint32_t)kblocks * (BK / 2);  // A: K/2 packed columns at the top of TMEM
 
   if (warp == W_TMA) {
     // ================= TMA producer =================
     if (lane == 0) {
-      uint32_t stage = 0, phase = 0, a_phase = 0;
+      uint32_t stage = 0, phase = 0;
       const uint64_t pol_keep = l2_policy_evict_last();     // item plane: re-read by every user block
-      const uint64_t pol_stream = l2_policy_evict_first();  // user plane: read once
       for (int ub = blockIdx.x; ub < p.n_ublocks; ub += gridDim.x) {
-        mbar_wait(smem_u32(&sm->a_empty), a_phase ^ 1);
-        mbar_arrive_expect_tx(smem_u32(&sm->a_full), (uint32_t)kblocks * SLAB_BYTES);
-        for (int kb = 0; kb < kblocks; ++kb)
-          tma_load_2d_hint(smem_u32(a_slabs + (size_t)kb * SLAB_BYTES), &tmap_a, smem_u32(&sm->a_full),
-                           kb * BK, ub * BM, pol_stream);
-        a_phase ^= 1;
         for (int s = 0; s < n_sched; ++s) {
           const int t = sched_tile(s, n_sample, p.sample_stride);
           for (int kb = 0; kb < kblocks; ++kb) {
@@ -148,33 +141,53 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   } else if (warp == W_MMA) {
     // ================= MMA issuer =================
     if (lane == 0) {
+      // One thread feeds the tensor core, so this loop is kept to a handful of instructions per MMA: running
+      // counters instead of divisions, the shared-memory descriptor advanced by adding the stage offset (measured:
+      // the unoptimised loop, not the tensor pipe, set the pace at ~110 cycles per instruction against 73).
       const uint32_t idesc = umma_idesc_f16(p.fmt, BM, BN);
+      const uint64_t bdesc0 = umma_desc_sw128(smem_u32(b_ring));
+      const uint32_t bar_b_full = smem_u32(&sm->b_full[0]), bar_b_empty = smem_u32(&sm->b_empty[0]);
+      const uint32_t bar_acc_full = smem_u32(&sm->acc_full[0]), bar_acc_empty = smem_u32(&sm->acc_empty[0]);
+      const uint32_t a_tmem0 = tmem_base + a_col;
       uint32_t stage = 0, phase = 0, a_phase = 0, acc = 0, acc_phase = 0;
+      long long w_a = 0, w_acc = 0, w_b = 0;  // cycles this thread spent blocked on each dependency (p.stats)
+      const bool stats = p.stats != nullptr;
+      const long long t_begin = clock64();
       for (int ub = blockIdx.x; ub < p.n_ublocks; ub += gridDim.x) {
-        mbar_wait(smem_u32(&sm->a_full), a_phase);
+        long long t0 = stats ? clock64() : 0;
+        mbar_wait(smem_u32(&sm->a_full), a_phase);  // the block's A operand has been written to TMEM
+        if (stats) w_a += clock64() - t0;
         a_phase ^= 1;
         tc_fence_after();
         for (int s = 0; s < n_sched; ++s) {
-          mbar_wait(smem_u32(&sm->acc_empty[acc]), acc_phase ^ 1);
+          if (stats) t0 = clock64();
+          mbar_wait(bar_acc_empty + 8 * acc, acc_phase ^ 1);
+          if (stats) w_acc += clock64() - t0;
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * BN;
-          for (int kb = 0; kb < kblocks; ++kb) {
-            mbar_wait(smem_u32(&sm->b_full[stage]), phase);
+          uint32_t a_tmem = a_tmem0;
+          for (int kb = 0; kb < kblocks; ++kb, a_tmem += BK / 2) {
+            if (stats) t0 = clock64();
+            mbar_wait(bar_b_full + 8 * stage, phase);
+            if (stats) w_b += clock64() - t0;
             tc_fence_after();
-            const uint64_t adesc = umma_desc_sw128(smem_u32(a_slabs + (size_t)kb * SLAB_BYTES));
-            const uint64_t bdesc = umma_desc_sw128(smem_u32(b_ring + (size_t)stage * SLAB_BYTES));
-#pragma unroll
-            for (int k4 = 0; k4 < BK / UMMA_K; ++k4) {
-              // advance 32 bytes (16 x 2 B) inside the 128-byte swizzle row: +2 in 16-byte units
-              umma_f16(d_tmem, adesc + 2 * k4, bdesc + 2 * k4, idesc, (uint32_t)((kb | k4) != 0));
-            }
-            umma_commit(smem_u32(&sm->b_empty[stage]));
+            const uint64_t bdesc = bdesc0 + (uint64_t)(stage * (SLAB_BYTES >> 4));
+            // B: +32 bytes (16 x 2 B) inside the 128-byte swizzle row = +2 in 16-byte units; A: 16 elements = 8 TMEM columns
+            umma_f16_ts(d_tmem, a_tmem, bdesc, idesc, (uint32_t)(kb != 0));
+            umma_f16_ts(d_tmem, a_tmem + 8, bdesc + 2, idesc, 1u);
+            umma_f16_ts(d_tmem, a_tmem + 16, bdesc + 4, idesc, 1u);
+            umma_f16_ts(d_tmem, a_tmem + 24, bdesc + 6, idesc, 1u);
+            umma_commit(bar_b_empty + 8 * stage);
             if (++stage == (uint32_t)b_stages) { stage = 0; phase ^= 1; }
           }
-          umma_commit(smem_u32(&sm->acc_full[acc]));
-          if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+          umma_commit(bar_acc_full + 8 * acc);
+          if (++acc == acc_stages) { acc = 0; acc_phase ^= 1; }
         }
-        umma_commit(smem_u32(&sm->a_empty));
+        umma_commit(smem_u32(&sm->a_empty));  // every MMA that reads this block's A has completed
+      }
+      if (stats) {
+        long long* o = p.stats + (size_t)blockIdx.x * 4;
+        o[0] = clock64() - t_begin; o[1] = w_a; o[2] = w_acc; o[3] = w_b;
       }
     }
   } else if (warp < EPI_WARPS * EPI_SETS) {
@@ -185,10 +198,39 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int row_local = q * 32 + lane;
     const int et = (warp & 7) * 32 + lane;  // 0..255 inside the set
     uint32_t base_seq = 0;                   // tiles issued before this user block (all sets count every tile)
+    uint32_t a_phase = 0;
     for (int ub = blockIdx.x; ub < p.n_ublocks; ub += gridDim.x, base_seq += (uint32_t)n_sched) {
       const int64_t row = (int64_t)ub * BM + row_local;
       const bool valid_row = row < p.nU;
       float thr = valid_row ? -INFINITY : INFINITY;
+
+      // ---------------- phase 0: set 0 writes the block's A operand into TMEM (half of the K columns per thread) ----------------
+      if (pset == 0) {
+        mbar_wait(smem_u32(&sm->a_empty), a_phase ^ 1);  // the previous block's MMAs are done with the old A
+        a_phase ^= 1;
+        tc_fence_after();
+        const int words = kblocks * (BK / 4);            // 32-bit words per thread: K/2 columns split over the two halves
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(p.a16) + (size_t)row * (kblocks * (BK / 2)) + (size_t)h * words;
+        const uint32_t tdst = tmem_base + ((uint32_t)(q * 32) << 16) + a_col + (uint32_t)h * words;
+        for (int w0 = 0; w0 < words; w0 += 16) {
+          uint32_t r[16];
+          if (valid_row) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              const uint4 t4 = __ldg(reinterpret_cast<const uint4*>(src + w0 + j));
+              r[j] = t4.x; r[j + 1] = t4.y; r[j + 2] = t4.z; r[j + 3] = t4.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) r[j] = 0u;
+          }
+          tmem_st_32x32b_x16(tdst + w0, r);
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&sm->a_full));
+      }
 
       // ---------------- phase 1: threshold hint from sampled tiles (set 0 scores them, both sets use the result) ----------------
       if (n_sample > 0) {
@@ -196,7 +238,7 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           float hs[HS];
 #pragma unroll
           for (int s = 0; s < N_SAMPLE; ++s) {
-            const uint32_t seq = base_seq + s, acc = seq & (ACC_STAGES - 1), acc_phase = (seq / ACC_STAGES) & 1;
+            const uint32_t seq = base_seq + s, acc = seq % acc_stages, acc_phase = (seq / acc_stages) & 1;
             mbar_wait(smem_u32(&sm->acc_full[acc]), acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + h * COLS_PER_THREAD;
@@ -267,7 +309,7 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       uint32_t cnt = 0;
       const uint32_t cap_lim = (uint32_t)(p.cap - GROUPS_PER_TILE);
       for (int t = pset; t < p.n_tiles; t += EPI_SETS) {
-        const uint32_t seq = base_seq + (uint32_t)(n_sample + t), acc = seq & (ACC_STAGES - 1), acc_phase = (seq / ACC_STAGES) & 1;
+        const uint32_t seq = base_seq + (uint32_t)(n_sample + t), acc = seq % acc_stages, acc_phase = (seq / acc_stages) & 1;
         mbar_wait(smem_u32(&sm->acc_full[acc]), acc_phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + h * COLS_PER_THREAD;
@@ -279,7 +321,9 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&sm->acc_empty[acc]));
 
+        if (p.debug_mode == 1) continue;   // measurement aid: MMA + TMA pipeline alone (no filtering)
         if (cnt > cap_lim) { thr = INFINITY; cnt = (uint32_t)p.cap + 1; }  // overflow: stop, the row goes to the rescue kernel
+        const float thr_st = p.debug_mode == 2 ? INFINITY : thr;  // measurement aid: filter arithmetic without the stores
         const uint32_t item0 = (uint32_t)(t * BN + h * COLS_PER_THREAD);
 #pragma unroll
         for (int g = 0; g < GROUPS_PER_TILE; ++g) {
@@ -296,7 +340,7 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               "@p st.global.v4.b32 [%2+16], {%8, %9, %10, %11};\n"
               "@p st.global.b32 [%3], %12;\n"
               "}\n"
-              ::"f"(m), "f"(thr), "l"(dst), "l"(idst), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]),
+              ::"f"(m), "f"(thr_st), "l"(dst), "l"(idst), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]),
                 "r"(v[6]), "r"(v[7]), "r"(item0 + 8 * g)
               : "memory");
           cnt += (m >= thr) ? 1u : 0u;
@@ -312,7 +356,7 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   // ---- teardown ----
   tc_fence_before();
   __syncthreads();
-  if (warp == W_ALLOC) { tc_fence_after(); tmem_dealloc(tmem_base, ACC_STAGES * BN); }
+  if (warp == W_ALLOC) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
 }
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -349,30 +393,32 @@ bool make_tmap(CUtensorMap* m, const void* base, int64_t rows, int K, int fmt) {
 }  // namespace
 
 int score_filter_b_stages(int kblocks) {
-  // B ring: as many 16 KB stages as fit beside the A slabs (at least 2 tiles' worth when possible)
-  int s = (200 * 1024 - kblocks * SLAB_BYTES - (int)sizeof(Smem)) / SLAB_BYTES;
+  // B ring: as many 16 KB stages as fit (the A operand is in TMEM), at least two tiles' worth when possible
+  (void)kblocks;
+  int s = (200 * 1024 - (int)sizeof(Smem)) / SLAB_BYTES;
   if (s > 16) s = 16;
-  if (s > 4 * kblocks) s = 4 * kblocks;
   return s;
 }
 
 size_t score_filter_smem_bytes(int kblocks) {
-  return 1024 + (size_t)(kblocks + score_filter_b_stages(kblocks)) * SLAB_BYTES + sizeof(Smem);
+  return 1024 + (size_t)score_filter_b_stages(kblocks) * SLAB_BYTES + sizeof(Smem);
 }
 
 // A16 [nU, K] and B16 [nI, K] are K-major 16-bit planes (fmt 0 = fp16, 1 = bf16), K = 64 * kblocks.
 cudaError_t launch_score_filter(const void* A16, const void* B16, FilterParams p, int sm_count, cudaStream_t stream,
                                 const char** err) {
   const int K = p.kblocks * BK;
-  CUtensorMap ta, tb;
-  if (!make_tmap(&ta, A16, p.nU, K, p.fmt) || !make_tmap(&tb, B16, p.nI, K, p.fmt)) {
+  CUtensorMap tb;
+  if (!make_tmap(&tb, B16, p.nI, K, p.fmt)) {
     *err = "cuTensorMapEncodeTiled failed";
     return cudaErrorInvalidValue;
   }
+  if (K > 512) { *err = "embedding dimension too large for the tensor-memory operand (d <= 512)"; return cudaErrorInvalidValue; }
+  p.a16 = A16;
   p.n_ublocks = (int)((p.nU + BM - 1) / BM);
   p.n_tiles = (p.nI + BN - 1) / BN;
   p.b_stages = score_filter_b_stages(p.kblocks);
-  if (p.b_stages < 2) { *err = "embedding dimension too large for the shared-memory operand ring"; return cudaErrorInvalidValue; }
+  p.acc_stages = (TMEM_COLS - K / 2) / BN;
   if (p.use_hint && p.n_tiles >= HINT_MIN_TILES) {
     p.n_sample = N_SAMPLE;
     p.sample_stride = (p.n_tiles - 1) / N_SAMPLE;  // sample tiles are full tiles (never the ragged last one)
@@ -384,7 +430,7 @@ cudaError_t launch_score_filter(const void* A16, const void* B16, FilterParams p
   const int grid = p.n_ublocks < sm_count ? p.n_ublocks : sm_count;
   cudaError_t e = cudaFuncSetAttribute(score_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  score_filter_kernel<<<grid, NUM_THREADS, smem, stream>>>(ta, tb, p);
+  score_filter_kernel<<<grid, NUM_THREADS, smem, stream>>>(tb, p);
   count_launch();
   return cudaGetLastError();
 }

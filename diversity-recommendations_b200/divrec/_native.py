@@ -30,6 +30,8 @@ SIGNATURES = {
     "divrec_last_error": (_c.c_char_p, []),
     "divrec_launch_count": (_i64, []),
     "divrec_set_profiling": (None, [_i32]),
+    "divrec_debug_filter_mode": (None, [_i32]),
+    "divrec_debug_filter_stats": (None, [_vp]),
     "divrec_profile_read": (_i32, [_c.POINTER(_c.c_float), _i32]),
     "divrec_score_topk_workspace": (_sz, [_i64, _i64, _i32, _i32, _i32]),
     "divrec_score_topk": (_i32, [_vp, _vp, _i64, _i64, _i32, _i32, _i32, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _sz, _vp]),

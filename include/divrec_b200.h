@@ -67,6 +67,12 @@ int64_t divrec_launch_count(void);
  * the last durations in ms, -1 where nothing was recorded.  Slots: 0 operand preparation,
  * 1 score+filter kernel, 2 select kernel, 3 ILD, 4 coverage histogram, 5 rescue kernel.  Host-only calls. */
 void divrec_set_profiling(int on);
+/* Measurement aid: 0 = normal; 1 = score+filter kernel runs its TMA/MMA pipeline but skips the filter;
+ * 2 = filter arithmetic without the candidate stores.  Results are meaningless unless mode == 0. */
+void divrec_debug_filter_mode(int mode);
+/* Measurement aid: device buffer int64 [148][4] receiving, per CTA of the score+filter kernel, the MMA-issuing
+ * thread's cycles: total, blocked on the A operand, on a free accumulator stage, on B operand data.  NULL = off. */
+void divrec_debug_filter_stats(void* dev_buf);
 int divrec_profile_read(float* ms_out /*host*/, int n);
 
 /* ---------------------------------------------------------------------------------------
