@@ -24,7 +24,7 @@ namespace divrec {
 namespace {
 
 constexpr int SEL_WARPS = 4;
-constexpr int SEL_CAP = 1024;             // candidate elements per row held in shared memory
+constexpr int SEL_CAP = 768;              // candidate elements per row held in shared memory
 constexpr int SEEN_CAP = 512;             // seen items of the row staged in shared memory (longer lists stay in global)
 constexpr int SORT_N = 128;               // >= MAX_K, power of two
 constexpr int LOAD_B = 4;                 // candidate groups fetched per lane per batch (memory-level parallelism)
@@ -32,10 +32,10 @@ constexpr int LOAD_B = 4;                 // candidate groups fetched per lane p
 struct SelSmem {
   uint32_t key[SEL_WARPS][SEL_CAP];
   uint32_t id[SEL_WARPS][SEL_CAP];
-  int32_t seen[SEL_WARPS][SEEN_CAP];
+  int32_t seen[SEL_WARPS][SEEN_CAP];           // phase B; reused as the 128-entry sort chunk of phase E
   unsigned long long top[SEL_WARPS][SORT_N];   // running top list, sorted descending
-  unsigned long long chunk[SEL_WARPS][SORT_N];
 };
+static_assert(SEEN_CAP * sizeof(int32_t) >= SORT_N * sizeof(unsigned long long), "sort chunk aliases the seen list");
 
 // descending bitonic sort of 128 64-bit keys held in shared memory by one warp
 __device__ __forceinline__ void warp_bitonic_desc_128(unsigned long long* a, uint32_t lane) {
@@ -183,7 +183,7 @@ __device__ __forceinline__ void report_fail(const SelectParams& p, int64_t row, 
 // NJ = float4 chunks of a table row per lane of an 8-lane sub-group: vector path for d <= 32 * NJ, d % 4 == 0.
 // NJ == 0: scalar path for any d (no fused metrics).
 template <int NJ, int DT>
-__global__ void __launch_bounds__(SEL_WARPS * 32)
+__global__ void __launch_bounds__(SEL_WARPS * 32, 6)
 select_topk_kernel(const SelectParams p) {
   extern __shared__ __align__(16) uint8_t sel_smem_raw[];
   SelSmem* sm = reinterpret_cast<SelSmem*>(sel_smem_raw);
@@ -196,7 +196,7 @@ select_topk_kernel(const SelectParams p) {
   uint32_t* id = sm->id[w];
   int32_t* seen_s = sm->seen[w];
   unsigned long long* top = sm->top[w];
-  unsigned long long* chunk = sm->chunk[w];
+  unsigned long long* chunk = reinterpret_cast<unsigned long long*>(sm->seen[w]);
   const int k = p.k;
 
   const int4 nl = *reinterpret_cast<const int4*>(p.list_count + row * LISTS_PER_ROW);
