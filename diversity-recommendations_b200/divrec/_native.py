@@ -187,9 +187,10 @@ def score_topk(U: torch.Tensor, V: torch.Tensor, k: int, seen_rowptr: Optional[t
 
 def score_topk_metrics(U: torch.Tensor, V: torch.Tensor, k: int, seen_rowptr: Optional[torch.Tensor] = None,
                        seen_items: Optional[torch.Tensor] = None, counts: Optional[torch.Tensor] = None,
-                       want_ild: bool = True, want_coverage: bool = True, mode: int = MODE_TENSOR):
+                       want_ild: bool = True, want_coverage: bool = True, mode: int = MODE_TENSOR, out=None):
     """score + mask + top-k with the cosine ILD and the coverage histogram fused into the selection kernel.
-    Returns (scores [nU,k], items [nU,k], ild [nU] or None, counts int32 [nI] or None)."""
+    Returns (scores [nU,k], items [nU,k], ild [nU] or None, counts int32 [nI] or None).
+    `out` = (scores, items, ild) preallocated contiguous views to write into (optional)."""
     lib = load_library()
     U = _cuda(U, "U")
     V = _cuda(V, "V", U.dtype)
@@ -205,9 +206,14 @@ def score_topk_metrics(U: torch.Tensor, V: torch.Tensor, k: int, seen_rowptr: Op
     with torch.cuda.device(U.device):
         ws_bytes = lib.divrec_score_topk_workspace(nU, nI, d, dt, k)
         ws = _workspace(ws_bytes, U.device)
-        out_s = torch.empty((nU, k), dtype=torch.float32, device=U.device)
-        out_i = torch.empty((nU, k), dtype=torch.int64, device=U.device)
-        ild = torch.empty(nU, dtype=torch.float32, device=U.device) if want_ild else None
+        if out is not None:
+            out_s, out_i, ild = out
+            assert out_s.is_contiguous() and out_i.is_contiguous() and (ild is None or ild.is_contiguous())
+            assert out_s.shape == (nU, k) and out_i.shape == (nU, k) and out_s.dtype == torch.float32 and out_i.dtype == torch.int64
+        else:
+            out_s = torch.empty((nU, k), dtype=torch.float32, device=U.device)
+            out_i = torch.empty((nU, k), dtype=torch.int64, device=U.device)
+            ild = torch.empty(nU, dtype=torch.float32, device=U.device) if want_ild else None
         if want_coverage and counts is None:
             counts = torch.zeros(nI, dtype=torch.int32, device=U.device)
         rc = lib.divrec_score_topk_metrics(_ptr(U), _ptr(V), nU, nI, d, dt, mode, _ptr(seen_rowptr), _ptr(seen_items), k,

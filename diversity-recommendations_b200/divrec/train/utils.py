@@ -176,45 +176,92 @@ _host_pipe = {}
 
 
 def host_recommend_and_score(U_host: torch.Tensor, V_host: torch.Tensor, seen_rowptr_host: torch.Tensor,
-                             seen_items_host: torch.Tensor, k: int, device, want_recommendations: bool = True):
+                             seen_items_host: torch.Tensor, k: int, device, want_recommendations: bool = True,
+                             chunks: int = 4):
     """The whole evaluation pass from HOST buffers: copy the embedding tables and the seen-item CSR to the
-    device, run score + mask + top-k, ILD and the coverage histogram, and bring the results back to
-    pinned host memory.  Equivalent of recommendations_score_loop(RankingDataset(test, frozen=train),
-    MatrixFactorization, [IntraListDiversityScore, EntropyDiversityScore], k) for a caller whose model and
-    interactions live in host memory.  Returns a dict with host tensors and the bytes moved."""
+    device, run score + mask + top-k with the cosine ILD and the coverage histogram fused, and bring the
+    results back to pinned host memory.  Equivalent of recommendations_score_loop(RankingDataset(test,
+    frozen=train), MatrixFactorization, [IntraListDiversityScore, EntropyDiversityScore], k) for a caller
+    whose model and interactions live in host memory.
+
+    Users are processed in `chunks` contiguous ranges on three streams -- host->device copies of the next
+    range, kernels of the current one, device->host copies of the previous one -- so the PCIe transfers hide
+    behind the kernels.  Pass pinned tensors (pageable memory makes the copies synchronous).
+    Returns a dict with host tensors and the bytes moved."""
     import math
     dev = torch.device(device)
-    nU, nI = U_host.shape[0], V_host.shape[0]
-    key = (dev.index, nU, nI, U_host.shape[1], k, seen_items_host.numel())
+    nU, d = U_host.shape
+    nI = V_host.shape[0]
+    key = (dev.index, nU, nI, d, k, seen_items_host.numel(), chunks)
     st = _host_pipe.get(key)
     if st is None:
+        wave = 148 * 128  # users scored by one wave of the persistent filter kernel
+        per = nU if nU <= wave else -(-(-(-nU // max(1, chunks))) // wave) * wave  # ceil(ceil(nU / chunks) / wave) * wave
+        bounds = list(range(0, nU, per)) + [nU]
         st = {
             "U": torch.empty_like(U_host, device=dev), "V": torch.empty_like(V_host, device=dev),
             "rp": torch.empty_like(seen_rowptr_host, device=dev), "it": torch.empty_like(seen_items_host, device=dev),
             "counts": torch.zeros(nI, dtype=torch.int32, device=dev),
+            "recs": torch.empty((nU, k), dtype=torch.int64, device=dev),
+            "scores": torch.empty((nU, k), dtype=torch.float32, device=dev),
+            "ild": torch.empty(nU, dtype=torch.float32, device=dev),
             "recs_h": torch.empty((nU, k), dtype=torch.int64).pin_memory(),
             "ild_h": torch.empty(nU, dtype=torch.float32).pin_memory(),
             "counts_h": torch.empty(nI, dtype=torch.int32).pin_memory(),
             "ent_h": torch.empty(2, dtype=torch.float32).pin_memory(),
+            "bounds": bounds,
+            "rp_list": seen_rowptr_host.tolist() if len(bounds) > 2 else None,
+            "s_in": torch.cuda.Stream(dev), "s_out": torch.cuda.Stream(dev),
         }
         _host_pipe.clear()
         _host_pipe[key] = st
-    h2d = 0
-    for name, src in (("U", U_host), ("V", V_host), ("rp", seen_rowptr_host), ("it", seen_items_host)):
-        st[name].copy_(src, non_blocking=True)
-        h2d += src.numel() * src.element_size()
+    bounds = st["bounds"]
+    main = torch.cuda.current_stream(dev)
+    s_in, s_out = st["s_in"], st["s_out"]
+    s_in.wait_stream(main)
+    s_out.wait_stream(main)
+    h2d = d2h = 0
+    # ---- host -> device: the item table and the row pointers first, then user rows + seen items range by range ----
+    ready = []
+    with torch.cuda.stream(s_in):
+        st["V"].copy_(V_host, non_blocking=True)
+        st["rp"].copy_(seen_rowptr_host, non_blocking=True)
+        h2d += V_host.numel() * V_host.element_size() + seen_rowptr_host.numel() * 8
+        for c in range(len(bounds) - 1):
+            a, b = bounds[c], bounds[c + 1]
+            st["U"][a:b].copy_(U_host[a:b], non_blocking=True)
+            h2d += (b - a) * d * U_host.element_size()
+            if seen_items_host.numel():
+                lo, hi = (st["rp_list"][a], st["rp_list"][b]) if st["rp_list"] is not None else (0, seen_items_host.numel())
+                if hi > lo:
+                    st["it"][lo:hi].copy_(seen_items_host[lo:hi], non_blocking=True)
+                    h2d += (hi - lo) * 4
+            ev = torch.cuda.Event()
+            ev.record(s_in)
+            ready.append(ev)
+    # ---- kernels on the caller's stream, device -> host behind them ----
     st["counts"].zero_()
-    _scores, recs, ild, _ = _native.score_topk_metrics(st["U"], st["V"], k, st["rp"], st["it"] if st["it"].numel() else None,
-                                                       counts=st["counts"])
+    items_dev = st["it"] if st["it"].numel() else None
+    for c in range(len(bounds) - 1):
+        a, b = bounds[c], bounds[c + 1]
+        main.wait_event(ready[c])
+        _native.score_topk_metrics(st["U"][a:b], st["V"], k, st["rp"][a:b + 1], items_dev, counts=st["counts"],
+                                   out=(st["scores"][a:b], st["recs"][a:b], st["ild"][a:b]))
+        done = torch.cuda.Event()
+        done.record(main)
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(done)
+            if want_recommendations:
+                st["recs_h"][a:b].copy_(st["recs"][a:b], non_blocking=True)
+                d2h += (b - a) * k * 8
+            st["ild_h"][a:b].copy_(st["ild"][a:b], non_blocking=True)
+            d2h += (b - a) * 4
     ent = _native.entropy_from_counts(st["counts"])
-    d2h = 0
-    outs = [("ild_h", ild), ("counts_h", st["counts"]), ("ent_h", ent)]
-    if want_recommendations:
-        outs.append(("recs_h", recs))
-    for name, src in outs:
-        st[name].copy_(src, non_blocking=True)
-        d2h += src.numel() * src.element_size()
-    torch.cuda.current_stream(dev).synchronize()
+    st["counts_h"].copy_(st["counts"], non_blocking=True)
+    st["ent_h"].copy_(ent, non_blocking=True)
+    d2h += nI * 4 + 8
+    main.wait_stream(s_out)
+    main.synchronize()
     entropy = (float(st["ent_h"][0]) - math.log(k)) / (math.log(nI) - math.log(k))
     return {"recommendations": st["recs_h"] if want_recommendations else None, "ild_per_user": st["ild_h"],
             "coverage_counts": st["counts_h"], "entropy_diversity": entropy, "h2d_bytes": h2d, "d2h_bytes": d2h}

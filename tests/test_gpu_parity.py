@@ -397,6 +397,26 @@ def test_shim_end_to_end_matches_reference_golden(native, dev):
         assert (got.cpu() - want).abs().max().item() <= REL * float(want.abs().max())
 
 
+def test_host_buffer_pipeline_equals_resident_path(native, dev):
+    """divrec.train.host_recommend_and_score (pinned host buffers, chunked and overlapped copies) must return
+    exactly what the device-resident fused call returns."""
+    from divrec.train import host_recommend_and_score
+    gen = torch.Generator().manual_seed(53)
+    nU, nI, d, k = 40000, 5000, 64, 20   # more than one 18 944-user wave -> several chunks
+    U, V = O.make_embeddings(nU, d, "gauss", gen), O.make_embeddings(nI, d, "gauss", gen)
+    seen = O.make_seen(nU, nI, 400000, gen)
+    rowptr, items = O.seen_csr(seen, nU)
+    s, i, ild, counts = native.score_topk_metrics(U.to(dev), V.to(dev), k, rowptr.to(dev), items.to(dev))
+    for chunks in (1, 3):
+        res = host_recommend_and_score(U.pin_memory(), V.pin_memory(), rowptr.pin_memory(), items.pin_memory(), k, dev, chunks=chunks)
+        assert torch.equal(res["recommendations"], i.cpu())
+        assert torch.equal(res["ild_per_user"], ild.cpu())
+        assert torch.equal(res["coverage_counts"], counts.cpu())
+        assert res["entropy_diversity"] == pytest.approx(float(O.entropy_diversity(i.cpu(), nI)), rel=1e-5)
+        assert res["h2d_bytes"] == U.numel() * 4 + V.numel() * 4 + rowptr.numel() * 8 + items.numel() * 4
+        assert res["d2h_bytes"] == nU * k * 8 + nU * 4 + nI * 4 + 8
+
+
 def test_relevance_metrics_vs_reference_formulas(native, dev):
     """precision / recall / AP / NDCG against a direct restatement of the reference loops
     (precision_at_k.py:16-22, recall_at_k.py:16-22, average_precision_at_k.py:18-24, ndcg :16-23)."""
