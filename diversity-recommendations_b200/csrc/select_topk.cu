@@ -98,50 +98,45 @@ __device__ __forceinline__ float sum8(float v) {
   return v;
 }
 
-struct GroupRef { const float* s; uint32_t item0; };
-// the row's LISTS_PER_ROW lists as one virtual sequence; e1/e2/e3 = end offsets of lists 0/1/2 in it
-__device__ __forceinline__ GroupRef group_at(const SelectParams& p, int64_t row, int e1, int e2, int e3, int g) {
-  const int l = (g >= e1) + (g >= e2) + (g >= e3);
-  const int idx = g - (l == 0 ? 0 : l == 1 ? e1 : l == 2 ? e2 : e3);
-  const size_t base = ((size_t)row * LISTS_PER_ROW + l) * (size_t)p.cap + idx;
-  return GroupRef{p.list_scores + base * GROUP, p.list_item0[base]};
-}
-
-// One pass over the row's captured groups, LOAD_B groups per lane in flight.
+// One pass over the row's captured groups: iteration `it` handles group it*32+lane of each of the row's four lists
+// (four independent 36-byte reads in flight per lane, trivial addressing).
 //   STORE: elements with score >= fmin are written to key[] / id[] (at most SEL_CAP), any order;
 //   returns how many there are in total.  Scores are compared as floats; -inf never qualifies.
 template <bool STORE>
-__device__ __forceinline__ int scan_groups(const SelectParams& p, int64_t row, int e1, int e2, int e3, int ng, float fmin,
+__device__ __forceinline__ int scan_groups(const SelectParams& p, int64_t row, const int4 nl, float fmin,
                                            uint32_t* key, uint32_t* id, uint32_t lane) {
   int total = 0;
   const float lim = fmaxf(fmin, -3.0e38f);
-  for (int g0 = 0; g0 < ng; g0 += 32 * LOAD_B) {
-    float4 a[LOAD_B], b[LOAD_B];
-    uint32_t item0[LOAD_B];
+  const int cnt[LISTS_PER_ROW] = {nl.x, nl.y, nl.z, nl.w};
+  const int nmax = max(max(nl.x, nl.y), max(nl.z, nl.w));
+  const size_t row_base = (size_t)row * LISTS_PER_ROW * (size_t)p.cap;
+  const uint32_t nI = (uint32_t)p.nI;
+  for (int g = lane; g < nmax + (int)lane; g += 32) {  // uniform trip count: every lane runs ceil(nmax / 32) iterations
+    float4 a[LISTS_PER_ROW], b[LISTS_PER_ROW];
+    uint32_t item0[LISTS_PER_ROW];
 #pragma unroll
-    for (int j = 0; j < LOAD_B; ++j) {
-      const int g = g0 + j * 32 + lane;
-      item0[j] = 0xffffffffu;
-      if (g < ng) {
-        const GroupRef gr = group_at(p, row, e1, e2, e3, g);
-        item0[j] = gr.item0;
-        a[j] = *reinterpret_cast<const float4*>(gr.s);
-        b[j] = *reinterpret_cast<const float4*>(gr.s + 4);
+    for (int l = 0; l < LISTS_PER_ROW; ++l) {
+      item0[l] = 0xffffffffu;
+      if (g < cnt[l]) {
+        const size_t base = row_base + (size_t)l * p.cap + g;
+        item0[l] = p.list_item0[base];
+        const float4* src = reinterpret_cast<const float4*>(p.list_scores + base * GROUP);
+        a[l] = src[0];
+        b[l] = src[1];
       }
     }
-    uint32_t m[LOAD_B];
+    uint32_t m[LISTS_PER_ROW];
     int mine = 0;
 #pragma unroll
-    for (int j = 0; j < LOAD_B; ++j) {
-      m[j] = 0;
-      if (item0[j] != 0xffffffffu) {
-        m[j] = (a[j].x >= lim ? 1u : 0u) | (a[j].y >= lim ? 2u : 0u) | (a[j].z >= lim ? 4u : 0u) | (a[j].w >= lim ? 8u : 0u) |
-               (b[j].x >= lim ? 16u : 0u) | (b[j].y >= lim ? 32u : 0u) | (b[j].z >= lim ? 64u : 0u) | (b[j].w >= lim ? 128u : 0u);
+    for (int l = 0; l < LISTS_PER_ROW; ++l) {
+      m[l] = 0;
+      if (item0[l] < nI) {  // also false for the 0xffffffff "no group" marker and for groups past the catalogue
+        m[l] = (a[l].x >= lim ? 1u : 0u) | (a[l].y >= lim ? 2u : 0u) | (a[l].z >= lim ? 4u : 0u) | (a[l].w >= lim ? 8u : 0u) |
+               (b[l].x >= lim ? 16u : 0u) | (b[l].y >= lim ? 32u : 0u) | (b[l].z >= lim ? 64u : 0u) | (b[l].w >= lim ? 128u : 0u);
         // only the last tile's groups can run past the catalogue (zero-filled operand rows score 0)
-        if (item0[j] >= (uint32_t)p.nI) m[j] = 0;
-        else if ((uint32_t)p.nI - item0[j] < 8u) m[j] &= (1u << ((uint32_t)p.nI - item0[j])) - 1u;
+        if (nI - item0[l] < 8u) m[l] &= (1u << (nI - item0[l])) - 1u;
       }
-      mine += __popc(m[j]);
+      mine += __popc(m[l]);
     }
     if (!STORE) {
       total += mine;
@@ -155,14 +150,14 @@ __device__ __forceinline__ int scan_groups(const SelectParams& p, int64_t row, i
       int pos = total + incl - mine;
       total += __shfl_sync(0xffffffffu, incl, 31);
 #pragma unroll
-      for (int j = 0; j < LOAD_B; ++j) {
-        uint32_t mm = m[j];
+      for (int l = 0; l < LISTS_PER_ROW; ++l) {
+        uint32_t mm = m[l];
         while (mm) {
           const int e = __ffs(mm) - 1;
           mm &= mm - 1;
-          const float v = e < 4 ? (e == 0 ? a[j].x : e == 1 ? a[j].y : e == 2 ? a[j].z : a[j].w)
-                                : (e == 4 ? b[j].x : e == 5 ? b[j].y : e == 6 ? b[j].z : b[j].w);
-          if (pos < SEL_CAP) { key[pos] = f32_to_key(__float_as_uint(v + 0.0f)); id[pos] = item0[j] + e; }
+          const float v = e < 4 ? (e == 0 ? a[l].x : e == 1 ? a[l].y : e == 2 ? a[l].z : a[l].w)
+                                : (e == 4 ? b[l].x : e == 5 ? b[l].y : e == 6 ? b[l].z : b[l].w);
+          if (pos < SEL_CAP) { key[pos] = f32_to_key(__float_as_uint(v + 0.0f)); id[pos] = item0[l] + e; }
           ++pos;
         }
       }
@@ -182,7 +177,7 @@ __device__ __forceinline__ void report_fail(const SelectParams& p, int64_t row, 
 
 // NJ = float4 chunks of a table row per lane of an 8-lane sub-group: vector path for d <= 32 * NJ, d % 4 == 0.
 // NJ == 0: scalar path for any d (no fused metrics).
-template <int NJ, int DT>
+template <int NJ, int DT, bool FULL>
 __global__ void __launch_bounds__(SEL_WARPS * 32, 6)
 select_topk_kernel(const SelectParams p) {
   extern __shared__ __align__(16) uint8_t sel_smem_raw[];
@@ -201,14 +196,15 @@ select_topk_kernel(const SelectParams p) {
 
   const int4 nl = *reinterpret_cast<const int4*>(p.list_count + row * LISTS_PER_ROW);
   if (p.force_fail || nl.x > p.cap || nl.y > p.cap || nl.z > p.cap || nl.w > p.cap) { report_fail(p, row, lane); return; }
-  const int le1 = nl.x, le2 = le1 + nl.y, le3 = le2 + nl.z, ng = le3 + nl.w;
 
   int64_t s0 = 0, s1 = 0;
   if (p.seen_rowptr != nullptr) { s0 = p.seen_rowptr[row]; s1 = p.seen_rowptr[row + 1]; }
   const int64_t seen_u = s1 - s0;
   const bool seen_in_smem = seen_u <= SEEN_CAP;
+  int seen_pow2 = 1;  // smallest power of two >= seen_u: the shared copy is padded with INT_MAX up to it
+  while (seen_pow2 < (int)seen_u && seen_pow2 < SEEN_CAP) seen_pow2 <<= 1;
   if (seen_in_smem)
-    for (int i = lane; i < (int)seen_u; i += 32) seen_s[i] = __ldg(p.seen_items + s0 + i);
+    for (int i = lane; i < seen_pow2; i += 32) seen_s[i] = i < (int)seen_u ? __ldg(p.seen_items + s0 + i) : 0x7fffffff;
 
   // 2 delta in the (scaled) units of the tensor-core scores
   int e2 = 0;
@@ -227,7 +223,7 @@ select_topk_kernel(const SelectParams p) {
   uint32_t thr_key = (thr == -INFINITY) ? 0u : f32_to_key(__float_as_uint(thr + 0.0f));  // effective capture threshold
 
   // ---- A: enumerate ----
-  int ne = scan_groups<true>(p, row, le1, le2, le3, ng, thr, key, id, lane);
+  int ne = scan_groups<true>(p, row, nl, thr, key, id, lane);
   if (ne > SEL_CAP) {
     // coarse cut: X = the need-th largest captured score, need = k + seen_u  =>  k-th best unmasked >= X
     const int64_t need64 = (int64_t)k + seen_u;
@@ -236,7 +232,7 @@ select_topk_kernel(const SelectParams p) {
     uint32_t lo = thr_key > KEY_NEG_INF ? thr_key : KEY_NEG_INF + 1, hi = 0xff800000u;  // hi: above every finite key
     while (hi - lo > 1) {
       const uint32_t mid = lo + ((hi - lo) >> 1);
-      const int c = scan_groups<false>(p, row, le1, le2, le3, ng, __uint_as_float(key_to_f32(mid)), key, id, lane);
+      const int c = scan_groups<false>(p, row, nl, __uint_as_float(key_to_f32(mid)), key, id, lane);
       if (c >= need) lo = mid; else hi = mid;
       if (c >= need && c <= need + need / 8) break;  // close enough
     }
@@ -244,7 +240,7 @@ select_topk_kernel(const SelectParams p) {
     const uint32_t cut_key = f32_to_key(__float_as_uint((X - margin2) + 0.0f));
     if (cut_key <= thr_key) { report_fail(p, row, lane); return; }
     thr_key = cut_key;
-    ne = scan_groups<true>(p, row, le1, le2, le3, ng, __uint_as_float(key_to_f32(thr_key)), key, id, lane);
+    ne = scan_groups<true>(p, row, nl, __uint_as_float(key_to_f32(thr_key)), key, id, lane);
     if (ne > SEL_CAP) { report_fail(p, row, lane); return; }
   }
 
@@ -254,12 +250,10 @@ select_topk_kernel(const SelectParams p) {
       const int64_t gid = (int64_t)id[i] + p.item_id_offset;
       if (seen_in_smem) {
         const int32_t g32 = (int32_t)gid;  // seen ids are int32
-        int lo = 0, hi = (int)seen_u;
-        while (lo < hi) {
-          const int mid = (lo + hi) >> 1;
-          if (seen_s[mid] < g32) lo = mid + 1; else hi = mid;
-        }
-        if (lo < (int)seen_u && seen_s[lo] == g32 && gid <= 0x7fffffffLL) key[i] = 0;
+        // largest position whose value is <= g32, found with one conditional add per level (no branches)
+        int pos = 0;
+        for (int half = seen_pow2 >> 1; half > 0; half >>= 1) pos += (seen_s[pos + half] <= g32) ? half : 0;
+        if (seen_s[pos] == g32 && gid < 0x7fffffffLL) key[i] = 0;
       } else {
         int64_t lo = 0, hi = seen_u;
         while (lo < hi) {
@@ -325,7 +319,7 @@ select_topk_kernel(const SelectParams p) {
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
       const int c4 = sub + 8 * j;
-      ur[j] = c4 < nvec ? ld4<DT>(p.U, row, d, c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      ur[j] = (FULL || c4 < nvec) ? ld4<DT>(p.U, row, d, c4) : make_float4(0.f, 0.f, 0.f, 0.f);
       acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     for (int r0 = 0; r0 < nr; r0 += 8) {
@@ -335,22 +329,22 @@ select_topk_kernel(const SelectParams p) {
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
         const int c4 = sub + 8 * j;
-        if (8 * j < nvec) {
-          va[j] = c4 < nvec ? ld4<DT>(p.V, ia, d, c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-          vb[j] = c4 < nvec ? ld4<DT>(p.V, ib, d, c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (FULL || 8 * j < nvec) {
+          va[j] = (FULL || c4 < nvec) ? ld4<DT>(p.V, ia, d, c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          vb[j] = (FULL || c4 < nvec) ? ld4<DT>(p.V, ib, d, c4) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
       float sa = 0.f, sb = 0.f;
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
-        if (8 * j < nvec) { sa = dot4(ur[j], va[j], sa); sb = dot4(ur[j], vb[j], sb); }
+        if (FULL || 8 * j < nvec) { sa = dot4(ur[j], va[j], sa); sb = dot4(ur[j], vb[j], sb); }
       }
       sa = sum8(sa); sb = sum8(sb);
       if (want_ild) {
         const float ia_n = ra < nr ? __ldg(p.inv_norm_v + ia) : 0.f, ib_n = rb < nr ? __ldg(p.inv_norm_v + ib) : 0.f;
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
-          if (8 * j < nvec) {
+          if (FULL || 8 * j < nvec) {
             acc[j].x = fmaf(va[j].x, ia_n, acc[j].x); acc[j].y = fmaf(va[j].y, ia_n, acc[j].y);
             acc[j].z = fmaf(va[j].z, ia_n, acc[j].z); acc[j].w = fmaf(va[j].w, ia_n, acc[j].w);
             acc[j].x = fmaf(vb[j].x, ib_n, acc[j].x); acc[j].y = fmaf(vb[j].y, ib_n, acc[j].y);
@@ -419,8 +413,10 @@ select_topk_kernel(const SelectParams p) {
     const unsigned long long kth = k <= SORT_N ? top[k - 1] : 0ull;  // smallest winning composite (0 when fewer than k)
     const int nvec = d >> 2;
     const int sub = lane & 7, grp = lane >> 3;
-    for (int r0 = 0; r0 < nr; r0 += 4) {
-      const int r = r0 + grp;
+    // list the losers (lane per candidate), reusing the front of key[] (the scores are no longer needed)
+    int nlose = 0;
+    for (int base = 0; base < nr; base += 32) {
+      const int r = base + lane;
       bool loser = false;
       uint32_t ia = 0;
       if (r < nr) {
@@ -430,18 +426,25 @@ select_topk_kernel(const SelectParams p) {
         if (kk > KEY_NEG_INF && kk < 0xff800000u) c = ((unsigned long long)kk << 32) | (unsigned long long)(~ia);
         loser = c < kth || c == 0ull;
       }
-      if (__ballot_sync(0xffffffffu, loser) == 0) continue;
-      float4 va[NJ > 0 ? NJ : 1];
+      const uint32_t lb = __ballot_sync(0xffffffffu, loser);
+      __syncwarp();
+      if (loser) key[nlose + __popc(lb & lt)] = ia;  // writes land at or before the slots already read
+      nlose += __popc(lb);
+    }
+    __syncwarp();
+    for (int r0 = 0; r0 < nlose; r0 += 4) {
+      const int r = r0 + grp;
+      const bool on = r < nlose;
+      const uint32_t ia = key[on ? r : 0];
+      const float inv = on ? __ldg(p.inv_norm_v + ia) : 0.f;
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
         const int c4 = sub + 8 * j;
-        va[j] = (loser && c4 < nvec) ? ld4<DT>(p.V, ia, d, c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      const float inv = loser ? __ldg(p.inv_norm_v + ia) : 0.f;
-#pragma unroll
-      for (int j = 0; j < NJ; ++j) {
-        acc[j].x = fmaf(-va[j].x, inv, acc[j].x); acc[j].y = fmaf(-va[j].y, inv, acc[j].y);
-        acc[j].z = fmaf(-va[j].z, inv, acc[j].z); acc[j].w = fmaf(-va[j].w, inv, acc[j].w);
+        if (on && (FULL || c4 < nvec)) {
+          const float4 va = ld4<DT>(p.V, ia, d, c4);
+          acc[j].x = fmaf(-va.x, inv, acc[j].x); acc[j].y = fmaf(-va.y, inv, acc[j].y);
+          acc[j].z = fmaf(-va.z, inv, acc[j].z); acc[j].w = fmaf(-va.w, inv, acc[j].w);
+        }
       }
     }
     // combine the four sub-groups' partial sums (same `sub` => same columns), then |sum e|^2
@@ -511,17 +514,21 @@ cudaError_t launch_select_topk(const SelectParams& p, cudaStream_t stream) {
   const int64_t grid = (p.nU + SEL_WARPS - 1) / SEL_WARPS;
   const bool vec = (p.d & 3) == 0 && p.d <= 256;  // wider rows take the scalar path (no fused metrics)
   cudaError_t e;
-#define DIVREC_LAUNCH_SELECT(NJ, DT)                                                                               \
-  do {                                                                                                             \
-    e = cudaFuncSetAttribute(select_topk_kernel<NJ, DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
-    if (e != cudaSuccess) return e;                                                                                \
-    select_topk_kernel<NJ, DT><<<(unsigned)grid, SEL_WARPS * 32, smem, stream>>>(p);                               \
+#define DIVREC_LAUNCH_SELECT(NJ, DT, FULL)                                                                               \
+  do {                                                                                                                   \
+    e = cudaFuncSetAttribute(select_topk_kernel<NJ, DT, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+    if (e != cudaSuccess) return e;                                                                                      \
+    select_topk_kernel<NJ, DT, FULL><<<(unsigned)grid, SEL_WARPS * 32, smem, stream>>>(p);                               \
   } while (0)
-  if (!vec) DIVREC_LAUNCH_SELECT(0, 0);
-  else if (p.dtype == 0 && p.d <= 128) DIVREC_LAUNCH_SELECT(4, 0);
-  else if (p.dtype == 0) DIVREC_LAUNCH_SELECT(8, 0);
-  else if (p.d <= 128) DIVREC_LAUNCH_SELECT(4, 1);
-  else DIVREC_LAUNCH_SELECT(8, 1);
+  if (!vec) DIVREC_LAUNCH_SELECT(0, 0, false);
+  else if (p.dtype == 0 && p.d == 128) DIVREC_LAUNCH_SELECT(4, 0, true);   // the common full-row shapes get branch-free loads
+  else if (p.dtype == 0 && p.d <= 128) DIVREC_LAUNCH_SELECT(4, 0, false);
+  else if (p.dtype == 0 && p.d == 256) DIVREC_LAUNCH_SELECT(8, 0, true);
+  else if (p.dtype == 0) DIVREC_LAUNCH_SELECT(8, 0, false);
+  else if (p.d == 128) DIVREC_LAUNCH_SELECT(4, 1, true);
+  else if (p.d <= 128) DIVREC_LAUNCH_SELECT(4, 1, false);
+  else if (p.d == 256) DIVREC_LAUNCH_SELECT(8, 1, true);
+  else DIVREC_LAUNCH_SELECT(8, 1, false);
 #undef DIVREC_LAUNCH_SELECT
   count_launch();
   return cudaGetLastError();
