@@ -89,7 +89,7 @@ static WsLayout ws_layout(int64_t nU, int64_t nI, int d, int dtype) {
   w.offListS = off; off += align_up(cpad * LISTS_PER_ROW * LIST_CAP * GROUP * sizeof(float), 1024);
   w.offListI = off; off += align_up(cpad * LISTS_PER_ROW * LIST_CAP * sizeof(uint32_t), 1024);
   w.offCounts = off; off += align_up(cpad * LISTS_PER_ROW * sizeof(int32_t), 1024);
-  w.offThr = off; off += align_up(cpad * sizeof(float), 1024);
+  w.offThr = off; off += align_up(cpad * LISTS_PER_ROW * sizeof(float), 1024);
   w.offFail = off; off += align_up(cpad * sizeof(int32_t), 1024);
   w.offScalars = off; off += 1024;  // u32[0..1] amax bits (U,V), i32[2..3] scale exps, u32[4] max item norm, i32[5] fail count
   w.offRescue = off; off += align_up(rescue_scratch_bytes(nI, &w.rescue_grid), 1024);
@@ -245,6 +245,8 @@ static int score_topk_impl(const void* U, const void* V, int64_t nU, int64_t nI,
       fp.list_item0 = reinterpret_cast<uint32_t*>(ws + w.offListI);
       fp.list_count = reinterpret_cast<int32_t*>(ws + w.offCounts);
       fp.thr_out = reinterpret_cast<float*>(ws + w.offThr);
+      fp.norms_u = norms_u; fp.nvmax_bits = nvmax; fp.amax_bits = sp.amax_bits; fp.scale_exps = sp.scale_exps;
+      fp.c_margin = sp.c_margin; fp.d = d;
       const char* err = "";
       prof_mark(PROF_FILTER, 0, st);
       e = launch_score_filter(A16, B16, fp, device_info().sm_count, st, &err);

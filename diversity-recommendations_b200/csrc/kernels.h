@@ -12,6 +12,7 @@ constexpr int LISTS_PER_ROW = 4;     // (column half of a tile) x (tile parity)
 constexpr int GROUP = 8;             // consecutive item columns appended together
 constexpr int N_SAMPLE = 16;         // item tiles scored first to seed the per-row threshold hint
 constexpr int HINT_MIN_TILES = 32;   // catalogues with fewer 128-item tiles keep every group (no hint)
+constexpr int TIGHTEN_MIN_ITEMS = 500000;  // catalogues at least this large use the filter variant that tightens lists online
 constexpr int MAX_K = 128;
 
 void count_launch();
@@ -33,7 +34,14 @@ struct FilterParams {
   float* list_scores;          // [nU_pad][4][cap][GROUP]  tensor-core scores (scaled units)
   uint32_t* list_item0;        // [nU_pad][4][cap]         local id of the first item of each group
   int32_t* list_count;         // [nU_pad][4]              groups appended; cap + 1 = overflow
-  float* thr_out;              // [nU_pad]                 threshold hint used for the row (scaled units, -inf = none)
+  float* thr_out;              // [nU_pad][4]              final capture threshold of each list (scaled units, -inf = none)
+  // error-bound inputs (the 2 delta margin of list tightening; same values as SelectParams)
+  const float* norms_u;
+  const uint32_t* nvmax_bits;
+  const uint32_t* amax_bits;
+  const int32_t* scale_exps;
+  float c_margin;
+  int d;
 };
 
 int score_filter_b_stages(int kblocks);

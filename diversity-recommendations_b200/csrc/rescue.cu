@@ -52,21 +52,50 @@ rescue_kernel(const RescueParams p) {
     __syncthreads();
     for (int c = tid; c < d; c += RT) u_s[c] = rd(p.U, p.dtype, row * d + c);
     __syncthreads();
-    // 1. exact scores -> ordered keys (0 is reserved for "not recommendable")
-    const bool vec = p.dtype == 0 && (d & 3) == 0;
+    // 1. exact scores -> ordered keys (0 is reserved for "not recommendable").  The summation order replays the
+    //    select kernel's exactly (same partial sums, same butterfly), so a row gets the same bits whichever
+    //    kernel scores it: item-sharded, user-sharded, tensor and SIMT routes agree bit for bit.
+    const bool vec = (d & 3) == 0 && d <= 256;  // select_topk.cu: 8 lanes per candidate, float4 chunk c4 = lane + 8 j
     for (int64_t i = tid; i < nI; i += RT) {
-      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      float s;
       if (vec) {
-        const float4* v = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.V) + i * d);
-        for (int c = 0; c < (d >> 2); ++c) {
-          const float4 x = __ldg(v + c);
-          const float4 y = *reinterpret_cast<const float4*>(u_s + 4 * c);
-          s0 = fmaf(x.x, y.x, s0); s1 = fmaf(x.y, y.y, s1); s2 = fmaf(x.z, y.z, s2); s3 = fmaf(x.w, y.w, s3);
+        float part[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        const int nvec = d >> 2;
+        for (int c0 = 0; c0 < nvec; c0 += 8) {  // partial l owns the float4 chunks l, l + 8, ...: same chains as select
+#pragma unroll
+          for (int l = 0; l < 8; ++l) {
+            const int c4 = c0 + l;
+            if (c4 < nvec) {
+              float4 x;
+              if (p.dtype == 0) {
+                x = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.V) + i * d) + c4);
+              } else {
+                const uint2 raw = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.V) + i * d) + c4);
+                x = make_float4(__uint_as_float(raw.x << 16), __uint_as_float(raw.x & 0xffff0000u),
+                                __uint_as_float(raw.y << 16), __uint_as_float(raw.y & 0xffff0000u));
+              }
+              const float4 y = *reinterpret_cast<const float4*>(u_s + 4 * c4);
+              float acc = part[l];
+              acc = fmaf(y.x, x.x, acc); acc = fmaf(y.y, x.y, acc); acc = fmaf(y.z, x.z, acc); acc = fmaf(y.w, x.w, acc);
+              part[l] = acc;
+            }
+          }
         }
+        s = ((part[0] + part[1]) + (part[2] + part[3])) + ((part[4] + part[5]) + (part[6] + part[7]));  // xor 1, 2, 4
       } else {
-        for (int c = 0; c < d; ++c) s0 = fmaf(rd(p.V, p.dtype, i * d + c), u_s[c], s0);
+        float part[32];  // scalar path: lane l takes columns l, l + 32, ...; butterfly xor 16, 8, 4, 2, 1
+#pragma unroll
+        for (int l = 0; l < 32; ++l) {
+          float acc = 0.f;
+          for (int c = l; c < d; c += 32) acc = fmaf(u_s[c], rd(p.V, p.dtype, i * d + c), acc);
+          part[l] = acc;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+          for (int l = 0; l < o; ++l) part[l] = part[l] + part[l + o];
+        s = part[0];
       }
-      const float s = (s0 + s1) + (s2 + s3);
       uint32_t kk = f32_to_key(__float_as_uint(s + 0.0f));
       if (kk <= KEY_NEG_INF || !(s == s)) kk = 0;
       keys[i] = kk;
@@ -90,7 +119,14 @@ rescue_kernel(const RescueParams p) {
       const unsigned prefix = sm.prefix, kmask = sm.kmask;
       for (int64_t i = tid; i < nI; i += RT) {
         const uint32_t kk = keys[i];
-        if (kk != 0 && (kk & kmask) == prefix) atomicAdd(&sm.hist[(kk >> (8 * pass)) & 255u], 1u);
+        // scores cluster in a few digit values: aggregate equal digits inside the warp before touching shared memory
+        const bool on = kk != 0 && (kk & kmask) == prefix;
+        const uint32_t digit = (kk >> (8 * pass)) & 255u;
+        const uint32_t active = __ballot_sync(__activemask(), on);
+        if (on) {
+          const uint32_t peers = __match_any_sync(active, digit);
+          if ((int)lane == __ffs(peers) - 1) atomicAdd(&sm.hist[digit], (unsigned)__popc(peers));
+        }
       }
       __syncthreads();
       if (tid == 0) {

@@ -43,7 +43,6 @@ namespace {
 constexpr int BM = 128;            // users per block  (TMEM lanes)
 constexpr int BN = 128;            // items per tile   (TMEM columns per accumulator stage)
 constexpr int BK = 64;             // 16-bit elements per k-block = one 128-byte swizzle row
-constexpr int UMMA_K = 16;         // K per tcgen05.mma for 16-bit inputs
 constexpr int SLAB_BYTES = BM * BK * 2;  // 16 KB: 128 rows x 128 B
 constexpr int TMEM_COLS = 512;     // accumulator stages (128 fp32 columns each) from column 0, the A operand at the top
 constexpr int EPI_WARPS = 8;       // warps that consume one tile (one set)
@@ -82,12 +81,110 @@ __device__ __forceinline__ float max32(const uint32_t* v) {
   return fmaxf(a, max8(v + 24));
 }
 
+// 2 delta of a user row in the (scaled) units of the tensor-core scores; same formula as select_topk.cu
+__device__ __forceinline__ float row_margin2(const FilterParams& p, int64_t row) {
+  int e2 = 0;
+  if (p.scale_exps != nullptr) e2 = p.scale_exps[0] + p.scale_exps[1];
+  const float nu = p.norms_u[row], nvmax = __uint_as_float(*p.nvmax_bits);
+  float delta = p.c_margin * nu * nvmax;
+  if (p.amax_bits != nullptr) {
+    const float au = __uint_as_float(p.amax_bits[0]), av = __uint_as_float(p.amax_bits[1]);
+    delta += 3.64e-12f * sqrtf((float)p.d) * (nu * av + nvmax * au);
+  }
+  return ldexpf(2.0f * delta, e2) * 1.0001f;
+}
+
+// Warp-cooperative tightening of ONE nearly full candidate list (large catalogues: the sampled hint cannot
+// resolve a 1e-5 quantile, so the list fills many times during a pass).  X = a lower bound of the need-th
+// largest score held by the list (need = k + seen_u + 8 real items score >= X, so at least k unmasked ones do):
+// the k-th best unmasked score of the row is >= X and nothing below X - 2 delta can reach the top-k.  The
+// threshold is raised to X - 2 delta and the groups that fall below it are dropped, order preserved.
+// Returns the new group count; thr_io is updated.  All 32 lanes call with the same arguments.
+__device__ __noinline__ uint32_t tighten_list(float* Ls, uint32_t* Li, uint32_t n, int need, float margin2, uint32_t nI,
+                                              float& thr_io) {
+  const uint32_t lane = lane_id();
+  const uint32_t lt = lanemask_lt();
+  constexpr int PER = LIST_CAP / 32;  // groups per lane
+  float4 a[PER], b[PER];
+  uint32_t it0[PER];
+  int n_el = 0;
+  uint32_t kmin = 0xffffffffu, kmax = 0;
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    const uint32_t g = (uint32_t)j * 32 + lane;
+    it0[j] = 0xffffffffu;
+    a[j] = b[j] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    if (g < n) {
+      it0[j] = Li[g];
+      a[j] = *reinterpret_cast<const float4*>(Ls + (size_t)g * GROUP);
+      b[j] = *reinterpret_cast<const float4*>(Ls + (size_t)g * GROUP + 4);
+      // columns past the catalogue (zero-filled operand rows) are not items
+      if (it0[j] + 0 >= nI) a[j].x = -INFINITY; if (it0[j] + 1 >= nI) a[j].y = -INFINITY;
+      if (it0[j] + 2 >= nI) a[j].z = -INFINITY; if (it0[j] + 3 >= nI) a[j].w = -INFINITY;
+      if (it0[j] + 4 >= nI) b[j].x = -INFINITY; if (it0[j] + 5 >= nI) b[j].y = -INFINITY;
+      if (it0[j] + 6 >= nI) b[j].z = -INFINITY; if (it0[j] + 7 >= nI) b[j].w = -INFINITY;
+      const float v[8] = {a[j].x, a[j].y, a[j].z, a[j].w, b[j].x, b[j].y, b[j].z, b[j].w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        if (v[e] > -INFINITY) {
+          const uint32_t kk = f32_to_key(__float_as_uint(v[e] + 0.0f));
+          ++n_el; kmin = min(kmin, kk); kmax = max(kmax, kk);
+        }
+      }
+    }
+  }
+  n_el = __reduce_add_sync(0xffffffffu, n_el);
+  kmin = __reduce_min_sync(0xffffffffu, kmin);
+  kmax = __reduce_max_sync(0xffffffffu, kmax);
+  if (n_el < need) return n;  // cannot certify a higher threshold: the caller declares the list overflowed
+  // bisection for a key with count(>= key) in [need, need + need/8]
+  uint32_t lo = kmin, hi = kmax + 1;
+  int c_lo = n_el;
+  const int c_ok = need + (need >> 3);
+  while (hi - lo > 1 && c_lo > c_ok) {
+    const uint32_t mid = lo + ((hi - lo) >> 1);
+    const float fm = __uint_as_float(key_to_f32(mid));
+    int c = 0;
+#pragma unroll
+    for (int j = 0; j < PER; ++j)
+      c += (a[j].x >= fm) + (a[j].y >= fm) + (a[j].z >= fm) + (a[j].w >= fm) + (b[j].x >= fm) + (b[j].y >= fm) +
+           (b[j].z >= fm) + (b[j].w >= fm);
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (c >= need) { lo = mid; c_lo = c; } else { hi = mid; }
+  }
+  const float X = __uint_as_float(key_to_f32(lo));
+  const float thr_new = fmaxf(thr_io, X - margin2);
+  thr_io = thr_new;
+  // order-preserving compaction: every group was read above, so in-place writes are safe
+  __syncwarp();
+  uint32_t outn = 0;
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    const float m = fmaxf(fmaxf(fmaxf(a[j].x, a[j].y), fmaxf(a[j].z, a[j].w)), fmaxf(fmaxf(b[j].x, b[j].y), fmaxf(b[j].z, b[j].w)));
+    const bool keep = it0[j] != 0xffffffffu && m >= thr_new;
+    const uint32_t kb = __ballot_sync(0xffffffffu, keep);
+    if (keep) {
+      const uint32_t pos = outn + __popc(kb & lt);
+      // pad columns were overwritten with -inf above: they can never be selected, which is what we want
+      *reinterpret_cast<float4*>(Ls + (size_t)pos * GROUP) = a[j];
+      *reinterpret_cast<float4*>(Ls + (size_t)pos * GROUP + 4) = b[j];
+      Li[pos] = it0[j];
+    }
+    outn += __popc(kb);
+  }
+  __syncwarp();
+  return outn;
+}
+
 // tile visited at schedule position s: N_SAMPLE strided sample tiles first (when hints are on),
 // then every tile in ascending order
 __device__ __forceinline__ int sched_tile(int s, int n_sample, int stride) {
   return s < n_sample ? s * stride : s - n_sample;
 }
 
+// TIGHTEN: large catalogues only (the out-of-line tightening call costs the hot loop ~15 % in register shuffling,
+// and below ~500k items the sampled hint keeps the lists short anyway).
+template <bool TIGHTEN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 score_filter_kernel(const __grid_constant__ CUtensorMap tmap_b, const FilterParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -307,8 +404,34 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmap_b, const FilterPara
       uint32_t* const Li_blk = p.list_item0 + (size_t)ub * (BM * 4) * (size_t)p.cap;
       const uint32_t goff = (uint32_t)((row_local * 4 + h * 2 + pset) * p.cap);
       uint32_t cnt = 0;
-      const uint32_t cap_lim = (uint32_t)(p.cap - GROUPS_PER_TILE);
+      // TIGHTEN: room is checked on every second tile of this thread, so two tiles' worth of slots are kept free
+      const uint32_t cap_lim = (uint32_t)(p.cap - (TIGHTEN ? 2 : 1) * GROUPS_PER_TILE);
       for (int t = pset; t < p.n_tiles; t += EPI_SETS) {
+        if (!TIGHTEN) {
+          if (cnt > cap_lim) { thr = INFINITY; cnt = (uint32_t)p.cap + 1; }  // overflow: stop, the row goes to the rescue kernel
+        } else if ((t & 2) == 0 && __any_sync(0xffffffffu, cnt > cap_lim)) {
+          // rare (large catalogues): lists that cannot take the next tiles' groups are tightened by the whole warp;
+          // everything the slow path needs is recomputed here to keep the hot loop's register set small
+          uint32_t full = __ballot_sync(0xffffffffu, valid_row && cnt > cap_lim && cnt <= (uint32_t)p.cap);
+          while (full) {
+            const int src = __ffs(full) - 1;
+            full &= full - 1;
+            const int64_t row_src = (int64_t)ub * BM + q * 32 + src;
+            int64_t seen_src = 0;
+            if (p.seen_rowptr != nullptr) seen_src = p.seen_rowptr[row_src + 1] - p.seen_rowptr[row_src];
+            const int64_t need64 = (int64_t)p.k + seen_src + 8;
+            const uint32_t n_src = __shfl_sync(0xffffffffu, cnt, src);
+            float thr_src = __shfl_sync(0xffffffffu, thr, src);
+            uint32_t n_new = n_src;
+            if (need64 + (need64 >> 3) + 16 <= (int64_t)cap_lim) {
+              const uint32_t g_src = (uint32_t)(((q * 32 + src) * 4 + h * 2 + pset) * p.cap);
+              n_new = tighten_list(Ls_blk + (size_t)g_src * GROUP, Li_blk + g_src, n_src, (int)need64, row_margin2(p, row_src),
+                                   (uint32_t)p.nI, thr_src);
+            }
+            if ((int)lane == src) { cnt = n_new; thr = thr_src; }
+          }
+          if (cnt > cap_lim) { thr = INFINITY; cnt = (uint32_t)p.cap + 1; }  // still no room: stop, the row goes to the rescue kernel
+        }
         const uint32_t seq = base_seq + (uint32_t)(n_sample + t), acc = seq % acc_stages, acc_phase = (seq / acc_stages) & 1;
         mbar_wait(smem_u32(&sm->acc_full[acc]), acc_phase);
         tc_fence_after();
@@ -322,7 +445,6 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmap_b, const FilterPara
         if (lane == 0) mbar_arrive(smem_u32(&sm->acc_empty[acc]));
 
         if (p.debug_mode == 1) continue;   // measurement aid: MMA + TMA pipeline alone (no filtering)
-        if (cnt > cap_lim) { thr = INFINITY; cnt = (uint32_t)p.cap + 1; }  // overflow: stop, the row goes to the rescue kernel
         const float thr_st = p.debug_mode == 2 ? INFINITY : thr;  // measurement aid: filter arithmetic without the stores
         const uint32_t item0 = (uint32_t)(t * BN + h * COLS_PER_THREAD);
 #pragma unroll
@@ -348,7 +470,7 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmap_b, const FilterPara
       }
       if (valid_row) {
         p.list_count[row * 4 + h * 2 + pset] = (int32_t)cnt;  // cap + 1 = overflowed
-        if (h == 0 && pset == 0) p.thr_out[row] = thr;         // every owner of the row computed the same hint
+        p.thr_out[row * 4 + h * 2 + pset] = thr;               // per list: the hint, raised wherever the list was tightened
       }
     }
   }
@@ -428,9 +550,16 @@ cudaError_t launch_score_filter(const void* A16, const void* B16, FilterParams p
   }
   const size_t smem = score_filter_smem_bytes(p.kblocks);
   const int grid = p.n_ublocks < sm_count ? p.n_ublocks : sm_count;
-  cudaError_t e = cudaFuncSetAttribute(score_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  score_filter_kernel<<<grid, NUM_THREADS, smem, stream>>>(tb, p);
+  cudaError_t e;
+  if (p.nI >= TIGHTEN_MIN_ITEMS) {
+    e = cudaFuncSetAttribute(score_filter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    score_filter_kernel<true><<<grid, NUM_THREADS, smem, stream>>>(tb, p);
+  } else {
+    e = cudaFuncSetAttribute(score_filter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    score_filter_kernel<false><<<grid, NUM_THREADS, smem, stream>>>(tb, p);
+  }
   count_launch();
   return cudaGetLastError();
 }

@@ -27,7 +27,6 @@ constexpr int SEL_WARPS = 4;
 constexpr int SEL_CAP = 768;              // candidate elements per row held in shared memory
 constexpr int SEEN_CAP = 512;             // seen items of the row staged in shared memory (longer lists stay in global)
 constexpr int SORT_N = 128;               // >= MAX_K, power of two
-constexpr int LOAD_B = 4;                 // candidate groups fetched per lane per batch (memory-level parallelism)
 
 struct SelSmem {
   uint32_t key[SEL_WARPS][SEL_CAP];
@@ -219,7 +218,8 @@ select_topk_kernel(const SelectParams p) {
   }
   const float margin2 = ldexpf(2.0f * delta, e2) * 1.0001f;
 
-  const float thr = p.thr[row];
+  const float4 thr4 = *reinterpret_cast<const float4*>(p.thr + row * LISTS_PER_ROW);
+  const float thr = fmaxf(fmaxf(thr4.x, thr4.y), fmaxf(thr4.z, thr4.w));  // everything >= the largest list threshold was captured by all lists
   uint32_t thr_key = (thr == -INFINITY) ? 0u : f32_to_key(__float_as_uint(thr + 0.0f));  // effective capture threshold
 
   // ---- A: enumerate ----
