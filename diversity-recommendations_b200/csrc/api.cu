@@ -2,6 +2,7 @@
 // kernel sequencing.  No torch types, no allocation, no device synchronisation.
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -211,7 +212,10 @@ static int score_topk_impl(const void* U, const void* V, int64_t nU, int64_t nI,
     sp.norms_u = norms_u; sp.nvmax_bits = nvmax; sp.inv_norm_v = inv_v;
     sp.out_scores = outs; sp.out_items = outi;
     sp.fail_rows = reinterpret_cast<int32_t*>(ws + w.offFail); sp.fail_count = fail_count;
+    sp.fail_reasons = reinterpret_cast<int32_t*>(scal) + 8;
     sp.force_fail = tensor ? 0 : 1;
+    const bool no_rescue = getenv("DIVREC_DEBUG_NO_RESCUE") != nullptr;  // debugging aid: leave uncertified rows undone
+    sp.debug_dump = no_rescue ? 1 : 0;
     sp.out_ild = out_ild ? out_ild + u0 : nullptr; sp.coverage = coverage;
 
     if (u0 > 0) {
@@ -269,7 +273,7 @@ static int score_topk_impl(const void* U, const void* V, int64_t nU, int64_t nI,
     rp2.scratch = reinterpret_cast<uint32_t*>(ws + w.offRescue); rp2.grid = w.rescue_grid;
     rp2.out_scores = outs; rp2.out_items = outi; rp2.out_ild = sp.out_ild; rp2.coverage = coverage;
     prof_mark(PROF_RESCUE, 0, st);
-    e = launch_rescue(rp2, st);
+    e = no_rescue ? cudaSuccess : launch_rescue(rp2, st);
     if (e != cudaSuccess) return cuda_fail(e, "rescue launch");
     prof_mark(PROF_RESCUE, 1, st);
     e = launch_add_counter(fail_count, reinterpret_cast<int32_t*>(scal) + 6, st);  // statistics: rows re-done exactly
@@ -297,9 +301,13 @@ int divrec_score_topk_rescued(const void* workspace, int64_t nU, int64_t nI, int
   if (!workspace || !host_out || nU <= 0 || nI <= 0 || d <= 0) return fail(DIVREC_ERR_ARG, "score_topk_rescued: bad argument");
   const WsLayout w = ws_layout(nU, nI, d, dtype);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  cudaError_t e = cudaMemcpyAsync(host_out, reinterpret_cast<const uint8_t*>(workspace) + w.offScalars + 6 * sizeof(int32_t),
-                                  sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+  // host_out[0] = rows re-done exactly; host_out[1..4] = by reason: list overflow / forced, too many candidates,
+  // hint not certified, too few captured
+  int32_t tmp[6];
+  cudaError_t e = cudaMemcpyAsync(tmp, reinterpret_cast<const uint8_t*>(workspace) + w.offScalars + 6 * sizeof(int32_t),
+                                  6 * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e == cudaSuccess) { host_out[0] = tmp[0]; for (int i = 0; i < 4; ++i) host_out[1 + i] = tmp[2 + i]; }
   if (e != cudaSuccess) return cuda_fail(e, "score_topk_rescued");
   return DIVREC_OK;
 }

@@ -81,6 +81,8 @@ struct SelectParams {
   int64_t* out_items;          // [nU,k]
   int32_t* fail_rows;          // [nU] rows the tensor-core path could not certify
   int32_t* fail_count;         // device counter (zeroed by the caller)
+  int32_t* fail_reasons;       // device [4] statistics by reason (see report_fail), may be null
+  int debug_dump;              // 1 = uncertified rows leave their diagnostics in out_scores (env DIVREC_DEBUG_NO_RESCUE)
   int force_fail;              // 1 = send every row to the rescue kernel (DIVREC_MODE_SIMT)
   float* out_ild;              // [nU] fused cosine ILD of the row's top-k (null = off; needs d % 4 == 0, d <= 512)
   int32_t* coverage;           // [>= nI + offset] fused coverage histogram over global item ids (null = off)

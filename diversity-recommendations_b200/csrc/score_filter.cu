@@ -541,7 +541,10 @@ cudaError_t launch_score_filter(const void* A16, const void* B16, FilterParams p
   p.n_tiles = (p.nI + BN - 1) / BN;
   p.b_stages = score_filter_b_stages(p.kblocks);
   p.acc_stages = (TMEM_COLS - K / 2) / BN;
-  if (p.use_hint && p.n_tiles >= HINT_MIN_TILES) {
+  // Large catalogues: 2048 sampled scores cannot resolve a 1e-5 quantile, and an uncertified row would cost a full
+  // exact pass over millions of items.  They start from thr = -inf instead and rely on the online tightening
+  // alone: every threshold is then a validated bound and no row depends on the rescue kernel.
+  if (p.use_hint && p.n_tiles >= HINT_MIN_TILES && p.nI < TIGHTEN_MIN_ITEMS) {
     p.n_sample = N_SAMPLE;
     p.sample_stride = (p.n_tiles - 1) / N_SAMPLE;  // sample tiles are full tiles (never the ragged last one)
   } else {

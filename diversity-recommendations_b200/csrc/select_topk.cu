@@ -167,10 +167,12 @@ __device__ __forceinline__ int scan_groups(const SelectParams& p, int64_t row, c
   return total;
 }
 
-__device__ __forceinline__ void report_fail(const SelectParams& p, int64_t row, uint32_t lane) {
+// reason: 0 forced / list overflow, 1 too many candidates, 2 threshold hint not certified, 3 too few captured
+__device__ __forceinline__ void report_fail(const SelectParams& p, int64_t row, uint32_t lane, int reason = 0) {
   if (lane == 0) {
     const int slot = atomicAdd(p.fail_count, 1);
     p.fail_rows[slot] = (int32_t)row;
+    if (p.fail_reasons != nullptr) atomicAdd(p.fail_reasons + reason, 1);
   }
 }
 
@@ -227,21 +229,22 @@ select_topk_kernel(const SelectParams p) {
   if (ne > SEL_CAP) {
     // coarse cut: X = the need-th largest captured score, need = k + seen_u  =>  k-th best unmasked >= X
     const int64_t need64 = (int64_t)k + seen_u;
-    if (need64 >= ne) { report_fail(p, row, lane); return; }
+    if (need64 >= ne) { report_fail(p, row, lane, 1); return; }
     const int need = (int)need64;
     uint32_t lo = thr_key > KEY_NEG_INF ? thr_key : KEY_NEG_INF + 1, hi = 0xff800000u;  // hi: above every finite key
     while (hi - lo > 1) {
       const uint32_t mid = lo + ((hi - lo) >> 1);
       const int c = scan_groups<false>(p, row, nl, __uint_as_float(key_to_f32(mid)), key, id, lane);
       if (c >= need) lo = mid; else hi = mid;
-      if (c >= need && c <= need + need / 8) break;  // close enough
+      // no early exit: X must be the exact need-th largest so that X - 2 delta can only raise the capture
+      // threshold (lists tightened by the filter were cut at a (need + 8)-th largest, which X dominates)
     }
     const float X = __uint_as_float(key_to_f32(lo));
     const uint32_t cut_key = f32_to_key(__float_as_uint((X - margin2) + 0.0f));
-    if (cut_key <= thr_key) { report_fail(p, row, lane); return; }
+    if (cut_key <= thr_key) { report_fail(p, row, lane, 1); return; }
     thr_key = cut_key;
     ne = scan_groups<true>(p, row, nl, __uint_as_float(key_to_f32(thr_key)), key, id, lane);
-    if (ne > SEL_CAP) { report_fail(p, row, lane); return; }
+    if (ne > SEL_CAP) { report_fail(p, row, lane, 1); return; }
   }
 
   // ---- B: seen-item mask (each candidate looked up in the row's sorted seen list) ----
@@ -281,18 +284,34 @@ select_topk_kernel(const SelectParams p) {
     uint32_t lo = kmin, hi = kmax + 1;
     int c_lo = nv;
     const int c_ok = k + max(2, k >> 4);
-    while (hi - lo > 1 && c_lo > c_ok) {
-      const uint32_t mid = lo + ((hi - lo) >> 1);
-      int c = 0;
-      for (int i = lane; i < ne; i += 32) c += (key[i] >= mid) ? 1 : 0;
-      c = __reduce_add_sync(0xffffffffu, c);
-      if (c >= k) { lo = mid; c_lo = c; } else { hi = mid; }
+    bool exact = false;
+    // a loose T (count up to k + k/16) is enough unless it drops T - 2 delta below the capture threshold: then the
+    // bisection continues to the exact k-th key before the row is declared uncertifiable
+    for (;;) {
+      while (hi - lo > 1 && (exact || c_lo > c_ok)) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        int c = 0;
+        for (int i = lane; i < ne; i += 32) c += (key[i] >= mid) ? 1 : 0;
+        c = __reduce_add_sync(0xffffffffu, c);
+        if (c >= k) { lo = mid; c_lo = c; } else { hi = mid; }
+      }
+      const float T = __uint_as_float(key_to_f32(lo));
+      cut = f32_to_key(__float_as_uint((T - margin2) + 0.0f));
+      if (thr_key == 0 || cut >= thr_key) break;          // certified
+      if (exact) {  // T is the exact k-th key (largest key with at least k candidates at or above it): not certifiable
+        if (p.debug_dump && lane == 0) {
+          float* o = p.out_scores + row * k;
+          o[0] = T; o[1] = margin2; o[2] = thr4.x; o[3] = thr4.y; o[4] = thr4.z; o[5] = thr4.w; o[6] = (float)ne; o[7] = (float)nv;
+          o[8] = (float)nl.x; o[9] = (float)nl.y; o[10] = (float)nl.z; o[11] = (float)nl.w; o[12] = (float)c_lo;
+          p.out_items[row * k] = -1002;
+        }
+        report_fail(p, row, lane, 2);
+        return;
+      }
+      exact = true;                                       // bisect down to the exact k-th key and try again
     }
-    const float T = __uint_as_float(key_to_f32(lo));
-    cut = f32_to_key(__float_as_uint((T - margin2) + 0.0f));
-    if (thr_key != 0 && cut < thr_key) { report_fail(p, row, lane); return; }  // not certified
   } else if (thr_key != 0) {
-    report_fail(p, row, lane);  // fewer than k unmasked candidates captured above a threshold
+    report_fail(p, row, lane, 3);  // fewer than k unmasked candidates captured above a threshold
     return;
   }
 

@@ -179,9 +179,10 @@ def score_topk(U: torch.Tensor, V: torch.Tensor, k: int, seen_rowptr: Optional[t
                                    item_id_offset, k, _ptr(out_s), _ptr(out_i), _ptr(ws), ws_bytes, _stream(U.device))
         _check(rc, "divrec_score_topk")
         if return_stats:
-            n = _c.c_int32(0)
-            _check(lib.divrec_score_topk_rescued(_ptr(ws), nU, nI, d, dt, _c.byref(n), _stream(U.device)), "divrec_score_topk_rescued")
-            return out_s, out_i, {"rescued_rows": int(n.value)}
+            n = (_c.c_int32 * 5)()
+            _check(lib.divrec_score_topk_rescued(_ptr(ws), nU, nI, d, dt, n, _stream(U.device)), "divrec_score_topk_rescued")
+            return out_s, out_i, {"rescued_rows": int(n[0]), "list_overflow": int(n[1]), "too_many_candidates": int(n[2]),
+                                  "hint_not_certified": int(n[3]), "too_few_captured": int(n[4])}
     return out_s, out_i
 
 

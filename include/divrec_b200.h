@@ -89,8 +89,9 @@ int divrec_profile_read(float* ms_out /*host*/, int n);
  *   than k unmasked items are padded with score -inf / item -1.
  *   Limits of this version: k <= 128; d <= 512 in DIVREC_MODE_TENSOR; nI < 2^31; tables 16-byte aligned;
  *   finite inputs.  Users are processed in internal passes of <= 151 552 rows, which bounds the workspace.
- *   divrec_score_topk_rescued: (host call, synchronises `stream`) how many rows of the last call on this
- *   workspace were re-done by the exact SIMT kernel.
+ *   divrec_score_topk_rescued: (host call, synchronises `stream`) host_out[0] = how many rows of the last call on
+ *   this workspace were re-done by the exact SIMT kernel; host_out[1..4] = why (candidate-list overflow or forced,
+ *   too many candidates, threshold hint not certified, too few candidates captured).  host_out holds 5 ints.
  * ------------------------------------------------------------------------------------- */
 size_t divrec_score_topk_workspace(int64_t nU, int64_t nI, int d, int dtype, int k);
 
@@ -114,7 +115,7 @@ int divrec_score_topk_metrics(const void* U, const void* V, int64_t nU, int64_t 
                               int32_t* coverage_counts, void* workspace, size_t ws_bytes, void* stream);
 
 int divrec_score_topk_rescued(const void* workspace, int64_t nU, int64_t nI, int d, int dtype,
-                                int32_t* host_out /*host*/, void* stream);
+                                int32_t* host_out /*host [5]*/, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * merge per-shard top-k lists after the all-gather (item-sharded catalogue)
