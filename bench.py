@@ -111,7 +111,14 @@ def run_step_device(N, model_U, V, rowptr, items, k, nI, counts):
     return s, i, ild
 
 
+def _quiet_nccl():
+    """NCCL prints its version banner on stdout when NCCL_DEBUG=VERSION/INFO; the contract is ONE JSON line."""
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE") and not os.environ.get("DIVREC_KEEP_NCCL_DEBUG"):
+        os.environ["NCCL_DEBUG"] = "WARN"
+
+
 def bench_ours(args):
+    _quiet_nccl()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -238,6 +245,7 @@ def bench_cfg4(args):
     """BASELINE.json configs[3]: 10M-item x d=256 bf16 item table sharded over the GPUs, 65 536 query users per step,
     per-shard score + top-100, NCCL all-gather of the per-shard lists, n-way merge.  Strong scaling: the
     catalogue is fixed, every rank holds 1/N of it.  Synthetic N(0,1) bf16 tables generated on the device."""
+    _quiet_nccl()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
