@@ -473,4 +473,28 @@ int divrec_bpr_loss_bwd(const float* pos, const float* neg, const float* g, int6
   return DIVREC_OK;
 }
 
+size_t divrec_mmr_workspace(int C, int d) {
+  if (C <= 0 || d <= 0) return 0;
+  return mmr_scratch_bytes(C, d, nullptr);
+}
+
+int divrec_mmr_rerank(const void* V, int64_t nI, int d, int dtype, const int64_t* cand_items, const float* cand_scores,
+                      int64_t nU, int C, int k, float lambda, int64_t* out_items, float* out_scores, void* workspace,
+                      size_t ws_bytes, void* stream) {
+  if (!V || !cand_items || !cand_scores || !out_items) return fail(DIVREC_ERR_ARG, "mmr_rerank: null pointer");
+  if (nI <= 0 || nU <= 0 || d <= 0 || C <= 0 || k <= 0 || k > C) return fail(DIVREC_ERR_ARG, "mmr_rerank: need nI, nU, d > 0 and 0 < k <= C");
+  if (dtype != DIVREC_F32 && dtype != DIVREC_BF16) return fail(DIVREC_ERR_ARG, "mmr_rerank: unknown dtype");
+  if (!(lambda >= 0.0f && lambda <= 1.0f)) return fail(DIVREC_ERR_ARG, "mmr_rerank: lambda must be in [0, 1]");
+  if ((size_t)((d + 3) & ~3) * 4 + (size_t)C * 12 > 200 * 1024) return fail(DIVREC_ERR_ARG, "mmr_rerank: C and d too large for shared memory");
+  if (!workspace || ws_bytes < mmr_scratch_bytes(C, d, nullptr)) return fail(DIVREC_ERR_WORKSPACE, "mmr_rerank: workspace too small");
+  if (reinterpret_cast<uintptr_t>(workspace) & 15) return fail(DIVREC_ERR_ARG, "mmr_rerank: workspace must be 16-byte aligned");
+  MmrParams mp{};
+  mp.V = V; mp.nI = nI; mp.d = d; mp.dtype = dtype; mp.cand_items = cand_items; mp.cand_scores = cand_scores; mp.nU = nU;
+  mp.C = C; mp.k = k; mp.lambda = lambda; mp.scratch = reinterpret_cast<float*>(workspace); mp.out_items = out_items;
+  mp.out_scores = out_scores;
+  cudaError_t e = launch_mmr(mp, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "mmr launch");
+  return DIVREC_OK;
+}
+
 }  // extern "C"

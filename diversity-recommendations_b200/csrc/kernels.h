@@ -146,4 +146,20 @@ cudaError_t launch_bpr_loss_fwd(const float* pos, const float* neg, int64_t B, f
 cudaError_t launch_bpr_loss_bwd(const float* pos, const float* neg, const float* g, int64_t B, float* gpos, float* gneg,
                                 cudaStream_t stream);
 
+struct MmrParams {
+  const void* V;
+  int64_t nI;
+  int d, dtype;
+  const int64_t* cand_items;   // [nU, C] sorted by (score desc, id asc), padded with -1
+  const float* cand_scores;    // [nU, C]
+  int64_t nU;
+  int C, k;
+  float lambda;
+  float* scratch;              // mmr_scratch_bytes
+  int64_t* out_items;          // [nU, k]
+  float* out_scores;           // [nU, k] relevance scores of the picks, or null
+};
+size_t mmr_scratch_bytes(int C, int d, int* grid_out);
+cudaError_t launch_mmr(MmrParams p, cudaStream_t stream);
+
 }  // namespace divrec

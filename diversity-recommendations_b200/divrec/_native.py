@@ -51,6 +51,8 @@ SIGNATURES = {
     "divrec_relevance_metrics": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp]),
     "divrec_bpr_loss_fwd": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp]),
     "divrec_bpr_loss_bwd": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "divrec_mmr_workspace": (_sz, [_i32, _i32]),
+    "divrec_mmr_rerank": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp, _i64, _i32, _i32, _f32, _vp, _vp, _vp, _sz, _vp]),
 }
 
 _lib = None
@@ -445,3 +447,25 @@ def bpr_loss_bwd(pos: torch.Tensor, neg: torch.Tensor, g: torch.Tensor) -> Tuple
         rc = lib.divrec_bpr_loss_bwd(_ptr(pos), _ptr(neg), _ptr(g), pos.numel(), _ptr(gp), _ptr(gn), _stream(pos.device))
     _check(rc, "divrec_bpr_loss_bwd")
     return gp, gn
+
+
+def mmr_rerank(V: torch.Tensor, cand_items: torch.Tensor, cand_scores: torch.Tensor, k: int, lam: float):
+    """Greedy MMR re-rank of each user's candidate list: (items [nU,k] int64, scores [nU,k] fp32 of the picks)."""
+    lib = load_library()
+    V = _cuda(V, "V")
+    dt = _table_dtype(V)
+    cand_items = _cuda(cand_items, "cand_items", torch.int64)
+    cand_scores = _cuda(cand_scores, "cand_scores", torch.float32)
+    if cand_items.dim() != 2 or cand_items.shape != cand_scores.shape:
+        raise ValueError("cand_items / cand_scores must be [nU, C]")
+    nU, C = cand_items.shape
+    nI, d = V.shape
+    out_i = torch.empty((nU, k), dtype=torch.int64, device=V.device)
+    out_s = torch.empty((nU, k), dtype=torch.float32, device=V.device)
+    with torch.cuda.device(V.device):
+        nbytes = lib.divrec_mmr_workspace(C, d)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=V.device)
+        rc = lib.divrec_mmr_rerank(_ptr(V), nI, d, dt, _ptr(cand_items), _ptr(cand_scores), nU, C, k, float(lam),
+                                   _ptr(out_i), _ptr(out_s), _ptr(ws), nbytes, _stream(V.device))
+    _check(rc, "divrec_mmr_rerank")
+    return out_i, out_s

@@ -214,6 +214,21 @@ int divrec_bpr_loss_fwd(const float* pos, const float* neg, int64_t B, float* lo
 int divrec_bpr_loss_bwd(const float* pos, const float* neg, const float* g, int64_t B, float* gpos,
                         float* gneg, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * greedy MMR-style re-rank of each user's top-C candidates (BASELINE.json config 5)
+ *   The reference has NO implementation of this (README.md:3-5 only announces "tools for increasing ...
+ *   diversity"; divrec/train/utils.py:167-216 cannot run): semantics are those of
+ *   oracle/divrec_oracle.py::mmr_rerank -- parity is pinned on the oracle, not on the reference.
+ *   cand_items [nU,C] (sorted by (score desc, id asc), padded with -1) / cand_scores [nU,C] are the output of
+ *   divrec_score_topk with k = C.  First pick = candidate 0, then k-1 times
+ *       argmax_c  lambda * score_c - (1 - lambda) * max_{j picked} cos(V_c, V_j)     (ties -> lowest rank).
+ *   out_items [nU,k] (padded with -1), out_scores [nU,k] (relevance of the picks) may be NULL.
+ * ------------------------------------------------------------------------------------- */
+size_t divrec_mmr_workspace(int C, int d);
+int divrec_mmr_rerank(const void* V, int64_t nI, int d, int dtype, const int64_t* cand_items,
+                      const float* cand_scores, int64_t nU, int C, int k, float lambda,
+                      int64_t* out_items, float* out_scores, void* workspace, size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -21,7 +21,7 @@ def header_functions():
 def test_header_declares_the_hot_path():
     fns = header_functions()
     for needed in ("divrec_score_topk", "divrec_topk_merge", "divrec_ild_cosine", "divrec_coverage_hist",
-                   "divrec_bpr_fwd", "divrec_bpr_bwd"):
+                   "divrec_bpr_fwd", "divrec_bpr_bwd", "divrec_mmr_rerank", "divrec_score_topk_metrics"):
         assert needed in fns, needed
 
 
@@ -69,5 +69,6 @@ def test_no_fallback_imports_in_product():
         for f in files:
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
-                assert "oracle" not in src.replace("# oracle", ""), os.path.join(dirpath, f)
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), os.path.join(dirpath, f)
+                assert "divrec_oracle as" not in src and "import_module(\"oracle" not in src
                 assert "import triton" not in src and "torch.compile" not in src

@@ -422,6 +422,48 @@ def test_shim_end_to_end_matches_reference_golden(native, dev):
         assert (got.cpu() - want).abs().max().item() <= REL * float(want.abs().max())
 
 
+def test_mmr_rerank_vs_oracle(native, dev):
+    """Greedy MMR re-rank (no reference implementation: parity is against the oracle).  Greedy arg-max chains are
+    sensitive to last-bit differences, so every pick is checked to be an (almost) maximiser of the oracle's
+    objective given the picks made so far, and identical whenever the oracle's margin is clear."""
+    from divrec.rerank import mmr_rerank
+    gen = torch.Generator().manual_seed(61)
+    nU, nI, d, C, k = 24, 4000, 64, 120, 30
+    U, V = O.make_embeddings(nU, d, "gauss", gen), O.make_embeddings(nI, d, "gauss", gen)
+    cand, sc = O.recommendations_dense(U, V, None, None, C)
+    cand[3, 100:] = -1   # a ragged candidate list
+    sc[3, 100:] = float("-inf")
+    for lam in (1.0, 0.5, 0.2):
+        want = O.mmr_rerank(cand, sc, V, k, lam)
+        got, rel = mmr_rerank(V.to(dev), cand.to(dev), sc.to(dev), k, lam)
+        got, rel = got.cpu(), rel.cpu()
+        assert torch.equal(got[:, 0], cand[:, 0])
+        if lam == 1.0:
+            assert torch.equal(got, cand[:, :k])
+        En = (V / V.norm(dim=1, keepdim=True)).double()
+        n_diff = 0
+        for u in range(nU):
+            ids = cand[u]
+            valid = ids >= 0
+            E = En[ids.clamp(min=0)]
+            picked = []
+            for r in range(k):
+                j = int((ids == got[u, r]).nonzero()[0]) if got[u, r] >= 0 else -1
+                assert j >= 0 and valid[j] and j not in picked
+                if r > 0:
+                    maxsim = (E @ E[picked].T).max(dim=1).values
+                    obj = lam * sc[u].double() - (1 - lam) * maxsim
+                    obj[picked] = float("-inf")
+                    obj[~valid] = float("-inf")
+                    assert float(obj[j]) >= float(obj.max()) - 1e-5     # an (almost) maximiser
+                picked.append(j)
+                assert float(rel[u, r]) == float(sc[u, j])
+            n_diff += int((got[u] != want[u]).any())
+        assert n_diff <= 2   # identical lists except where two objectives tie to ~1e-7
+        if lam < 1.0:        # re-ranking must not reduce the intra-list diversity
+            assert float(O.ild_cosine(got, V).mean()) >= float(O.ild_cosine(cand[:, :k], V).mean()) - 1e-6
+
+
 def test_host_buffer_pipeline_equals_resident_path(native, dev):
     """divrec.train.host_recommend_and_score (pinned host buffers, chunked and overlapped copies) must return
     exactly what the device-resident fused call returns."""
