@@ -339,6 +339,115 @@ def bench_cfg4(args):
         dist.destroy_process_group()
 
 
+def bench_cfg3(args):
+    """BASELINE.json configs[2]: BPR training step, 1M users x 1M items, d = 128 fp32, B = 65 536 triples per GPU:
+    fused gather + loss + AUC forward and scatter-add backward into dense gradient tables (the reference's
+    autograd semantics).  Users sharded: each rank draws its triples' users from its own range; the item-table
+    gradient is all-reduced.  Gradient buffers persist across steps (zero_grad belongs to the optimiser: out of scope)."""
+    _quiet_nccl()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    from divrec import _native as N, parallel
+    N.load_library()
+    nU = nI = 1_000_000
+    d, B = 128, 65536
+    g = torch.Generator(device=dev).manual_seed(5)
+    U = torch.randn((nU, d), generator=g, device=dev)
+    V = torch.randn((nI, d), generator=g, device=dev)
+    a, b = parallel.shard_range(nU, rank, world)
+    gh = torch.Generator().manual_seed(100 + rank)
+    uh = torch.randint(a, b, (B,), generator=gh).pin_memory()
+    ph = torch.randint(0, nI, (B,), generator=gh).pin_memory()
+    nh = torch.randint(0, nI, (B,), generator=gh).pin_memory()
+    u, p_, n_ = uh.to(dev), ph.to(dev), nh.to(dev)
+    gU, gV = torch.zeros_like(U), torch.zeros_like(V)
+    Bg = B * world
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(uu, pp, nn):
+        pos, neg, loss_sum, auc_sum = N.bpr_fwd(U, V, uu, pp, nn)
+        N.bpr_bwd(U, V, uu, pp, nn, pos, neg, 1.0 / Bg, gU, gV)
+        if dist is not None:
+            dist.all_reduce(gV)
+            dist.all_reduce(loss_sum)
+        return loss_sum
+
+    for _ in range(max(3, args.warmup)):
+        step(u, p_, n_)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = N.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step(u, p_, n_)
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    launches = N.launch_count() - l0
+    # kernels alone (no collective) for the roofline
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record()
+    for _ in range(args.steps):
+        pos, neg, ls, au = N.bpr_fwd(U, V, u, p_, n_)
+        N.bpr_bwd(U, V, u, p_, n_, pos, neg, 1.0 / Bg, gU, gV)
+    k1.record()
+    torch.cuda.synchronize()
+    kms = k0.elapsed_time(k1) / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    loss_h = torch.empty(1, dtype=torch.float32).pin_memory()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0.record()
+    for _ in range(args.steps):
+        u.copy_(uh, non_blocking=True); p_.copy_(ph, non_blocking=True); n_.copy_(nh, non_blocking=True)
+        ls = step(u, p_, n_)
+        loss_h.copy_(ls, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    t1.record()
+    barrier()
+    e2e = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(e2e, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        pk = peaks()
+        ms_per_step = float(ms) / args.steps
+        bytes_per_triple = 3 * d * 4 + 3 * 2 * d * 4 + 24   # 3 row reads + 3 row read-modify-writes + ids (SURVEY.md 8d)
+        ach = B * bytes_per_triple / (kms * 1e-3) / 1e9
+        line = {"metric": "BPR triples/sec (gather + loss + scatter-add backward)", "value": Bg / (ms_per_step * 1e-3), "unit": "triples/s",
+                "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "cfg3: BPR step, 1M users x 1M items", "d": d, "triples_per_gpu": B,
+                           "sharding": "triples partitioned by user shard; item-gradient all-reduce" if world > 1 else "single GPU",
+                           "l2": "tables + dense gradients (2 GB) exceed the 126 MB L2"},
+                "clocks": clocks,
+                "e2e": {"value": Bg / (float(e2e) / args.steps * 1e-3), "unit": "triples/s", "h2d_bytes_per_step": 3 * B * 8,
+                        "d2h_bytes_per_step": 4, "api": "divrec._native.bpr_fwd / bpr_bwd (triples from pinned host memory, loss back)"},
+                "gpu_launches": int(launches),
+                "roofline": {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
+                             "traffic": None, "kernel": "bpr_fwd_kernel + bpr_bwd_kernel", "kernel_ms": kms,
+                             "algorithmic_bytes_per_launch": B * bytes_per_triple, "peak_source": pk["source"] + " copy bandwidth"},
+                "cpu_baseline": None}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def cpu_baseline(workload, sample_users):
     """The oracle port (dense torch-CPU restatement of the reference loop) on this box's host cores."""
     from oracle import divrec_oracle as O
@@ -399,7 +508,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS) + ["cfg4"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS) + ["cfg3", "cfg4"])
     ap.add_argument("--cfg4-items", type=int, default=10_000_000)
     ap.add_argument("--cfg4-queries", type=int, default=65536)
     ap.add_argument("--cpu-sample", type=int, default=32768)
@@ -412,6 +521,8 @@ def main():
             sys.exit("bench.py: no CUDA device -- divrec_b200 has no CPU path (use --impl reference for the CPU oracle)")
         if args.workload == "cfg4":
             bench_cfg4(args)
+        elif args.workload == "cfg3":
+            bench_cfg3(args)
         else:
             bench_ours(args)
 
