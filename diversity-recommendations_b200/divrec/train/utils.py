@@ -76,10 +76,44 @@ def get_model_recommendations(dataset: RankingDataset, model: RankingModel, numb
 
 def recommendations_score_loop(dataset: RankingDataset, model: RankingModel, losses: List[RecommendationsAwareLoss],
                                number_of_recommendations: int):
+    """[loss(interactions, recommendations) for loss in losses] as in the reference (train/utils.py:80-91).
+    With a MatrixFactorization model, a cosine IntraListDiversityScore over the model's own item table and an
+    EntropyDiversityScore are not computed from the [U,k] lists afterwards: their per-user ILD and coverage
+    histogram come out of the fused selection kernel (divrec_score_topk_metrics) in the same pass."""
+    import math
+    from ..losses import IntraListDiversityScore
+    from ..metrics import EntropyDiversityScore
     model.eval()
     interactions = dataset.data.interactions
-    recommendations = get_model_recommendations(dataset, model, number_of_recommendations)
-    return [loss(interactions, recommendations) for loss in losses]
+    k = int(number_of_recommendations)
+    dev = _model_device(model)
+    fused = {}
+    if isinstance(model, MatrixFactorization) and dev.type == "cuda":
+        V = model.item_embeddings.weight
+        for i, loss in enumerate(losses):
+            if (type(loss) is IntraListDiversityScore and loss.item_embeddings is not None and loss.ild_mode == "sumvec"
+                    and loss.item_embeddings.data_ptr() == V.data_ptr() and k >= 2 and V.shape[1] % 4 == 0 and V.shape[1] <= 256):
+                fused[i] = "ild"
+            elif type(loss) is EntropyDiversityScore and int(loss.dataset.number_of_items) == V.shape[0]:
+                fused[i] = "entropy"
+    if not fused:
+        recommendations = get_model_recommendations(dataset, model, k)
+        return [loss(interactions, recommendations) for loss in losses]
+    with torch.no_grad():
+        rowptr, items = dataset.seen_csr(dev)
+        _scores, recommendations, ild, counts = _native.score_topk_metrics(
+            model.user_embeddings.weight, model.item_embeddings.weight, k, rowptr, items if items.numel() else None,
+            want_ild="ild" in fused.values(), want_coverage="entropy" in fused.values())
+    out = []
+    for i, loss in enumerate(losses):
+        if fused.get(i) == "ild":
+            out.append(loss.reduce_loss_values(ild))
+        elif fused.get(i) == "entropy":
+            entropy = _native.entropy_from_counts(counts)[0]
+            out.append((entropy - math.log(k)) / (loss.max_entropy - math.log(k)))
+        else:
+            out.append(loss(interactions, recommendations))
+    return out
 
 
 def point_wise_train_loop(dataset: PointWiseDataset, model: RankingModel, loss: PointWiseLoss,
