@@ -37,6 +37,9 @@ WORKLOADS = {
     "cfg1": (943, 1682, 64, 10, 90570),
 }
 METRIC = "users/sec scored (score+top-k+ILD)"
+# dram__bytes_read.sum + dram__bytes_write.sum per launch at cfg2, from the committed ncu --set full capture
+# (profiles/r01_ncu_filter_select_v5.txt); bench.py cannot run ncu itself
+NCU_DRAM_TRAFFIC_CFG2 = {"score_filter_kernel": 0.171565e9 + 2.365629e9, "select_topk_kernel": 2.551790e9 + 0.166450e9}
 
 
 def peaks():
@@ -230,8 +233,11 @@ def bench_ours(args):
                 "api": "divrec.train.host_recommend_and_score (pinned host buffers -> C ABI -> host results)"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "score_filter_kernel", "kernel_ms": kms,
+                     "traffic": NCU_DRAM_TRAFFIC_CFG2["score_filter_kernel"] if args.workload == "cfg2" else None,
+                     "kernel": "score_filter_kernel", "kernel_ms": kms,
                      "algorithmic_flop_per_launch": flop, "peak_source": pk["source"] + " bf16 sustained (kernel timed inside a long step)"},
+        # the selection kernel is the other large share of the step (ncu launch list: profiles/r01_ncu_launches_v5.txt)
+        "roofline_select": select_roofline(phases, nU, d, k, pk, args.workload),
         "cpu_baseline": cpu,
         "phases_ms": {name: sorted(ph[name] for ph in phases)[len(phases) // 2] for name in phases[0]},
         "rescued_rows_per_step": stats["rescued_rows"],
@@ -446,6 +452,19 @@ def bench_cfg3(args):
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
+
+
+def select_roofline(phases, nU, d, k, pk, workload):
+    """HBM view of select_topk_kernel: candidate groups (~490 x 36 B per user at cfg2) + k row gathers + outputs."""
+    ms = sorted(ph["select_ms"] for ph in phases)[len(phases) // 2]
+    groups = 490 if workload == "cfg2" else None
+    if groups is None:
+        return {"kernel": "select_topk_kernel", "kernel_ms": ms}
+    algo = nU * (groups * 36 + k * d * 4 + k * 12 + 4)
+    ach = algo / (ms * 1e-3) / 1e9
+    return {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
+            "traffic": NCU_DRAM_TRAFFIC_CFG2["select_topk_kernel"], "kernel": "select_topk_kernel", "kernel_ms": ms,
+            "algorithmic_bytes_per_launch": algo, "note": "issue-bound, not bandwidth-bound (ncu: issue slots 58 % busy, row gathers hit L2)"}
 
 
 def cpu_baseline(workload, sample_users):
