@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libdivrec_b200.so")
 OBJ_DIR = os.path.join(HERE, "build")
-SOURCES = ["api.cu", "score_filter.cu", "select_topk.cu", "rescue.cu", "prep.cu", "metrics.cu", "bpr.cu", "mmr.cu"]
+SOURCES = ["api.cu", "score_filter.cu", "select_topk.cu", "rescue.cu", "prep.cu", "metrics.cu", "bpr.cu", "mmr.cu", "score_filter2.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

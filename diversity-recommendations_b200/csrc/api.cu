@@ -253,7 +253,11 @@ static int score_topk_impl(const void* U, const void* V, int64_t nU, int64_t nI,
       fp.c_margin = sp.c_margin; fp.d = d;
       const char* err = "";
       prof_mark(PROF_FILTER, 0, st);
-      e = launch_score_filter(A16, B16, fp, device_info().sm_count, st, &err);
+      // the common shape (d <= 128, catalogue below the online-tightening threshold) scores two user blocks per CTA
+      const bool two_blocks = w.K <= 128 && nI < TIGHTEN_MIN_ITEMS && !getenv("DIVREC_DEBUG_ONE_BLOCK");
+      sp.merged_lists = two_blocks ? 1 : 0;
+      e = two_blocks ? launch_score_filter2(A16, B16, fp, device_info().sm_count, st, &err)
+                     : launch_score_filter(A16, B16, fp, device_info().sm_count, st, &err);
       if (e != cudaSuccess) return cuda_fail(e, err[0] ? err : "score_filter launch");
       prof_mark(PROF_FILTER, 1, st);
     } else {

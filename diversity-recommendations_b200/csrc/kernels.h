@@ -48,6 +48,10 @@ int score_filter_b_stages(int kblocks);
 size_t score_filter_smem_bytes(int kblocks);
 cudaError_t launch_score_filter(const void* A16, const void* B16, FilterParams p, int sm_count,
                                 cudaStream_t stream, const char** err);
+// two user blocks per CTA (d_pad <= 128, nI < TIGHTEN_MIN_ITEMS); a row's lists come out merged pairwise:
+// slots (h,0)+(h,1) hold ONE list of 2 * cap groups, list_count[h*2+1] = 0
+cudaError_t launch_score_filter2(const void* A16, const void* B16, FilterParams p, int sm_count,
+                                 cudaStream_t stream, const char** err);
 
 // fp32 [rows,d] -> one fp16 plane [rows,d_pad] of X * 2^scale_exp (max |x| scaled into [2^13, 2^14)),
 // plus fp32 row norms of X and (optionally) the maximum row norm as float bits.
@@ -82,6 +86,7 @@ struct SelectParams {
   int32_t* fail_rows;          // [nU] rows the tensor-core path could not certify
   int32_t* fail_count;         // device counter (zeroed by the caller)
   int32_t* fail_reasons;       // device [4] statistics by reason (see report_fail), may be null
+  int merged_lists;            // 1 = lists written by launch_score_filter2 (slots 0 and 2 hold up to 2 * cap groups)
   int debug_dump;              // 1 = uncertified rows leave their diagnostics in out_scores (env DIVREC_DEBUG_NO_RESCUE)
   int force_fail;              // 1 = send every row to the rescue kernel (DIVREC_MODE_SIMT)
   float* out_ild;              // [nU] fused cosine ILD of the row's top-k (null = off; needs d % 4 == 0, d <= 512)

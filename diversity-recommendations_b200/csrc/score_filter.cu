@@ -33,6 +33,8 @@
 //   warp  16   TMA producer (one lane): A block once per user block, B k-blocks through a ring
 //   warp  17   MMA issuer (one lane): tcgen05.mma kind::f16, M=128 N=128 K=16, fp32 accum in TMEM
 //   warp  18   TMEM allocator
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -458,8 +460,7 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmap_b, const FilterPara
               "{\n"
               ".reg .pred p;\n"
               "setp.ge.f32 p, %0, %1;\n"
-              "@p st.global.v4.b32 [%2], {%4, %5, %6, %7};\n"
-              "@p st.global.v4.b32 [%2+16], {%8, %9, %10, %11};\n"
+              "@p st.global.v8.b32 [%2], {%4, %5, %6, %7, %8, %9, %10, %11};\n"  // one 256-bit store (STG.E.ENL2.256)
               "@p st.global.b32 [%3], %12;\n"
               "}\n"
               ::"f"(m), "f"(thr_st), "l"(dst), "l"(idst), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]),
@@ -514,6 +515,8 @@ bool make_tmap(CUtensorMap* m, const void* base, int64_t rows, int K, int fmt) {
 
 }  // namespace
 
+bool make_tmap_b(CUtensorMap* m, const void* base, int64_t rows, int K, int fmt) { return make_tmap(m, base, rows, K, fmt); }
+
 int score_filter_b_stages(int kblocks) {
   // B ring: as many 16 KB stages as fit (the A operand is in TMEM), at least two tiles' worth when possible
   (void)kblocks;
@@ -552,7 +555,8 @@ cudaError_t launch_score_filter(const void* A16, const void* B16, FilterParams p
     p.sample_stride = 1;
   }
   const size_t smem = score_filter_smem_bytes(p.kblocks);
-  const int grid = p.n_ublocks < sm_count ? p.n_ublocks : sm_count;
+  int grid = p.n_ublocks < sm_count ? p.n_ublocks : sm_count;
+  if (const char* g = getenv("DIVREC_DEBUG_FILTER_GRID")) { const int v = atoi(g); if (v > 0 && v < grid) grid = v; }  // measurement aid
   cudaError_t e;
   if (p.nI >= TIGHTEN_MIN_ITEMS) {
     e = cudaFuncSetAttribute(score_filter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -1,0 +1,376 @@
+// score_filter2.cu -- the score + filter kernel for the common shape (d <= 128, catalogue below 500k items):
+// TWO 128-user blocks per CTA share every item tile.
+//
+// Why: with the A operand in tensor memory the tensor pipe needs a new 32 KB item tile every ~590 cycles, i.e.
+// ~55 B/cycle of shared-memory ingest per SM -- measured to be the limit of a single SM's L2->smem path (the wait
+// for B operand data was 19 % of the issuing thread's time and did not change when the grid was shrunk to 74 or 37
+// CTAs, so it is not chip-level L2 contention).  Scoring two user blocks against each tile halves the ingest per
+// MMA and removes that wait.  Same arithmetic, same candidate-list format and same certification contract as
+// score_filter.cu (see there for the algorithm); what changes is the schedule:
+//   TMEM      A(block 0) | A(block 1) at the top (2 x K/2 <= 128 columns), three 128-column accumulator stages
+//             rotating over (tile, block) pairs;
+//   epilogue  set b (8 warps) owns user block b and consumes every tile of it; a user row owns two candidate
+//             lists (column halves) of 2 x LIST_CAP groups, stored in the four-list layout as slots (h, 0)+(h, 1);
+//   MMA       per tile: 8 k-steps for block 0, 8 for block 1 against the same shared-memory stages, which are
+//             released after the second pass.
+#include <cstdlib>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace divrec {
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 64;
+constexpr int SLAB_BYTES = BM * BK * 2;
+constexpr int TMEM_COLS = 512;
+constexpr int ACC_STAGES = 3;
+constexpr int NB = 2;              // user blocks per CTA
+constexpr int EPI_WARPS = 8;       // per set
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int W_TMA = EPI_WARPS * NB, W_MMA = W_TMA + 1, W_ALLOC = W_TMA + 2;
+constexpr int NUM_THREADS = (W_ALLOC + 1) * 32;
+constexpr int COLS_PER_THREAD = BN / 2;
+constexpr int GROUPS_PER_TILE = COLS_PER_THREAD / GROUP;
+constexpr int HS = 2 * N_SAMPLE;
+
+struct Smem2 {
+  uint64_t b_full[16];
+  uint64_t b_empty[16];
+  uint64_t acc_full[4];
+  uint64_t acc_empty[4];
+  uint64_t a_full;
+  uint64_t a_empty;
+  uint32_t tmem_base;
+  uint32_t pad;
+  float sorted[NB][HS][EPI_THREADS];
+};
+
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float m;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(m) : "f"(a), "f"(b), "f"(c));
+  return m;
+}
+__device__ __forceinline__ float max8(const uint32_t* v) {
+  const float a = max3(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]));
+  const float b = max3(__uint_as_float(v[3]), __uint_as_float(v[4]), __uint_as_float(v[5]));
+  return max3(a, b, fmaxf(__uint_as_float(v[6]), __uint_as_float(v[7])));
+}
+__device__ __forceinline__ float max32(const uint32_t* v) {
+  const float a = max3(max8(v), max8(v + 8), max8(v + 16));
+  return fmaxf(a, max8(v + 24));
+}
+__device__ __forceinline__ int sched_tile(int s, int n_sample, int stride) {
+  return s < n_sample ? s * stride : s - n_sample;
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+score_filter2_kernel(const __grid_constant__ CUtensorMap tmap_b, const FilterParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem_base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* b_ring = smem_base;
+  Smem2* sm = reinterpret_cast<Smem2*>(b_ring + (size_t)p.b_stages * SLAB_BYTES);
+
+  const int warp = threadIdx.x >> 5;
+  const uint32_t lane = lane_id();
+  const int b_stages = p.b_stages;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < b_stages; ++i) { mbar_init(smem_u32(&sm->b_full[i]), 1); mbar_init(smem_u32(&sm->b_empty[i]), 1); }
+    for (int i = 0; i < 4; ++i) { mbar_init(smem_u32(&sm->acc_full[i]), 1); mbar_init(smem_u32(&sm->acc_empty[i]), EPI_WARPS); }
+    mbar_init(smem_u32(&sm->a_full), EPI_WARPS * NB);  // every epilogue warp writes part of the two A operands
+    mbar_init(smem_u32(&sm->a_empty), 1);
+    fence_mbar_init();
+  }
+  if (warp == W_TMA && lane == 0) tma_prefetch_desc(&tmap_b);
+  if (warp == W_ALLOC) { tmem_alloc(smem_u32(&sm->tmem_base), TMEM_COLS); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&sm->tmem_base);
+
+  const int kblocks = p.kblocks;  // 1 or 2
+  const int n_sample = p.n_sample;
+  const int n_sched = n_sample + p.n_tiles;
+  const int n_dblocks = (p.n_ublocks + NB - 1) / NB;
+  const uint32_t a_cols = (uint32_t)kblocks * (BK / 2);  // TMEM columns of one A operand
+
+  if (warp == W_TMA) {
+    // ================= TMA producer: one pass over the schedule per PAIR of user blocks =================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      const uint64_t pol_keep = l2_policy_evict_last();
+      for (int db = blockIdx.x; db < n_dblocks; db += gridDim.x) {
+        for (int s = 0; s < n_sched; ++s) {
+          const int t = sched_tile(s, n_sample, p.sample_stride);
+          for (int kb = 0; kb < kblocks; ++kb) {
+            mbar_wait(smem_u32(&sm->b_empty[stage]), phase ^ 1);
+            mbar_arrive_expect_tx(smem_u32(&sm->b_full[stage]), SLAB_BYTES);
+            tma_load_2d_hint(smem_u32(b_ring + (size_t)stage * SLAB_BYTES), &tmap_b, smem_u32(&sm->b_full[stage]), kb * BK,
+                             t * BN, pol_keep);
+            if (++stage == (uint32_t)b_stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == W_MMA) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_f16(p.fmt, BM, BN);
+      const uint64_t bdesc0 = umma_desc_sw128(smem_u32(b_ring));
+      const uint32_t bar_b_full = smem_u32(&sm->b_full[0]), bar_b_empty = smem_u32(&sm->b_empty[0]);
+      const uint32_t bar_acc_full = smem_u32(&sm->acc_full[0]), bar_acc_empty = smem_u32(&sm->acc_empty[0]);
+      uint32_t stage = 0, phase = 0, a_phase = 0, acc = 0, acc_phase = 0;
+      long long w_a = 0, w_acc = 0, w_b = 0;
+      const bool stats = p.stats != nullptr;
+      const long long t_begin = clock64();
+      for (int db = blockIdx.x; db < n_dblocks; db += gridDim.x) {
+        long long t0 = stats ? clock64() : 0;
+        mbar_wait(smem_u32(&sm->a_full), a_phase);
+        if (stats) w_a += clock64() - t0;
+        a_phase ^= 1;
+        tc_fence_after();
+        for (int s = 0; s < n_sched; ++s) {
+          const uint32_t stage0 = stage, phase0 = phase;
+#pragma unroll
+          for (int b = 0; b < NB; ++b) {
+            if (stats) t0 = clock64();
+            mbar_wait(bar_acc_empty + 8 * acc, acc_phase ^ 1);
+            if (stats) w_acc += clock64() - t0;
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * BN;
+            uint32_t a_tmem = tmem_base + TMEM_COLS - (uint32_t)(b + 1) * a_cols;
+            stage = stage0;
+            phase = phase0;
+            for (int kb = 0; kb < kblocks; ++kb, a_tmem += BK / 2) {
+              if (b == 0) {
+                if (stats) t0 = clock64();
+                mbar_wait(bar_b_full + 8 * stage, phase);
+                if (stats) w_b += clock64() - t0;
+                tc_fence_after();
+              }
+              const uint64_t bdesc = bdesc0 + (uint64_t)(stage * (SLAB_BYTES >> 4));
+              umma_f16_ts(d_tmem, a_tmem, bdesc, idesc, (uint32_t)(kb != 0));
+              umma_f16_ts(d_tmem, a_tmem + 8, bdesc + 2, idesc, 1u);
+              umma_f16_ts(d_tmem, a_tmem + 16, bdesc + 4, idesc, 1u);
+              umma_f16_ts(d_tmem, a_tmem + 24, bdesc + 6, idesc, 1u);
+              if (b == NB - 1) umma_commit(bar_b_empty + 8 * stage);  // both user blocks have read this stage
+              if (++stage == (uint32_t)b_stages) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(bar_acc_full + 8 * acc);
+            if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+          }
+        }
+        umma_commit(smem_u32(&sm->a_empty));
+      }
+      if (stats) {
+        long long* o = p.stats + (size_t)blockIdx.x * 4;
+        o[0] = clock64() - t_begin; o[1] = w_a; o[2] = w_acc; o[3] = w_b;
+      }
+    }
+  } else if (warp < EPI_WARPS * NB) {
+    // ================= epilogue: set `bset` owns user block `bset` of the pair =================
+    const int q = warp & 3;
+    const int h = (warp >> 2) & 1;
+    const int bset = warp >> 3;
+    const int row_local = q * 32 + lane;
+    const int et = (warp & 7) * 32 + lane;
+    uint32_t base_seq = 0;  // accumulator uses before this pair: NB per schedule position
+    uint32_t a_phase = 0;
+    for (int db = blockIdx.x; db < n_dblocks; db += gridDim.x, base_seq += (uint32_t)(NB * n_sched)) {
+      const int ub = db * NB + bset;
+      const int64_t row = (int64_t)ub * BM + row_local;
+      const bool valid_row = ub < p.n_ublocks && row < p.nU;
+      float thr = valid_row ? -INFINITY : INFINITY;
+
+      // ---- phase 0: this set's A operand -> TMEM ----
+      {
+        mbar_wait(smem_u32(&sm->a_empty), a_phase ^ 1);
+        a_phase ^= 1;
+        tc_fence_after();
+        const int words = kblocks * (BK / 4);
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(p.a16) + (size_t)row * (kblocks * (BK / 2)) + (size_t)h * words;
+        const uint32_t tdst = tmem_base + ((uint32_t)(q * 32) << 16) + TMEM_COLS - (uint32_t)(bset + 1) * a_cols + (uint32_t)h * words;
+        for (int w0 = 0; w0 < words; w0 += 16) {
+          uint32_t r[16];
+          if (valid_row) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              const uint4 t4 = __ldg(reinterpret_cast<const uint4*>(src + w0 + j));
+              r[j] = t4.x; r[j + 1] = t4.y; r[j + 2] = t4.z; r[j + 3] = t4.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) r[j] = 0u;
+          }
+          tmem_st_32x32b_x16(tdst + w0, r);
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&sm->a_full));
+      }
+
+      // ---- phase 1: threshold hint (each set samples for its own block) ----
+      if (n_sample > 0) {
+        float hs[HS];
+#pragma unroll
+        for (int s = 0; s < N_SAMPLE; ++s) {
+          const uint32_t seq = base_seq + (uint32_t)(NB * s + bset), acc = seq % ACC_STAGES, acc_phase = (seq / ACC_STAGES) & 1;
+          mbar_wait(smem_u32(&sm->acc_full[acc]), acc_phase);
+          tc_fence_after();
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + h * COLS_PER_THREAD;
+          uint32_t v0[32];
+          tmem_ld_32x32b_x32(taddr, v0);
+          tmem_wait_ld();
+          hs[2 * s] = max32(v0);
+          tmem_ld_32x32b_x32(taddr + 32, v0);
+          tmem_wait_ld();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&sm->acc_empty[acc]));
+          hs[2 * s + 1] = max32(v0);
+        }
+#pragma unroll
+        for (int size = 2; size <= HS; size <<= 1) {
+#pragma unroll
+          for (int stride = size >> 1; stride > 0; stride >>= 1) {
+#pragma unroll
+            for (int i = 0; i < HS; ++i) {
+              const int j = i ^ stride;
+              if (j > i) {
+                const bool desc = (i & size) == 0;
+                const float a = hs[i], b = hs[j];
+                const float mx = fmaxf(a, b), mn = fminf(a, b);
+                hs[i] = desc ? mx : mn;
+                hs[j] = desc ? mn : mx;
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < HS; ++i) sm->sorted[bset][i][et] = hs[i];
+        if (bset == 0) asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+        else asm volatile("bar.sync 2, %0;" ::"n"(EPI_THREADS) : "memory");
+        if (valid_row) {
+          int64_t seen_u = 0;
+          if (p.seen_rowptr != nullptr) seen_u = p.seen_rowptr[row + 1] - p.seen_rowptr[row];
+          const float f0 = ((float)p.k + (float)seen_u + 8.0f) / (float)p.nI;
+          int r = 2 * HS + 1;
+          if (f0 < 0.25f) {
+            const float pg = 1.0f - __expf(32.0f * log1pf(-f0));
+            const float n = (float)(2 * HS);
+            r = (int)ceilf(n * pg + 3.0f * sqrtf(n * pg * (1.0f - pg))) + 1;
+          }
+          if (r <= 2 * HS - 4) {
+            const int ea = row_local, eb = row_local + 128;
+            int i = 0, j = 0;
+            float pick = INFINITY;
+            for (int c = 0; c < r; ++c) {
+              const float a = i < HS ? sm->sorted[bset][i][ea] : -INFINITY;
+              const float b = j < HS ? sm->sorted[bset][j][eb] : -INFINITY;
+              if (a >= b) { pick = a; ++i; } else { pick = b; ++j; }
+            }
+            thr = pick;
+          }
+        }
+        if (bset == 0) asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+        else asm volatile("bar.sync 2, %0;" ::"n"(EPI_THREADS) : "memory");
+      }
+
+      // ---- phase 2: fixed-threshold group filter over every tile of this set's block ----
+      float* const Ls_blk = p.list_scores + (size_t)ub * (BM * 4) * ((size_t)p.cap * GROUP);
+      uint32_t* const Li_blk = p.list_item0 + (size_t)ub * (BM * 4) * (size_t)p.cap;
+      const uint32_t goff = (uint32_t)((row_local * 4 + h * 2) * p.cap);  // slots (h,0)+(h,1): one list of 2 * cap groups
+      const uint32_t cap2 = 2u * (uint32_t)p.cap;
+      const uint32_t cap_lim = cap2 - GROUPS_PER_TILE;
+      uint32_t cnt = 0;
+      for (int t = 0; t < p.n_tiles; ++t) {
+        const uint32_t seq = base_seq + (uint32_t)(NB * (n_sample + t) + bset), acc = seq % ACC_STAGES, acc_phase = (seq / ACC_STAGES) & 1;
+        mbar_wait(smem_u32(&sm->acc_full[acc]), acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + h * COLS_PER_THREAD;
+        uint32_t v0[32], v1[32];
+        tmem_ld_32x32b_x32(taddr, v0);
+        tmem_ld_32x32b_x32(taddr + 32, v1);
+        tmem_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&sm->acc_empty[acc]));
+
+        if (p.debug_mode == 1) continue;
+        if (cnt > cap_lim) { thr = INFINITY; cnt = cap2 + 1; }  // overflow: the row goes to the rescue kernel
+        const float thr_st = p.debug_mode == 2 ? INFINITY : thr;
+        const uint32_t item0 = (uint32_t)(t * BN + h * COLS_PER_THREAD);
+#pragma unroll
+        for (int g = 0; g < GROUPS_PER_TILE; ++g) {
+          const uint32_t* v = g < 4 ? &v0[8 * g] : &v1[8 * (g - 4)];
+          const float m = max8(v);
+          float* dst = Ls_blk + (size_t)(goff + cnt) * GROUP;
+          uint32_t* idst = Li_blk + (goff + cnt);
+          asm volatile(
+              "{\n"
+              ".reg .pred p;\n"
+              "setp.ge.f32 p, %0, %1;\n"
+              "@p st.global.v8.b32 [%2], {%4, %5, %6, %7, %8, %9, %10, %11};\n"  // one 256-bit store (STG.E.ENL2.256)
+              "@p st.global.b32 [%3], %12;\n"
+              "}\n"
+              ::"f"(m), "f"(thr_st), "l"(dst), "l"(idst), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]),
+                "r"(v[6]), "r"(v[7]), "r"(item0 + 8 * g)
+              : "memory");
+          cnt += (m >= thr) ? 1u : 0u;
+        }
+      }
+      if (valid_row) {
+        p.list_count[row * 4 + h * 2] = (int32_t)cnt;  // 2 * cap + 1 = overflowed
+        p.list_count[row * 4 + h * 2 + 1] = 0;
+        p.thr_out[row * 4 + h * 2] = thr;
+        p.thr_out[row * 4 + h * 2 + 1] = thr;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == W_ALLOC) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
+}
+
+}  // namespace
+
+bool make_tmap_b(CUtensorMap* m, const void* base, int64_t rows, int K, int fmt);  // score_filter.cu
+
+cudaError_t launch_score_filter2(const void* A16, const void* B16, FilterParams p, int sm_count, cudaStream_t stream,
+                                 const char** err) {
+  const int K = p.kblocks * BK;
+  CUtensorMap tb;
+  if (!make_tmap_b(&tb, B16, p.nI, K, p.fmt)) {
+    *err = "cuTensorMapEncodeTiled failed";
+    return cudaErrorInvalidValue;
+  }
+  p.a16 = A16;
+  p.n_ublocks = (int)((p.nU + BM - 1) / BM);
+  p.n_tiles = (p.nI + BN - 1) / BN;
+  int s = (204 * 1024 - (int)sizeof(Smem2)) / SLAB_BYTES;
+  if (s > 16) s = 16;
+  p.b_stages = s;
+  p.acc_stages = ACC_STAGES;
+  if (p.use_hint && p.n_tiles >= HINT_MIN_TILES) {
+    p.n_sample = N_SAMPLE;
+    p.sample_stride = (p.n_tiles - 1) / N_SAMPLE;
+  } else {
+    p.n_sample = 0;
+    p.sample_stride = 1;
+  }
+  const size_t smem = 1024 + (size_t)p.b_stages * SLAB_BYTES + sizeof(Smem2);
+  const int n_dblocks = (p.n_ublocks + NB - 1) / NB;
+  int grid = n_dblocks < sm_count ? n_dblocks : sm_count;
+  if (const char* g = getenv("DIVREC_DEBUG_FILTER_GRID")) { const int v = atoi(g); if (v > 0 && v < grid) grid = v; }
+  cudaError_t e = cudaFuncSetAttribute(score_filter2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  score_filter2_kernel<<<grid, NUM_THREADS, smem, stream>>>(tb, p);
+  count_launch();
+  return cudaGetLastError();
+}
+
+}  // namespace divrec

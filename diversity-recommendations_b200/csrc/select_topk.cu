@@ -106,8 +106,16 @@ __device__ __forceinline__ int scan_groups(const SelectParams& p, int64_t row, c
                                            uint32_t* key, uint32_t* id, uint32_t lane) {
   int total = 0;
   const float lim = fmaxf(fmin, -3.0e38f);
-  const int cnt[LISTS_PER_ROW] = {nl.x, nl.y, nl.z, nl.w};
-  const int nmax = max(max(nl.x, nl.y), max(nl.z, nl.w));
+  // four parallel read streams: the row's four lists, or -- when the two-block filter wrote two lists of
+  // 2 * cap groups (slots 0 and 2) -- the two halves of each
+  int cnt[LISTS_PER_ROW] = {nl.x, nl.y, nl.z, nl.w};
+  int start[LISTS_PER_ROW] = {0, p.cap, 2 * p.cap, 3 * p.cap};
+  if (p.merged_lists) {
+    const int h0 = (nl.x + 1) >> 1, h2 = (nl.z + 1) >> 1;
+    cnt[0] = h0; cnt[1] = nl.x - h0; start[1] = h0;
+    cnt[2] = h2; cnt[3] = nl.z - h2; start[3] = 2 * p.cap + h2;
+  }
+  const int nmax = max(max(cnt[0], cnt[1]), max(cnt[2], cnt[3]));
   const size_t row_base = (size_t)row * LISTS_PER_ROW * (size_t)p.cap;
   const uint32_t nI = (uint32_t)p.nI;
   for (int g = lane; g < nmax + (int)lane; g += 32) {  // uniform trip count: every lane runs ceil(nmax / 32) iterations
@@ -117,7 +125,7 @@ __device__ __forceinline__ int scan_groups(const SelectParams& p, int64_t row, c
     for (int l = 0; l < LISTS_PER_ROW; ++l) {
       item0[l] = 0xffffffffu;
       if (g < cnt[l]) {
-        const size_t base = row_base + (size_t)l * p.cap + g;
+        const size_t base = row_base + (size_t)start[l] + g;
         item0[l] = p.list_item0[base];
         const float4* src = reinterpret_cast<const float4*>(p.list_scores + base * GROUP);
         a[l] = src[0];
@@ -196,7 +204,8 @@ select_topk_kernel(const SelectParams p) {
   const int k = p.k;
 
   const int4 nl = *reinterpret_cast<const int4*>(p.list_count + row * LISTS_PER_ROW);
-  if (p.force_fail || nl.x > p.cap || nl.y > p.cap || nl.z > p.cap || nl.w > p.cap) { report_fail(p, row, lane); return; }
+  const int cap_l = p.merged_lists ? 2 * p.cap : p.cap;  // capacity of a list (an overflowed list reports capacity + 1)
+  if (p.force_fail || nl.x > cap_l || nl.y > cap_l || nl.z > cap_l || nl.w > cap_l) { report_fail(p, row, lane); return; }
 
   int64_t s0 = 0, s1 = 0;
   if (p.seen_rowptr != nullptr) { s0 = p.seen_rowptr[row]; s1 = p.seen_rowptr[row + 1]; }
