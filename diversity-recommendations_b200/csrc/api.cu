@@ -69,7 +69,7 @@ constexpr int64_t CHUNK_USERS = 148 * 8 * 128;  // users per internal pass: 8 us
 
 // workspace layout of score_topk (one chunk of users at a time; the item plane is prepared once)
 struct WsLayout {
-  int d_pad, K;
+  int d_pad, K, cap;
   bool convA, convB;  // operands have to be rewritten into the workspace (fp32 -> fp16, or bf16 padding)
   int64_t chunk;
   int rescue_grid;
@@ -81,14 +81,15 @@ static WsLayout ws_layout(int64_t nU, int64_t nI, int d, int dtype) {
   w.K = w.d_pad;
   w.convA = w.convB = (dtype == DIVREC_F32) || (d != w.d_pad);
   w.chunk = nU < CHUNK_USERS ? nU : CHUNK_USERS;
+  w.cap = nI >= TIGHTEN_MIN_ITEMS ? LIST_CAP_MAX : LIST_CAP;
   const size_t cpad = align_up((size_t)w.chunk, 128);
   size_t off = 0;
   w.offA = off; if (w.convA) off += align_up(cpad * w.K * 2, 1024);
   w.offB = off; if (w.convB) off += align_up((size_t)nI * w.K * 2, 1024);
   w.offNormU = off; off += align_up(cpad * sizeof(float), 1024);
   w.offInvV = off; off += align_up((size_t)nI * sizeof(float), 1024);
-  w.offListS = off; off += align_up(cpad * LISTS_PER_ROW * LIST_CAP * GROUP * sizeof(float), 1024);
-  w.offListI = off; off += align_up(cpad * LISTS_PER_ROW * LIST_CAP * sizeof(uint32_t), 1024);
+  w.offListS = off; off += align_up(cpad * LISTS_PER_ROW * w.cap * GROUP * sizeof(float), 1024);
+  w.offListI = off; off += align_up(cpad * LISTS_PER_ROW * w.cap * sizeof(uint32_t), 1024);
   w.offCounts = off; off += align_up(cpad * LISTS_PER_ROW * sizeof(int32_t), 1024);
   w.offThr = off; off += align_up(cpad * LISTS_PER_ROW * sizeof(float), 1024);
   w.offFail = off; off += align_up(cpad * sizeof(int32_t), 1024);
@@ -202,7 +203,7 @@ static int score_topk_impl(const void* U, const void* V, int64_t nU, int64_t nI,
     int64_t* outi = out_items + (size_t)u0 * k;
 
     SelectParams sp{};
-    sp.nU = cu; sp.nI = (int32_t)nI; sp.k = k; sp.d = d; sp.dtype = dtype; sp.cap = LIST_CAP;
+    sp.nU = cu; sp.nI = (int32_t)nI; sp.k = k; sp.d = d; sp.dtype = dtype; sp.cap = w.cap;
     sp.U = Uc; sp.V = V;
     sp.list_scores = reinterpret_cast<float*>(ws + w.offListS);
     sp.list_item0 = reinterpret_cast<uint32_t*>(ws + w.offListI);
@@ -244,7 +245,7 @@ static int score_topk_impl(const void* U, const void* V, int64_t nU, int64_t nI,
 
       FilterParams fp{};
       fp.nU = cu; fp.nI = (int32_t)nI; fp.kblocks = w.K / 64; fp.fmt = dtype == DIVREC_F32 ? 0 : 1; fp.k = k;
-      fp.use_hint = 1; fp.cap = LIST_CAP; fp.seen_rowptr = rp; fp.debug_mode = g_debug_mode.load(); fp.stats = g_filter_stats.load();
+      fp.use_hint = 1; fp.cap = w.cap; fp.seen_rowptr = rp; fp.debug_mode = g_debug_mode.load(); fp.stats = g_filter_stats.load();
       fp.list_scores = reinterpret_cast<float*>(ws + w.offListS);
       fp.list_item0 = reinterpret_cast<uint32_t*>(ws + w.offListI);
       fp.list_count = reinterpret_cast<int32_t*>(ws + w.offCounts);

@@ -8,6 +8,7 @@
 namespace divrec {
 
 constexpr int LIST_CAP = 256;        // candidate groups per list; a user row owns LISTS_PER_ROW lists
+constexpr int LIST_CAP_MAX = 512;    // ... and for catalogues that tighten lists online (fewer, larger tightenings)
 constexpr int LISTS_PER_ROW = 4;     // (column half of a tile) x (tile parity)
 constexpr int GROUP = 8;             // consecutive item columns appended together
 constexpr int N_SAMPLE = 16;         // item tiles scored first to seed the per-row threshold hint
@@ -24,12 +25,14 @@ struct FilterParams {
   int fmt;      // 0 = fp16 plane, 1 = bf16
   int k;
   int use_hint;
+  float hint_sigma;  // safety of the sampled threshold hint in standard deviations (set by the launcher)
+  int hint_extra;    // extra ranks on top
   int debug_mode;  // 0 = normal; 1 = skip the filter (pipeline timing); 2 = filter without stores
   int cap;      // = LIST_CAP
   // filled by the launcher
   int n_ublocks, n_tiles, b_stages, acc_stages, n_sample, sample_stride;
   const void* a16;             // [nU, K] 16-bit user plane (read row-wise into TMEM)
-  long long* stats;            // [grid][4] MMA-issuer cycles: total, blocked on A, on accumulators, on B (null = off)
+  long long* stats;            // [grid][8] MMA-issuer cycles: total, blocked on A, on accumulators, on B; [4] tightening events, [5] their cycles (null = off)
   const int64_t* seen_rowptr;  // [nU+1] or null (only the per-row counts are used here)
   float* list_scores;          // [nU_pad][4][cap][GROUP]  tensor-core scores (scaled units)
   uint32_t* list_item0;        // [nU_pad][4][cap]         local id of the first item of each group

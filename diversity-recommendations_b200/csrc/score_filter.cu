@@ -98,7 +98,7 @@ __device__ __forceinline__ float row_margin2(const FilterParams& p, int64_t row)
 
 // Warp-cooperative tightening of ONE nearly full candidate list (large catalogues: the sampled hint cannot
 // resolve a 1e-5 quantile, so the list fills many times during a pass).  X = a lower bound of the need-th
-// largest score held by the list (need = k + seen_u + 8 real items score >= X, so at least k unmasked ones do):
+// largest GROUP MAXIMUM held by the list (need = k + seen_u + 8 distinct items score >= X, so at least k unmasked ones do):
 // the k-th best unmasked score of the row is >= X and nothing below X - 2 delta can reach the top-k.  The
 // threshold is raised to X - 2 delta and the groups that fall below it are dropped, order preserved.
 // Returns the new group count; thr_io is updated.  All 32 lanes call with the same arguments.
@@ -106,32 +106,29 @@ __device__ __noinline__ uint32_t tighten_list(float* Ls, uint32_t* Li, uint32_t 
                                               float& thr_io) {
   const uint32_t lane = lane_id();
   const uint32_t lt = lanemask_lt();
-  constexpr int PER = LIST_CAP / 32;  // groups per lane
-  float4 a[PER], b[PER];
-  uint32_t it0[PER];
+  constexpr int MAXPER = LIST_CAP_MAX / 32;  // groups per lane at the largest list capacity
+  // pass 1: group maxima only (each is a real item's score): MAXPER registers per lane, MAXPER compares per bisection step
+  float gm[MAXPER];
   int n_el = 0;
   uint32_t kmin = 0xffffffffu, kmax = 0;
 #pragma unroll
-  for (int j = 0; j < PER; ++j) {
+  for (int j = 0; j < MAXPER; ++j) {
     const uint32_t g = (uint32_t)j * 32 + lane;
-    it0[j] = 0xffffffffu;
-    a[j] = b[j] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    gm[j] = -INFINITY;
     if (g < n) {
-      it0[j] = Li[g];
-      a[j] = *reinterpret_cast<const float4*>(Ls + (size_t)g * GROUP);
-      b[j] = *reinterpret_cast<const float4*>(Ls + (size_t)g * GROUP + 4);
-      // columns past the catalogue (zero-filled operand rows) are not items
-      if (it0[j] + 0 >= nI) a[j].x = -INFINITY; if (it0[j] + 1 >= nI) a[j].y = -INFINITY;
-      if (it0[j] + 2 >= nI) a[j].z = -INFINITY; if (it0[j] + 3 >= nI) a[j].w = -INFINITY;
-      if (it0[j] + 4 >= nI) b[j].x = -INFINITY; if (it0[j] + 5 >= nI) b[j].y = -INFINITY;
-      if (it0[j] + 6 >= nI) b[j].z = -INFINITY; if (it0[j] + 7 >= nI) b[j].w = -INFINITY;
-      const float v[8] = {a[j].x, a[j].y, a[j].z, a[j].w, b[j].x, b[j].y, b[j].z, b[j].w};
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        if (v[e] > -INFINITY) {
-          const uint32_t kk = f32_to_key(__float_as_uint(v[e] + 0.0f));
-          ++n_el; kmin = min(kmin, kk); kmax = max(kmax, kk);
-        }
+      const uint32_t it0 = Li[g];
+      float4 a = *reinterpret_cast<const float4*>(Ls + (size_t)g * GROUP);
+      float4 b = *reinterpret_cast<const float4*>(Ls + (size_t)g * GROUP + 4);
+      if (it0 + 7 >= nI) {  // columns past the catalogue (zero-filled operand rows) are not items
+        if (it0 + 0 >= nI) a.x = -INFINITY; if (it0 + 1 >= nI) a.y = -INFINITY;
+        if (it0 + 2 >= nI) a.z = -INFINITY; if (it0 + 3 >= nI) a.w = -INFINITY;
+        if (it0 + 4 >= nI) b.x = -INFINITY; if (it0 + 5 >= nI) b.y = -INFINITY;
+        if (it0 + 6 >= nI) b.z = -INFINITY; if (it0 + 7 >= nI) b.w = -INFINITY;
+      }
+      gm[j] = fmaxf(fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w)), fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w)));
+      if (gm[j] > -INFINITY) {
+        const uint32_t kk = f32_to_key(__float_as_uint(gm[j] + 0.0f));
+        ++n_el; kmin = min(kmin, kk); kmax = max(kmax, kk);
       }
     }
   }
@@ -139,7 +136,7 @@ __device__ __noinline__ uint32_t tighten_list(float* Ls, uint32_t* Li, uint32_t 
   kmin = __reduce_min_sync(0xffffffffu, kmin);
   kmax = __reduce_max_sync(0xffffffffu, kmax);
   if (n_el < need) return n;  // cannot certify a higher threshold: the caller declares the list overflowed
-  // bisection for a key with count(>= key) in [need, need + need/8]
+  // bisection for a key with count(group maxima >= key) in [need, need + need/8]
   uint32_t lo = kmin, hi = kmax + 1;
   int c_lo = n_el;
   const int c_ok = need + (need >> 3);
@@ -148,33 +145,39 @@ __device__ __noinline__ uint32_t tighten_list(float* Ls, uint32_t* Li, uint32_t 
     const float fm = __uint_as_float(key_to_f32(mid));
     int c = 0;
 #pragma unroll
-    for (int j = 0; j < PER; ++j)
-      c += (a[j].x >= fm) + (a[j].y >= fm) + (a[j].z >= fm) + (a[j].w >= fm) + (b[j].x >= fm) + (b[j].y >= fm) +
-           (b[j].z >= fm) + (b[j].w >= fm);
+    for (int j = 0; j < MAXPER; ++j) c += (gm[j] >= fm) ? 1 : 0;
     c = __reduce_add_sync(0xffffffffu, c);
     if (c >= need) { lo = mid; c_lo = c; } else { hi = mid; }
   }
   const float X = __uint_as_float(key_to_f32(lo));
   const float thr_new = fmaxf(thr_io, X - margin2);
   thr_io = thr_new;
-  // order-preserving compaction: every group was read above, so in-place writes are safe
-  __syncwarp();
+  // pass 2: order-preserving compaction, 32 groups at a time (a chunk is read completely before anything is
+  // written, and writes land at or before the chunk, so later chunks are still intact)
   uint32_t outn = 0;
 #pragma unroll
-  for (int j = 0; j < PER; ++j) {
-    const float m = fmaxf(fmaxf(fmaxf(a[j].x, a[j].y), fmaxf(a[j].z, a[j].w)), fmaxf(fmaxf(b[j].x, b[j].y), fmaxf(b[j].z, b[j].w)));
-    const bool keep = it0[j] != 0xffffffffu && m >= thr_new;
+  for (int j = 0; j < MAXPER; ++j) {
+    if ((uint32_t)j * 32 >= n) break;
+    const uint32_t g = (uint32_t)j * 32 + lane;
+    const bool keep = g < n && gm[j] >= thr_new;
+    float4 a, b;
+    uint32_t it0 = 0;
+    if (keep) {
+      it0 = Li[g];
+      a = *reinterpret_cast<const float4*>(Ls + (size_t)g * GROUP);
+      b = *reinterpret_cast<const float4*>(Ls + (size_t)g * GROUP + 4);
+    }
     const uint32_t kb = __ballot_sync(0xffffffffu, keep);
+    __syncwarp();
     if (keep) {
       const uint32_t pos = outn + __popc(kb & lt);
-      // pad columns were overwritten with -inf above: they can never be selected, which is what we want
-      *reinterpret_cast<float4*>(Ls + (size_t)pos * GROUP) = a[j];
-      *reinterpret_cast<float4*>(Ls + (size_t)pos * GROUP + 4) = b[j];
-      Li[pos] = it0[j];
+      *reinterpret_cast<float4*>(Ls + (size_t)pos * GROUP) = a;
+      *reinterpret_cast<float4*>(Ls + (size_t)pos * GROUP + 4) = b;
+      Li[pos] = it0;
     }
     outn += __popc(kb);
+    __syncwarp();
   }
-  __syncwarp();
   return outn;
 }
 
@@ -285,7 +288,7 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmap_b, const FilterPara
         umma_commit(smem_u32(&sm->a_empty));  // every MMA that reads this block's A has completed
       }
       if (stats) {
-        long long* o = p.stats + (size_t)blockIdx.x * 4;
+        long long* o = p.stats + (size_t)blockIdx.x * 8;
         o[0] = clock64() - t_begin; o[1] = w_a; o[2] = w_acc; o[3] = w_b;
       }
     }
@@ -383,7 +386,7 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmap_b, const FilterPara
           if (f0 < 0.25f) {
             const float pg = 1.0f - __expf(32.0f * log1pf(-f0));  // P(a 32-column group maximum is in that fraction)
             const float n = (float)(2 * HS);
-            r = (int)ceilf(n * pg + 3.0f * sqrtf(n * pg * (1.0f - pg))) + 1;
+            r = (int)ceilf(n * pg + p.hint_sigma * sqrtf(n * pg * (1.0f - pg))) + p.hint_extra;
           }
           if (r <= 2 * HS - 4) {
             const int ea = row_local, eb = row_local + 128;  // the row's two column halves in `sorted`
@@ -408,12 +411,12 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmap_b, const FilterPara
       uint32_t cnt = 0;
       // TIGHTEN: room is checked on every second tile of this thread, so two tiles' worth of slots are kept free
       const uint32_t cap_lim = (uint32_t)(p.cap - (TIGHTEN ? 2 : 1) * GROUPS_PER_TILE);
-      for (int t = pset; t < p.n_tiles; t += EPI_SETS) {
-        if (!TIGHTEN) {
-          if (cnt > cap_lim) { thr = INFINITY; cnt = (uint32_t)p.cap + 1; }  // overflow: stop, the row goes to the rescue kernel
-        } else if ((t & 2) == 0 && __any_sync(0xffffffffu, cnt > cap_lim)) {
-          // rare (large catalogues): lists that cannot take the next tiles' groups are tightened by the whole warp;
-          // everything the slow path needs is recomputed here to keep the hot loop's register set small
+      int t = pset;
+      while (t < p.n_tiles) {
+        if (TIGHTEN) {
+          // rare (large catalogues): lists that cannot take the next tiles' groups are tightened by the whole warp.  This
+          // sits OUTSIDE the hot tile loop (which only breaks out to get here), so the out-of-line call does not force the
+          // loop's state into local memory; everything the slow path needs is recomputed.
           uint32_t full = __ballot_sync(0xffffffffu, valid_row && cnt > cap_lim && cnt <= (uint32_t)p.cap);
           while (full) {
             const int src = __ffs(full) - 1;
@@ -426,13 +429,24 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmap_b, const FilterPara
             float thr_src = __shfl_sync(0xffffffffu, thr, src);
             uint32_t n_new = n_src;
             if (need64 + (need64 >> 3) + 16 <= (int64_t)cap_lim) {
+              const long long tt0 = p.stats != nullptr ? clock64() : 0;
               const uint32_t g_src = (uint32_t)(((q * 32 + src) * 4 + h * 2 + pset) * p.cap);
               n_new = tighten_list(Ls_blk + (size_t)g_src * GROUP, Li_blk + g_src, n_src, (int)need64, row_margin2(p, row_src),
                                    (uint32_t)p.nI, thr_src);
+              if (p.stats != nullptr && lane == 0) {  // measurement aid: tightening events and their cycles per CTA
+                atomicAdd(reinterpret_cast<unsigned long long*>(p.stats) + (size_t)blockIdx.x * 8 + 4, 1ull);
+                atomicAdd(reinterpret_cast<unsigned long long*>(p.stats) + (size_t)blockIdx.x * 8 + 5, (unsigned long long)(clock64() - tt0));
+              }
             }
             if ((int)lane == src) { cnt = n_new; thr = thr_src; }
           }
           if (cnt > cap_lim) { thr = INFINITY; cnt = (uint32_t)p.cap + 1; }  // still no room: stop, the row goes to the rescue kernel
+        }
+      for (; t < p.n_tiles; t += EPI_SETS) {
+        if (!TIGHTEN) {
+          if (cnt > cap_lim) { thr = INFINITY; cnt = (uint32_t)p.cap + 1; }  // overflow: stop, the row goes to the rescue kernel
+        } else if ((t & 2) == 0 && __any_sync(0xffffffffu, valid_row && cnt > cap_lim && cnt <= (uint32_t)p.cap)) {
+          break;  // a list of this warp is nearly full: tighten it (above), then resume with this tile
         }
         const uint32_t seq = base_seq + (uint32_t)(n_sample + t), acc = seq % acc_stages, acc_phase = (seq / acc_stages) & 1;
         mbar_wait(smem_u32(&sm->acc_full[acc]), acc_phase);
@@ -469,6 +483,7 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmap_b, const FilterPara
           cnt += (m >= thr) ? 1u : 0u;
         }
       }
+      }  // while (t < n_tiles)
       if (valid_row) {
         p.list_count[row * 4 + h * 2 + pset] = (int32_t)cnt;  // cap + 1 = overflowed
         p.thr_out[row * 4 + h * 2 + pset] = thr;               // per list: the hint, raised wherever the list was tightened
@@ -544,10 +559,13 @@ cudaError_t launch_score_filter(const void* A16, const void* B16, FilterParams p
   p.n_tiles = (p.nI + BN - 1) / BN;
   p.b_stages = score_filter_b_stages(p.kblocks);
   p.acc_stages = (TMEM_COLS - K / 2) / BN;
-  // Large catalogues: 2048 sampled scores cannot resolve a 1e-5 quantile, and an uncertified row would cost a full
-  // exact pass over millions of items.  They start from thr = -inf instead and rely on the online tightening
-  // alone: every threshold is then a validated bound and no row depends on the rescue kernel.
-  if (p.use_hint && p.n_tiles >= HINT_MIN_TILES && p.nI < TIGHTEN_MIN_ITEMS) {
+  // Large catalogues: 2048 sampled scores cannot resolve a 1e-5 quantile, so the hint only trims the warm-up of the
+  // online tightening (measured on a 1.25M-item shard: starting from thr = -inf appends ~11k groups per row and the
+  // stores are 55 % of the kernel).  An uncertified row would cost an exact pass over millions of items there, so the
+  // hint is taken 5 sigma (+2 ranks) on the safe side instead of 3 (+1): ~1e-6 failures per row.
+  p.hint_sigma = p.nI >= TIGHTEN_MIN_ITEMS ? 5.0f : 3.0f;
+  p.hint_extra = p.nI >= TIGHTEN_MIN_ITEMS ? 2 : 1;
+  if (p.use_hint && p.n_tiles >= HINT_MIN_TILES) {
     p.n_sample = N_SAMPLE;
     p.sample_stride = (p.n_tiles - 1) / N_SAMPLE;  // sample tiles are full tiles (never the ragged last one)
   } else {
@@ -558,7 +576,7 @@ cudaError_t launch_score_filter(const void* A16, const void* B16, FilterParams p
   int grid = p.n_ublocks < sm_count ? p.n_ublocks : sm_count;
   if (const char* g = getenv("DIVREC_DEBUG_FILTER_GRID")) { const int v = atoi(g); if (v > 0 && v < grid) grid = v; }  // measurement aid
   cudaError_t e;
-  if (p.nI >= TIGHTEN_MIN_ITEMS) {
+  if (p.nI >= TIGHTEN_MIN_ITEMS && !getenv("DIVREC_DEBUG_NO_TIGHTEN")) {
     e = cudaFuncSetAttribute(score_filter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     score_filter_kernel<true><<<grid, NUM_THREADS, smem, stream>>>(tb, p);

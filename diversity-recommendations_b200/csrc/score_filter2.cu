@@ -165,7 +165,7 @@ score_filter2_kernel(const __grid_constant__ CUtensorMap tmap_b, const FilterPar
         umma_commit(smem_u32(&sm->a_empty));
       }
       if (stats) {
-        long long* o = p.stats + (size_t)blockIdx.x * 4;
+        long long* o = p.stats + (size_t)blockIdx.x * 8;
         o[0] = clock64() - t_begin; o[1] = w_a; o[2] = w_acc; o[3] = w_b;
       }
     }
@@ -355,6 +355,8 @@ cudaError_t launch_score_filter2(const void* A16, const void* B16, FilterParams 
   if (s > 16) s = 16;
   p.b_stages = s;
   p.acc_stages = ACC_STAGES;
+  p.hint_sigma = 3.0f;
+  p.hint_extra = 1;
   if (p.use_hint && p.n_tiles >= HINT_MIN_TILES) {
     p.n_sample = N_SAMPLE;
     p.sample_stride = (p.n_tiles - 1) / N_SAMPLE;

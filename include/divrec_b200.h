@@ -70,8 +70,9 @@ void divrec_set_profiling(int on);
 /* Measurement aid: 0 = normal; 1 = score+filter kernel runs its TMA/MMA pipeline but skips the filter;
  * 2 = filter arithmetic without the candidate stores.  Results are meaningless unless mode == 0. */
 void divrec_debug_filter_mode(int mode);
-/* Measurement aid: device buffer int64 [148][4] receiving, per CTA of the score+filter kernel, the MMA-issuing
- * thread's cycles: total, blocked on the A operand, on a free accumulator stage, on B operand data.  NULL = off. */
+/* Measurement aid: device buffer int64 [148][8] (caller-zeroed) receiving, per CTA of the score+filter kernel, the
+ * MMA-issuing thread's cycles: [0] total, [1] blocked on the A operand, [2] on a free accumulator stage, [3] on B operand
+ * data; [4] list-tightening events and [5] the cycles spent in them (summed over warps).  NULL = off. */
 void divrec_debug_filter_stats(void* dev_buf);
 int divrec_profile_read(float* ms_out /*host*/, int n);
 

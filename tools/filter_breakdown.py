@@ -21,7 +21,7 @@ for mode in (0, 1):
     out[f"mode{mode}"] = sorted(ms)[len(ms) // 2]
     print(mode, out[f"mode{mode}"], flush=True)
 lib.divrec_debug_filter_mode(0)
-buf = torch.zeros((148, 4), dtype=torch.int64, device=dev)
+buf = torch.zeros((148, 8), dtype=torch.int64, device=dev)
 for mode in (0, 1):
     lib.divrec_debug_filter_mode(mode)
     lib.divrec_debug_filter_stats(buf.data_ptr())
