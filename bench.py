@@ -381,9 +381,13 @@ def bench_cfg3(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    loss_buf = torch.zeros(1, dtype=torch.float32, device=dev)
+    auc_buf = torch.zeros(1, dtype=torch.int32, device=dev)
+
     def step(uu, pp, nn):
-        pos, neg, loss_sum, auc_sum = N.bpr_fwd(U, V, uu, pp, nn)
-        N.bpr_bwd(U, V, uu, pp, nn, pos, neg, 1.0 / Bg, gU, gV)
+        # forward + backward in ONE kernel (divrec_bpr_step): the rows of a triple are read once
+        loss_buf.zero_(); auc_buf.zero_()
+        _p, _n, loss_sum, auc_sum = N.bpr_step(U, V, uu, pp, nn, 1.0 / Bg, gU, gV, want_scores=False, loss_sum=loss_buf, auc_sum=auc_buf)
         if dist is not None:
             dist.all_reduce(gV)
             dist.all_reduce(loss_sum)
@@ -409,8 +413,7 @@ def bench_cfg3(args):
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     k0.record()
     for _ in range(args.steps):
-        pos, neg, ls, au = N.bpr_fwd(U, V, u, p_, n_)
-        N.bpr_bwd(U, V, u, p_, n_, pos, neg, 1.0 / Bg, gU, gV)
+        N.bpr_step(U, V, u, p_, n_, 1.0 / Bg, gU, gV, want_scores=False, loss_sum=loss_buf, auc_sum=auc_buf)
     k1.record()
     torch.cuda.synchronize()
     kms = k0.elapsed_time(k1) / args.steps
@@ -443,10 +446,10 @@ def bench_cfg3(args):
                            "l2": "tables + dense gradients (2 GB) exceed the 126 MB L2"},
                 "clocks": clocks,
                 "e2e": {"value": Bg / (float(e2e) / args.steps * 1e-3), "unit": "triples/s", "h2d_bytes_per_step": 3 * B * 8,
-                        "d2h_bytes_per_step": 4, "api": "divrec._native.bpr_fwd / bpr_bwd (triples from pinned host memory, loss back)"},
+                        "d2h_bytes_per_step": 4, "api": "divrec._native.bpr_step (triples from pinned host memory, loss back)"},
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
-                             "traffic": None, "kernel": "bpr_fwd_kernel + bpr_bwd_kernel", "kernel_ms": kms,
+                             "traffic": None, "kernel": "bpr_step_kernel", "kernel_ms": kms,
                              "algorithmic_bytes_per_launch": B * bytes_per_triple, "peak_source": pk["source"] + " copy bandwidth"},
                 "cpu_baseline": None}
         print(json.dumps(line))

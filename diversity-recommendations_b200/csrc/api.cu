@@ -327,6 +327,24 @@ int divrec_topk_merge(const float* gathered_scores, const int64_t* gathered_item
   return DIVREC_OK;
 }
 
+int divrec_topk_pack(const float* scores, const int64_t* items, int64_t n, uint64_t* out_packed, void* stream) {
+  if (!scores || !items || !out_packed) return fail(DIVREC_ERR_ARG, "topk_pack: null pointer");
+  if (n <= 0) return fail(DIVREC_ERR_ARG, "topk_pack: n must be positive");
+  cudaError_t e = launch_topk_pack(scores, items, n, out_packed, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "topk_pack launch");
+  return DIVREC_OK;
+}
+
+int divrec_topk_merge_packed(const uint64_t* gathered, int n_shards, int64_t nU, int k, float* out_scores,
+                             int64_t* out_items, void* stream) {
+  if (!gathered || !out_scores || !out_items) return fail(DIVREC_ERR_ARG, "topk_merge_packed: null pointer");
+  if (n_shards <= 0 || nU <= 0 || k <= 0) return fail(DIVREC_ERR_ARG, "topk_merge_packed: n_shards, nU, k must be positive");
+  if ((size_t)n_shards * k > 6144) return fail(DIVREC_ERR_ARG, "topk_merge_packed: n_shards * k must be <= 6144 (use divrec_topk_merge)");
+  cudaError_t e = launch_topk_merge_packed(gathered, n_shards, nU, k, out_scores, out_items, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "topk_merge_packed launch");
+  return DIVREC_OK;
+}
+
 int divrec_ild_cosine(const void* V, int64_t nI, int d, int dtype, const int64_t* recs, int64_t nU, int k,
                       int ild_mode, float* inv_norm, float* out_per_user, void* stream) {
   if (!V || !recs || !inv_norm || !out_per_user) return fail(DIVREC_ERR_ARG, "ild_cosine: null pointer");
@@ -405,6 +423,21 @@ int divrec_bpr_bwd(const float* U, const float* V, const int64_t* u, const int64
     return fail(DIVREC_ERR_ARG, "bpr_bwd: gradient tables must be 16-byte aligned");
   cudaError_t e = launch_bpr_bwd(U, V, u, p, n, pos, neg, g, grad_scale, B, d, gU, gV, reinterpret_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "bpr_bwd launch");
+  return DIVREC_OK;
+}
+
+int divrec_bpr_step(const float* U, const float* V, const int64_t* u, const int64_t* p, const int64_t* n, int64_t B, int d,
+                    float grad_scale, float* pos, float* neg, float* loss_sum, int32_t* auc_sum, float* gU, float* gV,
+                    void* stream) {
+  int rc = check_rows(U, V, d, "bpr_step");
+  if (rc != DIVREC_OK) return rc;
+  if (!u || !p || !n) return fail(DIVREC_ERR_ARG, "bpr_step: null index pointer");
+  if (B <= 0) return fail(DIVREC_ERR_ARG, "bpr_step: B must be positive");
+  if ((gU && (reinterpret_cast<uintptr_t>(gU) & 15)) || (gV && (reinterpret_cast<uintptr_t>(gV) & 15)))
+    return fail(DIVREC_ERR_ARG, "bpr_step: gradient tables must be 16-byte aligned");
+  cudaError_t e = launch_bpr_step(U, V, u, p, n, B, d, grad_scale, pos, neg, loss_sum, auc_sum, gU, gV,
+                                  reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "bpr_step launch");
   return DIVREC_OK;
 }
 

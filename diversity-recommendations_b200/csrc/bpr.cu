@@ -98,6 +98,75 @@ bpr_bwd_kernel(const float* __restrict__ U, const float* __restrict__ V, const i
   }
 }
 
+// Forward AND backward of one batch in ONE pass over the rows (the train loop's loss.backward() has upstream
+// gradient 1, so c = -sigmoid(-(pos - neg)) * grad_scale is known as soon as the two dot products are): the three
+// rows of a triple are read once into registers, used for the scores, then for the three scatter-adds.  DRAM
+// traffic per triple = 3 row reads + 3 row read-modify-writes = the algorithmic figure (the two-kernel form reads
+// the rows twice).  NV = float4 chunks of a row per lane (d <= 128 * NV).
+template <int NV>
+__global__ void __launch_bounds__(256)
+bpr_step_kernel(const float* __restrict__ U, const float* __restrict__ V, const int64_t* __restrict__ u,
+                const int64_t* __restrict__ p, const int64_t* __restrict__ n, int64_t B, int d, float grad_scale,
+                float* __restrict__ pos, float* __restrict__ neg, float* __restrict__ loss_sum,
+                int32_t* __restrict__ auc_sum, float* __restrict__ gU, float* __restrict__ gV) {
+  __shared__ float red_loss[8];
+  __shared__ int red_auc[8];
+  const uint32_t lane = lane_id();
+  const int warp = threadIdx.x >> 5;
+  const int nvec = d >> 2;
+  float wl = 0.f;
+  int wa = 0;
+  for (int64_t b = (int64_t)blockIdx.x * 8 + warp; b < B; b += (int64_t)gridDim.x * 8) {
+    const int64_t iu = u[b], ip = p[b], in = n[b];
+    const float4* ur = reinterpret_cast<const float4*>(U + iu * d);
+    const float4* pr = reinterpret_cast<const float4*>(V + ip * d);
+    const float4* nr = reinterpret_cast<const float4*>(V + in * d);
+    float4 a[NV], x[NV], y[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int c = (int)lane + 32 * j;
+      if (c < nvec) { a[j] = __ldg(ur + c); x[j] = __ldg(pr + c); y[j] = __ldg(nr + c); }
+      else { a[j] = x[j] = y[j] = make_float4(0.f, 0.f, 0.f, 0.f); }
+    }
+    float sp = 0.f, sn = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      sp = fmaf(a[j].x, x[j].x, sp); sp = fmaf(a[j].y, x[j].y, sp); sp = fmaf(a[j].z, x[j].z, sp); sp = fmaf(a[j].w, x[j].w, sp);
+      sn = fmaf(a[j].x, y[j].x, sn); sn = fmaf(a[j].y, y[j].y, sn); sn = fmaf(a[j].z, y[j].z, sn); sn = fmaf(a[j].w, y[j].w, sn);
+    }
+    sp = warp_sum(sp);   // xor-shuffle reduction: every lane holds the same sums (same order as bpr_fwd_kernel)
+    sn = warp_sum(sn);
+    const float c = -grad_scale / (1.0f + expf(sp - sn));
+    if (lane == 0) {
+      if (pos) pos[b] = sp;
+      if (neg) neg[b] = sn;
+      wl += neg_logsigmoid(sp - sn);
+      wa += (sp >= sn) ? 1 : 0;
+    }
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int v = (int)lane + 32 * j;
+      if (v < nvec) {
+        if (gU) red_add_v4(gU + iu * d + v * 4, c * (x[j].x - y[j].x), c * (x[j].y - y[j].y), c * (x[j].z - y[j].z), c * (x[j].w - y[j].w));
+        if (gV) {
+          red_add_v4(gV + ip * d + v * 4, c * a[j].x, c * a[j].y, c * a[j].z, c * a[j].w);
+          red_add_v4(gV + in * d + v * 4, -c * a[j].x, -c * a[j].y, -c * a[j].z, -c * a[j].w);
+        }
+      }
+    }
+  }
+  if (lane == 0) { red_loss[warp] = wl; red_auc[warp] = wa; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float l = 0.f;
+    int au = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { l += red_loss[i]; au += red_auc[i]; }
+    if (loss_sum) atomicAdd(loss_sum, l);
+    if (auc_sum) atomicAdd(auc_sum, au);
+  }
+}
+
 __global__ void __launch_bounds__(256)
 pair_scores_kernel(const float* __restrict__ U, const float* __restrict__ V, const int64_t* __restrict__ uid,
                    const int64_t* __restrict__ iid, int64_t L, int d, float* __restrict__ out) {
@@ -181,6 +250,20 @@ cudaError_t launch_bpr_bwd(const float* U, const float* V, const int64_t* u, con
                            const float* pos, const float* neg, const float* g, float grad_scale, int64_t B, int d,
                            float* gU, float* gV, cudaStream_t stream) {
   bpr_bwd_kernel<<<warp_grid(B), 256, 0, stream>>>(U, V, u, p, n, pos, neg, g, grad_scale, B, d, gU, gV);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_bpr_step(const float* U, const float* V, const int64_t* u, const int64_t* p, const int64_t* n, int64_t B,
+                            int d, float grad_scale, float* pos, float* neg, float* loss_sum, int32_t* auc_sum, float* gU,
+                            float* gV, cudaStream_t stream) {
+  // every resident warp loops over several triples, so loads of the next triple overlap the scatter-adds of this one
+  int64_t g = (B + 7) / 8;
+  if (g > 148 * 8) g = 148 * 8;
+  if (d <= 128) bpr_step_kernel<1><<<(unsigned)g, 256, 0, stream>>>(U, V, u, p, n, B, d, grad_scale, pos, neg, loss_sum, auc_sum, gU, gV);
+  else if (d <= 256) bpr_step_kernel<2><<<(unsigned)g, 256, 0, stream>>>(U, V, u, p, n, B, d, grad_scale, pos, neg, loss_sum, auc_sum, gU, gV);
+  else if (d <= 512) bpr_step_kernel<4><<<(unsigned)g, 256, 0, stream>>>(U, V, u, p, n, B, d, grad_scale, pos, neg, loss_sum, auc_sum, gU, gV);
+  else bpr_step_kernel<8><<<(unsigned)g, 256, 0, stream>>>(U, V, u, p, n, B, d, grad_scale, pos, neg, loss_sum, auc_sum, gU, gV);
   count_launch();
   return cudaGetLastError();
 }

@@ -122,6 +122,10 @@ cudaError_t launch_add_counter(const int32_t* src, int32_t* dst, cudaStream_t st
 cudaError_t launch_topk_merge(const float* gs, const int64_t* gi, int n_shards, int64_t nU, int k,
                               float* out_scores, int64_t* out_items, cudaStream_t stream);
 
+cudaError_t launch_topk_pack(const float* scores, const int64_t* items, int64_t n, uint64_t* out, cudaStream_t stream);
+cudaError_t launch_topk_merge_packed(const uint64_t* g, int n_shards, int64_t nU, int k, float* out_scores,
+                                     int64_t* out_items, cudaStream_t stream);
+
 cudaError_t launch_inv_norm(const void* V, int64_t nI, int d, int dtype, float* inv_norm, cudaStream_t stream);
 cudaError_t launch_ild_sumvec(const void* V, int64_t nI, int d, int dtype, const int64_t* recs, int64_t nU, int k,
                               const float* inv_norm, float* out, cudaStream_t stream);
@@ -138,6 +142,9 @@ cudaError_t launch_bpr_fwd(const float* U, const float* V, const int64_t* u, con
 cudaError_t launch_bpr_bwd(const float* U, const float* V, const int64_t* u, const int64_t* p, const int64_t* n,
                            const float* pos, const float* neg, const float* g, float grad_scale, int64_t B, int d,
                            float* gU, float* gV, cudaStream_t stream);
+cudaError_t launch_bpr_step(const float* U, const float* V, const int64_t* u, const int64_t* p, const int64_t* n, int64_t B,
+                            int d, float grad_scale, float* pos, float* neg, float* loss_sum, int32_t* auc_sum, float* gU,
+                            float* gV, cudaStream_t stream);
 cudaError_t launch_pair_scores(const float* U, const float* V, const int64_t* uid, const int64_t* iid, int64_t L,
                                int d, float* out, cudaStream_t stream);
 

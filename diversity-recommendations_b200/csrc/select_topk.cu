@@ -28,13 +28,15 @@ constexpr int SEL_CAP = 768;              // candidate elements per row held in 
 constexpr int SEEN_CAP = 512;             // seen items of the row staged in shared memory (longer lists stay in global)
 constexpr int SORT_N = 128;               // >= MAX_K, power of two
 
+// Per warp ONE contiguous region of 32-bit words: [key: SEL_CAP][id: SEL_CAP][seen: SEEN_CAP (phase B; reused as the
+// 128-entry sort chunk of phase E)][top: SORT_N 64-bit, the running top list].  The coarse cut of rows that captured
+// more than SEL_CAP elements uses the whole region as a keys-only buffer of SEL_WORDS entries.
+constexpr int SEL_WORDS = 2 * SEL_CAP + SEEN_CAP + 2 * SORT_N;
 struct SelSmem {
-  uint32_t key[SEL_WARPS][SEL_CAP];
-  uint32_t id[SEL_WARPS][SEL_CAP];
-  int32_t seen[SEL_WARPS][SEEN_CAP];           // phase B; reused as the 128-entry sort chunk of phase E
-  unsigned long long top[SEL_WARPS][SORT_N];   // running top list, sorted descending
+  uint32_t w[SEL_WARPS][SEL_WORDS];
 };
 static_assert(SEEN_CAP * sizeof(int32_t) >= SORT_N * sizeof(unsigned long long), "sort chunk aliases the seen list");
+static_assert(((2 * SEL_CAP + SEEN_CAP) * 4) % 8 == 0 && (SEL_WORDS * 4) % 16 == 0, "64-bit alignment of the top list");
 
 // descending bitonic sort of 128 64-bit keys held in shared memory by one warp
 __device__ __forceinline__ void warp_bitonic_desc_128(unsigned long long* a, uint32_t lane) {
@@ -99,9 +101,10 @@ __device__ __forceinline__ float sum8(float v) {
 
 // One pass over the row's captured groups: iteration `it` handles group it*32+lane of each of the row's four lists
 // (four independent 36-byte reads in flight per lane, trivial addressing).
-//   STORE: elements with score >= fmin are written to key[] / id[] (at most SEL_CAP), any order;
-//   returns how many there are in total.  Scores are compared as floats; -inf never qualifies.
-template <bool STORE>
+//   MODE 1: elements with score >= fmin are written to key[] / id[] (at most SEL_CAP), any order;
+//   MODE 2: their keys only are written to key[0 .. SEL_WORDS) (the warp's whole region);  MODE 0: count only.
+//   Returns how many there are in total.  Scores are compared as floats; -inf never qualifies.
+template <int MODE>
 __device__ __forceinline__ int scan_groups(const SelectParams& p, int64_t row, const int4 nl, float fmin,
                                            uint32_t* key, uint32_t* id, uint32_t lane) {
   int total = 0;
@@ -145,7 +148,7 @@ __device__ __forceinline__ int scan_groups(const SelectParams& p, int64_t row, c
       }
       mine += __popc(m[l]);
     }
-    if (!STORE) {
+    if (MODE == 0) {
       total += mine;
     } else {
       int incl = mine;
@@ -164,13 +167,17 @@ __device__ __forceinline__ int scan_groups(const SelectParams& p, int64_t row, c
           mm &= mm - 1;
           const float v = e < 4 ? (e == 0 ? a[l].x : e == 1 ? a[l].y : e == 2 ? a[l].z : a[l].w)
                                 : (e == 4 ? b[l].x : e == 5 ? b[l].y : e == 6 ? b[l].z : b[l].w);
-          if (pos < SEL_CAP) { key[pos] = f32_to_key(__float_as_uint(v + 0.0f)); id[pos] = item0[l] + e; }
+          if (MODE == 1) {
+            if (pos < SEL_CAP) { key[pos] = f32_to_key(__float_as_uint(v + 0.0f)); id[pos] = item0[l] + e; }
+          } else {
+            if (pos < SEL_WORDS) key[pos] = f32_to_key(__float_as_uint(v + 0.0f));
+          }
           ++pos;
         }
       }
     }
   }
-  if (!STORE) total = __reduce_add_sync(0xffffffffu, total);
+  if (MODE == 0) total = __reduce_add_sync(0xffffffffu, total);
   __syncwarp();
   return total;
 }
@@ -196,11 +203,11 @@ select_topk_kernel(const SelectParams p) {
   const uint32_t lt = lanemask_lt();
   const int64_t row = (int64_t)blockIdx.x * SEL_WARPS + w;
   if (row >= p.nU) return;
-  uint32_t* key = sm->key[w];
-  uint32_t* id = sm->id[w];
-  int32_t* seen_s = sm->seen[w];
-  unsigned long long* top = sm->top[w];
-  unsigned long long* chunk = reinterpret_cast<unsigned long long*>(sm->seen[w]);
+  uint32_t* key = sm->w[w];
+  uint32_t* id = key + SEL_CAP;
+  int32_t* seen_s = reinterpret_cast<int32_t*>(key + 2 * SEL_CAP);
+  unsigned long long* top = reinterpret_cast<unsigned long long*>(key + 2 * SEL_CAP + SEEN_CAP);
+  unsigned long long* chunk = reinterpret_cast<unsigned long long*>(seen_s);
   const int k = p.k;
 
   const int4 nl = *reinterpret_cast<const int4*>(p.list_count + row * LISTS_PER_ROW);
@@ -234,25 +241,58 @@ select_topk_kernel(const SelectParams p) {
   uint32_t thr_key = (thr == -INFINITY) ? 0u : f32_to_key(__float_as_uint(thr + 0.0f));  // effective capture threshold
 
   // ---- A: enumerate ----
-  int ne = scan_groups<true>(p, row, nl, thr, key, id, lane);
+  int ne = scan_groups<1>(p, row, nl, thr, key, id, lane);
   if (ne > SEL_CAP) {
-    // coarse cut: X = the need-th largest captured score, need = k + seen_u  =>  k-th best unmasked >= X
+    // coarse cut: X = a lower bound of the need-th largest captured score, need = k + seen_u  =>  the k-th best
+    // unmasked score is >= X, nothing below X - 2 delta can reach the top-k: the capture threshold is raised to it
     const int64_t need64 = (int64_t)k + seen_u;
     if (need64 >= ne) { report_fail(p, row, lane, 1); return; }
     const int need = (int)need64;
-    uint32_t lo = thr_key > KEY_NEG_INF ? thr_key : KEY_NEG_INF + 1, hi = 0xff800000u;  // hi: above every finite key
-    while (hi - lo > 1) {
-      const uint32_t mid = lo + ((hi - lo) >> 1);
-      const int c = scan_groups<false>(p, row, nl, __uint_as_float(key_to_f32(mid)), key, id, lane);
-      if (c >= need) lo = mid; else hi = mid;
-      // no early exit: X must be the exact need-th largest so that X - 2 delta can only raise the capture
-      // threshold (lists tightened by the filter were cut at a (need + 8)-th largest, which X dominates)
+    uint32_t cut_key;
+    if (ne <= SEL_WORDS) {
+      // the captured keys fit the warp's shared region: ONE more pass over the lists, then bisect in shared memory
+      // (large catalogues leave up to 4 x 512 groups per row; bisecting with passes over global memory cost 7 ms
+      // per 65 536 rows on a 1.25M-item shard)
+      scan_groups<2>(p, row, nl, thr, key, id, lane);
+      uint32_t kmin = 0xffffffffu, kmax = 0;
+      for (int i = lane; i < ne; i += 32) { const uint32_t kk = key[i]; kmin = min(kmin, kk); kmax = max(kmax, kk); }
+      kmin = __reduce_min_sync(0xffffffffu, kmin);
+      kmax = __reduce_max_sync(0xffffffffu, kmax);
+      uint32_t lo = kmin, hi = kmax + 1;
+      int c_lo = ne;
+      const int c_ok = need + max(2, need >> 3);
+      bool exact = false;
+      for (;;) {
+        while (hi - lo > 1 && (exact || c_lo > c_ok)) {
+          const uint32_t mid = lo + ((hi - lo) >> 1);
+          int c = 0;
+          for (int i = lane; i < ne; i += 32) c += (key[i] >= mid) ? 1 : 0;
+          c = __reduce_add_sync(0xffffffffu, c);
+          if (c >= need) { lo = mid; c_lo = c; } else { hi = mid; }
+        }
+        const float X = __uint_as_float(key_to_f32(lo));
+        cut_key = f32_to_key(__float_as_uint((X - margin2) + 0.0f));
+        if (cut_key > thr_key || exact) break;
+        exact = true;  // the loose bound does not raise the threshold: go on to the exact need-th largest
+      }
+      __syncwarp();
+      if (seen_in_smem)  // the keys-only buffer ran over the staged seen list: stage it again
+        for (int i = lane; i < seen_pow2; i += 32) seen_s[i] = i < (int)seen_u ? __ldg(p.seen_items + s0 + i) : 0x7fffffff;
+    } else {
+      uint32_t lo = thr_key > KEY_NEG_INF ? thr_key : KEY_NEG_INF + 1, hi = 0xff800000u;  // hi: above every finite key
+      while (hi - lo > 1) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        const int c = scan_groups<0>(p, row, nl, __uint_as_float(key_to_f32(mid)), key, id, lane);
+        if (c >= need) lo = mid; else hi = mid;
+      }
+      const float X = __uint_as_float(key_to_f32(lo));
+      cut_key = f32_to_key(__float_as_uint((X - margin2) + 0.0f));
     }
-    const float X = __uint_as_float(key_to_f32(lo));
-    const uint32_t cut_key = f32_to_key(__float_as_uint((X - margin2) + 0.0f));
+    // lists tightened by the filter were cut at a (need + 8)-th largest, which the exact X dominates: a cut that
+    // does not raise the threshold means the row really holds too many near-ties
     if (cut_key <= thr_key) { report_fail(p, row, lane, 1); return; }
     thr_key = cut_key;
-    ne = scan_groups<true>(p, row, nl, __uint_as_float(key_to_f32(thr_key)), key, id, lane);
+    ne = scan_groups<1>(p, row, nl, __uint_as_float(key_to_f32(thr_key)), key, id, lane);
     if (ne > SEL_CAP) { report_fail(p, row, lane, 1); return; }
   }
 
@@ -535,7 +575,80 @@ topk_merge_kernel(const float* __restrict__ gs, const int64_t* __restrict__ gi, 
   }
 }
 
+// ---- packed exchange format (item-sharded catalogue) --------------------------------------------
+// A (score, global id) pair travels as ONE 64-bit composite (ordered score key << 32 | ~id): descending
+// composite order IS the canonical order (score desc, id asc), padding is 0.  One all-gather of 8 B per
+// element instead of two of 4 + 8 B, and the merge compares plain integers.
+__global__ void __launch_bounds__(256)
+topk_pack_kernel(const float* __restrict__ scores, const int64_t* __restrict__ items, int64_t n,
+                 unsigned long long* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  const int64_t it = items[i];
+  unsigned long long c = 0ull;
+  if (it >= 0) c = ((unsigned long long)f32_to_key(__float_as_uint(scores[i] + 0.0f)) << 32) | (unsigned long long)(~(uint32_t)it);
+  out[i] = c;
+}
+
+// One warp per user: the n_shards * k composites of the row are staged in shared memory (coalesced), each
+// element's output rank = its rank in its own list + the number of larger composites in every other list
+// (composites are unique: ids differ across shards).
+__global__ void __launch_bounds__(128)
+topk_merge_packed_kernel(const unsigned long long* __restrict__ g, int n_shards, int64_t nU, int k,
+                         float* __restrict__ out_scores, int64_t* __restrict__ out_items) {
+  extern __shared__ __align__(16) unsigned long long mp_smem[];
+  const int w = threadIdx.x >> 5;
+  const uint32_t lane = lane_id();
+  const int64_t row = (int64_t)blockIdx.x * 4 + w;
+  if (row >= nU) return;
+  const int total = n_shards * k;
+  unsigned long long* a = mp_smem + (size_t)w * total;
+  for (int e = lane; e < total; e += 32) {
+    const int s = e / k, r = e - s * k;
+    a[e] = g[((int64_t)s * nU + row) * k + r];
+  }
+  for (int r = lane; r < k; r += 32) { out_scores[row * k + r] = -INFINITY; out_items[row * k + r] = -1; }
+  __syncwarp();
+  for (int e = lane; e < total; e += 32) {
+    const unsigned long long c = a[e];
+    if (c == 0ull) continue;  // padding
+    const int s = e / k, r = e - s * k;
+    int rank = r;
+    for (int s2 = 0; s2 < n_shards && rank < k; ++s2) {
+      if (s2 == s) continue;
+      const unsigned long long* l = a + s2 * k;
+      int lo = 0, hi = k;  // first position whose composite is < c (lists are descending, padding 0 at the end)
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (l[mid] > c) lo = mid + 1; else hi = mid;
+      }
+      rank += lo;
+    }
+    if (rank < k) {
+      out_scores[row * k + rank] = __uint_as_float(key_to_f32((uint32_t)(c >> 32)));
+      out_items[row * k + rank] = (int64_t)(~(uint32_t)c);
+    }
+  }
+}
+
 }  // namespace
+
+cudaError_t launch_topk_pack(const float* scores, const int64_t* items, int64_t n, uint64_t* out, cudaStream_t stream) {
+  topk_pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(scores, items, n, reinterpret_cast<unsigned long long*>(out));
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_topk_merge_packed(const uint64_t* g, int n_shards, int64_t nU, int k, float* out_scores,
+                                     int64_t* out_items, cudaStream_t stream) {
+  const size_t smem = (size_t)4 * n_shards * k * sizeof(unsigned long long);
+  cudaError_t e = cudaFuncSetAttribute(topk_merge_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  topk_merge_packed_kernel<<<(unsigned)((nU + 3) / 4), 128, smem, stream>>>(reinterpret_cast<const unsigned long long*>(g), n_shards,
+                                                                            nU, k, out_scores, out_items);
+  count_launch();
+  return cudaGetLastError();
+}
 
 cudaError_t launch_select_topk(const SelectParams& p, cudaStream_t stream) {
   const size_t smem = sizeof(SelSmem);

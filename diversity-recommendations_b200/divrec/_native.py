@@ -38,12 +38,15 @@ SIGNATURES = {
     "divrec_score_topk_metrics": (_i32, [_vp, _vp, _i64, _i64, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "divrec_score_topk_rescued": (_i32, [_vp, _i64, _i64, _i32, _i32, _c.POINTER(_c.c_int32), _vp]),
     "divrec_topk_merge": (_i32, [_vp, _vp, _i32, _i64, _i32, _vp, _vp, _vp]),
+    "divrec_topk_pack": (_i32, [_vp, _vp, _i64, _vp, _vp]),
+    "divrec_topk_merge_packed": (_i32, [_vp, _i32, _i64, _i32, _vp, _vp, _vp]),
     "divrec_ild_cosine": (_i32, [_vp, _i64, _i32, _i32, _vp, _i64, _i32, _i32, _vp, _vp, _vp]),
     "divrec_ild_matrix": (_i32, [_vp, _i32, _i64, _vp, _i64, _i32, _vp, _vp]),
     "divrec_coverage_hist": (_i32, [_vp, _i64, _i64, _vp, _vp]),
     "divrec_entropy_from_counts": (_i32, [_vp, _i64, _vp, _vp]),
     "divrec_bpr_fwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp]),
     "divrec_bpr_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _i64, _i32, _vp, _vp, _vp]),
+    "divrec_bpr_step": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "divrec_pair_scores": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp]),
     "divrec_pair_scores_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp]),
     "divrec_ild_labels": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _vp]),
@@ -241,6 +244,39 @@ def topk_merge(gathered_scores: torch.Tensor, gathered_items: torch.Tensor) -> T
     return out_s, out_i
 
 
+MERGE_PACKED_MAX = 6144  # n_shards * k the shared-memory merge takes
+
+
+def topk_pack(scores: torch.Tensor, items: torch.Tensor) -> torch.Tensor:
+    """[nU,k] (fp32 score, int64 global id < 2^32) -> [nU,k] int64 composites whose descending UNSIGNED order is
+    (score desc, id asc); padding (-inf, -1) -> 0.  The exchange format of the item-sharded all-gather."""
+    lib = load_library()
+    s = _cuda(scores, "scores", torch.float32)
+    i = _cuda(items, "items", torch.int64)
+    if s.shape != i.shape:
+        raise ValueError("scores and items must have the same shape")
+    out = torch.empty(s.shape, dtype=torch.int64, device=s.device)
+    with torch.cuda.device(s.device):
+        rc = lib.divrec_topk_pack(_ptr(s), _ptr(i), s.numel(), _ptr(out), _stream(s.device))
+    _check(rc, "divrec_topk_pack")
+    return out
+
+
+def topk_merge_packed(gathered: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """[n_shards, nU, k] composites (topk_pack) -> global (scores [nU,k] fp32, items [nU,k] int64)."""
+    lib = load_library()
+    g = _cuda(gathered, "gathered", torch.int64)
+    if g.dim() != 3:
+        raise ValueError("gathered must be [n_shards, nU, k]")
+    n_shards, nU, k = g.shape
+    out_s = torch.empty((nU, k), dtype=torch.float32, device=g.device)
+    out_i = torch.empty((nU, k), dtype=torch.int64, device=g.device)
+    with torch.cuda.device(g.device):
+        rc = lib.divrec_topk_merge_packed(_ptr(g), n_shards, nU, k, _ptr(out_s), _ptr(out_i), _stream(g.device))
+    _check(rc, "divrec_topk_merge_packed")
+    return out_s, out_i
+
+
 def ild_cosine(V: torch.Tensor, recs: torch.Tensor, mode: int = ILD_SUMVEC) -> torch.Tensor:
     """per-user sum_{a<b}(1 - cos(V[rec_a], V[rec_b])) / (k (k-1)), fp32 [nU]"""
     lib = load_library()
@@ -319,6 +355,35 @@ def bpr_fwd(U, V, u, p, n):
         rc = lib.divrec_bpr_fwd(_ptr(U), _ptr(V), _ptr(u), _ptr(p), _ptr(n), B, d, _ptr(pos), _ptr(neg),
                                 _ptr(loss_sum), _ptr(auc_sum), _stream(U.device))
     _check(rc, "divrec_bpr_fwd")
+    return pos, neg, loss_sum, auc_sum
+
+
+def bpr_step(U, V, u, p, n, grad_scale: float, gU: Optional[torch.Tensor], gV: Optional[torch.Tensor],
+             want_scores: bool = True, loss_sum: Optional[torch.Tensor] = None, auc_sum: Optional[torch.Tensor] = None):
+    """Forward + backward of one batch in one kernel (upstream gradient of the loss = grad_scale * B, i.e. grad_scale = 1/B
+    for `mean_loss.backward()`): gradients accumulate into the dense tables gU / gV.
+    Returns pos [B] | None, neg [B] | None, loss_sum [1] fp32, auc_sum [1] int32."""
+    lib = load_library()
+    U = _cuda(U, "U", torch.float32)
+    V = _cuda(V, "V", torch.float32)
+    u = _cuda(u, "user_id", torch.int64)
+    p = _cuda(p, "positive_item_id", torch.int64)
+    n = _cuda(n, "negative_item_id", torch.int64)
+    for name, t in (("gU", gU), ("gV", gV)):
+        if t is not None and (not t.is_cuda or not t.is_contiguous() or t.dtype != torch.float32):
+            raise TypeError(f"{name} must be a contiguous float32 CUDA tensor")
+    B = u.numel()
+    d = U.shape[1]
+    pos = torch.empty(B, dtype=torch.float32, device=U.device) if want_scores else None
+    neg = torch.empty(B, dtype=torch.float32, device=U.device) if want_scores else None
+    if loss_sum is None:
+        loss_sum = torch.zeros(1, dtype=torch.float32, device=U.device)
+    if auc_sum is None:
+        auc_sum = torch.zeros(1, dtype=torch.int32, device=U.device)
+    with torch.cuda.device(U.device):
+        rc = lib.divrec_bpr_step(_ptr(U), _ptr(V), _ptr(u), _ptr(p), _ptr(n), B, d, float(grad_scale), _ptr(pos), _ptr(neg),
+                                 _ptr(loss_sum), _ptr(auc_sum), _ptr(gU), _ptr(gV), _stream(U.device))
+    _check(rc, "divrec_bpr_step")
     return pos, neg, loss_sum, auc_sum
 
 

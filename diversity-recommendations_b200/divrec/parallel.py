@@ -56,6 +56,13 @@ def recommend_user_sharded(U: torch.Tensor, V: torch.Tensor, seen_rowptr: Option
     return items, scores, ild, (stat[0] / stat[1]).to(torch.float32), counts, (a, b)
 
 
+def _all_gather_stacked(t: torch.Tensor, world: int, group) -> torch.Tensor:
+    """all_gather of equally shaped [n, k] tensors straight into one [world, n, k] buffer (no per-rank copies)."""
+    flat = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(flat, t.contiguous(), group=group)
+    return flat.view((world,) + tuple(t.shape))
+
+
 def recommend_item_sharded(U: torch.Tensor, V_shard: torch.Tensor, shard_offset: int, k: int,
                            seen_rowptr: Optional[torch.Tensor] = None, seen_items: Optional[torch.Tensor] = None,
                            group=None, kernels=None) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -67,11 +74,16 @@ def recommend_item_sharded(U: torch.Tensor, V_shard: torch.Tensor, shard_offset:
     s, i = K.score_topk(U, V_shard, k, seen_rowptr, seen_items, item_id_offset=shard_offset)
     if world == 1:
         return s, i
-    gs = [torch.empty_like(s) for _ in range(world)]
-    gi = [torch.empty_like(i) for _ in range(world)]
-    dist.all_gather(gs, s.contiguous(), group=group)
-    dist.all_gather(gi, i.contiguous(), group=group)
-    return K.topk_merge(torch.stack(gs), torch.stack(gi))
+    # the exchange step.  Packed form (one 64-bit composite per pair, one all-gather, integer merge) when the
+    # backend has it and the sizes allow; otherwise the two-tensor form.
+    packed = (hasattr(K, "topk_pack") and world * k <= getattr(K, "MERGE_PACKED_MAX", 0)
+              and shard_offset + V_shard.shape[0] < 2 ** 32)
+    flag = torch.tensor([1 if packed else 0], dtype=torch.int32, device=s.device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)  # every rank must take the same route
+    if int(flag) == 1:
+        mine = K.topk_pack(s, i)
+        return K.topk_merge_packed(_all_gather_stacked(mine, world, group))
+    return K.topk_merge(_all_gather_stacked(s, world, group), _all_gather_stacked(i, world, group))
 
 
 def bpr_step_sharded(U: torch.Tensor, V: torch.Tensor, u: torch.Tensor, p: torch.Tensor, n: torch.Tensor,
@@ -82,9 +94,12 @@ def bpr_step_sharded(U: torch.Tensor, V: torch.Tensor, u: torch.Tensor, p: torch
     Returns (loss_global, auc_global, gU_local_rows_dense, gV_global)."""
     K = _kernels(kernels)
     rank, world = _world(group)
-    pos, neg, loss_sum, auc_sum = K.bpr_fwd(U, V, u, p, n)
     gU, gV = torch.zeros_like(U), torch.zeros_like(V)
-    K.bpr_bwd(U, V, u, p, n, pos, neg, 1.0 / global_batch, gU, gV)
+    if hasattr(K, "bpr_step"):  # forward + backward in one pass over the rows
+        _pos, _neg, loss_sum, auc_sum = K.bpr_step(U, V, u, p, n, 1.0 / global_batch, gU, gV, want_scores=False)
+    else:
+        pos, neg, loss_sum, auc_sum = K.bpr_fwd(U, V, u, p, n)
+        K.bpr_bwd(U, V, u, p, n, pos, neg, 1.0 / global_batch, gU, gV)
     stat = torch.stack([loss_sum.reshape(()).to(torch.float64), auc_sum.reshape(()).to(torch.float64)])
     if world > 1:
         dist.all_reduce(gV, group=group)

@@ -1,5 +1,6 @@
 from .utils import (
     bpr_step,
+    bpr_train_step,
     get_model_recommendations,
     host_recommend_and_score,
     pair_wise_score_loop,
@@ -19,5 +20,6 @@ __all__ = [
     "pair_wise_train_loop",
     "recommendations_train_loop",
     "bpr_step",
+    "bpr_train_step",
     "host_recommend_and_score",
 ]

@@ -165,6 +165,23 @@ def bpr_step(model: MatrixFactorization, user_id, positive_item_id, negative_ite
     return _FusedBpr.apply(U, V, user_id.to(**to), positive_item_id.to(**to), negative_item_id.to(**to))
 
 
+def bpr_train_step(model: MatrixFactorization, user_id, positive_item_id, negative_item_id):
+    """`loss = mean(-logsigmoid(pos - neg)); loss.backward()` (divrec/train/utils.py:145-149) as ONE kernel: the
+    upstream gradient of the loop's backward() is 1, so the rows of a triple are read once and the gradients are
+    accumulated straight into the dense `.grad` tables (created zero-filled when absent, as autograd would).
+    Returns (loss 0-dim, detached; pos [B]; neg [B]; auc_sum int32 [1])."""
+    U, V = model.user_embeddings.weight, model.item_embeddings.weight
+    to = dict(device=U.device, dtype=torch.int64)
+    u, p, n = user_id.to(**to), positive_item_id.to(**to), negative_item_id.to(**to)
+    grads = []
+    for w in (U, V):
+        if w.requires_grad and w.grad is None:
+            w.grad = torch.zeros_like(w)
+        grads.append(w.grad if w.requires_grad else None)
+    pos, neg, loss_sum, auc_sum = _native.bpr_step(U.detach(), V.detach(), u, p, n, 1.0 / u.numel(), grads[0], grads[1])
+    return loss_sum[0] / u.numel(), pos, neg, auc_sum
+
+
 def pair_wise_train_loop(dataset: PairWiseDataset, model: RankingModel, loss: PairWiseLoss,
                          optimizer: torch.optim.Optimizer, scores: Optional[List[PairWiseLoss]] = None,
                          **loader_params) -> Tuple[float, List[float]]:
@@ -175,14 +192,14 @@ def pair_wise_train_loop(dataset: PairWiseDataset, model: RankingModel, loss: Pa
     fused = isinstance(model, MatrixFactorization) and type(loss) is LogSigmoidDifferenceLoss
     n, loss_total, score_totals = 0, 0.0, [0.0] * len(scores)
     for user_id, pos, neg, user_features, pos_features, neg_features in dataset.loader(**loader_params):
-        if fused:
-            value, positives, negatives, auc_sum = bpr_step(model, user_id, pos, neg)
+        if fused:  # forward + backward in one pass over the rows
+            value, positives, negatives, auc_sum = bpr_train_step(model, user_id, pos, neg)
         else:
             user_id = user_id.to(dev)
             positives = model(user_id, pos.to(dev), user_features, pos_features)
             negatives = model(user_id, neg.to(dev), user_features, neg_features)
             value = loss(positives, negatives)
-        value.backward()
+            value.backward()
         optimizer.step()
         optimizer.zero_grad()
         n += 1

@@ -127,6 +127,16 @@ int divrec_score_topk_rescued(const void* workspace, int64_t nU, int64_t nI, int
 int divrec_topk_merge(const float* gathered_scores, const int64_t* gathered_items, int n_shards,
                       int64_t nU, int k, float* out_scores, int64_t* out_items, void* stream);
 
+/* The same exchange in packed form: one 64-bit composite per (score, id) pair --
+ *   (ordered fp32 key of the score) << 32 | ~(uint32_t)id, padding = 0 -- so that descending integer
+ *   order is exactly (score desc, id asc).  divrec_topk_pack converts a shard's [nU,k] lists (n = nU*k
+ *   elements, global ids < 2^32), ONE all-gather of 8 B per element replaces two of 4 + 8 B, and
+ *   divrec_topk_merge_packed merges [n_shards, nU, k] composites (n_shards * k <= 6144) into the
+ *   reference's layout (fp32 scores, int64 ids, padded with (-inf, -1)). */
+int divrec_topk_pack(const float* scores, const int64_t* items, int64_t n, uint64_t* out_packed, void* stream);
+int divrec_topk_merge_packed(const uint64_t* gathered, int n_shards, int64_t nU, int k, float* out_scores,
+                             int64_t* out_items, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * intra-list diversity with cosine distance over the item table
  *   replaces: divrec/losses/intra_list_diversity_score.py:20-42 fed with
@@ -174,6 +184,15 @@ int divrec_bpr_fwd(const float* U, const float* V, const int64_t* u, const int64
 int divrec_bpr_bwd(const float* U, const float* V, const int64_t* u, const int64_t* p,
                    const int64_t* n, const float* pos, const float* neg, const float* g,
                    float grad_scale, int64_t B, int d, float* gU, float* gV, void* stream);
+
+/* Forward and backward of one batch in ONE pass (the loop's `loss_value.backward()` at
+ *   divrec/train/utils.py:149 has upstream gradient 1, so g_b = -sigmoid(-(pos_b-neg_b)) * grad_scale
+ *   is known as soon as the scores are; grad_scale = 1/B for the mean loss): rows are read once, DRAM
+ *   traffic = 3 row reads + 3 row read-modify-writes per triple.  pos / neg may be NULL; loss_sum and
+ *   auc_sum as in divrec_bpr_fwd; gU / gV accumulate (dense tables, caller-owned, either may be NULL). */
+int divrec_bpr_step(const float* U, const float* V, const int64_t* u, const int64_t* p,
+                    const int64_t* n, int64_t B, int d, float grad_scale, float* pos, float* neg,
+                    float* loss_sum, int32_t* auc_sum, float* gU, float* gV, void* stream);
 
 /* paired scoring  out[l] = <U[user_id[l]], V[item_id[l]]>
  *   replaces: divrec/models/matrix_factorization.py:19-28 (MatrixFactorization.forward) */

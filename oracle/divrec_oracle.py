@@ -128,6 +128,34 @@ def topk_merge(gathered_scores: torch.Tensor, gathered_items: torch.Tensor, k: i
     return torch.gather(s1, 1, o2), torch.gather(i1, 1, o2)
 
 
+def topk_pack(scores: torch.Tensor, items: torch.Tensor) -> torch.Tensor:
+    """The packed exchange format of the item-sharded all-gather (include/divrec_b200.h, divrec_topk_pack):
+    (order-preserving 32-bit key of the fp32 score) << 32 | ~uint32(id); padding (id < 0) -> 0.  Descending
+    unsigned order of the composites is the canonical order of train/utils.py:73-75 (score desc, id asc).
+    Returned as int64 (the bit pattern of the uint64 composite)."""
+    bits = (scores.contiguous() + 0.0).view(torch.int32).numpy().view(np.uint32).astype(np.uint64)
+    key = np.where(bits & np.uint64(0x80000000), ~bits & np.uint64(0xFFFFFFFF), bits | np.uint64(0x80000000))
+    ids = items.numpy()
+    inv = (~ids.astype(np.uint64)) & np.uint64(0xFFFFFFFF)
+    c = np.where(ids >= 0, (key << np.uint64(32)) | inv, np.uint64(0))
+    return torch.from_numpy(c.view(np.int64).copy())
+
+
+def topk_merge_packed(gathered: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Merge [n_shards, U, k] composites: the k largest (unsigned) per user, unpacked to (scores, items)."""
+    n, nU, k = gathered.shape
+    c = gathered.permute(1, 0, 2).reshape(nU, n * k).numpy().view(np.uint64)
+    c = np.sort(c, axis=1)[:, ::-1][:, :k]
+    key = (c >> np.uint64(32)).astype(np.uint32)
+    bits = np.where(key & np.uint32(0x80000000), key & np.uint32(0x7FFFFFFF), ~key)
+    scores = torch.from_numpy(bits.astype(np.uint32).view(np.float32).copy())
+    items = torch.from_numpy(((~c) & np.uint64(0xFFFFFFFF)).astype(np.int64))
+    pad = torch.from_numpy(c == 0)
+    scores = torch.where(pad, torch.full_like(scores, float("-inf")), scores)
+    items = torch.where(pad, torch.full_like(items, -1), items)
+    return scores, items
+
+
 # --------------------------------------------------------------------------------------------
 # intra-list diversity
 # --------------------------------------------------------------------------------------------

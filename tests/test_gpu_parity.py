@@ -230,6 +230,8 @@ def test_large_catalogue_tightens_lists_online(native, dev):
         gi.append(b)
     ms, mi = native.topk_merge(torch.stack(gs), torch.stack(gi))
     assert torch.equal(mi, i) and torch.equal(ms, s)
+    ps, pi = native.topk_merge_packed(torch.stack([native.topk_pack(a, b) for a, b in zip(gs, gi)]))
+    assert torch.equal(pi, i) and torch.equal(ps, s)
 
 
 def test_bf16_tables(native, dev):
@@ -281,6 +283,34 @@ def test_item_sharded_merge_equals_unsharded(native, dev):
     assert torch.equal(mi, full_i) and torch.equal(ms, full_s)
     o_s, o_i = O.topk_merge(torch.stack(gs).cpu(), torch.stack(gi).cpu(), k)
     assert torch.equal(mi.cpu(), o_i) and torch.equal(ms.cpu(), o_s)
+    # the packed exchange format (one 64-bit composite per pair) merges to the same bits
+    ps, pi = native.topk_merge_packed(torch.stack([native.topk_pack(a, b) for a, b in zip(gs, gi)]))
+    assert torch.equal(pi, full_i) and torch.equal(ps, full_s)
+
+
+def test_packed_merge_with_padded_shard_lists(native, dev):
+    """Shards smaller than k: every per-shard list ends in (-inf, -1) padding, which packs to 0 and must never win;
+    negative scores, exact ties across shards and rows with fewer than k items overall are all in here."""
+    gen = torch.Generator().manual_seed(23)
+    nU, nI, d, k, n_sh = 70, 160, 16, 50, 8
+    U, V = O.make_embeddings(nU, d, "grid", gen), O.make_embeddings(nI, d, "grid", gen)
+    seen = O.make_seen(nU, nI, 20000, gen)  # ~83 % of the 160 items seen per user: rows end with fewer than k
+    rowptr, items = csr_dev(seen, nU, dev)
+    Ud, Vd = U.to(dev), V.to(dev)
+    per = nI // n_sh
+    gs, gi = [], []
+    for sh in range(n_sh):
+        s, i = native.score_topk(Ud, Vd[sh * per:(sh + 1) * per].contiguous(), k, rowptr, items, item_id_offset=sh * per)
+        gs.append(s)
+        gi.append(i)
+    o_i, o_s = O.recommendations_dense(U, V, *O.seen_csr(seen, nU), k)
+    assert (o_i < 0).any() and (torch.stack(gi) < 0).any()
+    packed = [native.topk_pack(a, b) for a, b in zip(gs, gi)]
+    assert all(torch.equal(pk.cpu(), O.topk_pack(a.cpu(), b.cpu())) for pk, a, b in zip(packed, gs, gi))
+    ps, pi = native.topk_merge_packed(torch.stack(packed))
+    assert torch.equal(pi.cpu(), o_i) and torch.equal(ps.cpu(), o_s)
+    ms, mi = native.topk_merge(torch.stack(gs), torch.stack(gi))
+    assert torch.equal(mi, pi) and torch.equal(ms, ps)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -377,6 +407,28 @@ def test_bpr_vs_reference_golden(native, dev, name):
     torch.testing.assert_close(lv, -torch.nn.functional.logsigmoid(g["pos"] - g["neg"]), rtol=1e-5, atol=1e-6)
 
 
+@pytest.mark.parametrize("name", ["bpr_small", "bpr_d64"])
+def test_bpr_one_kernel_step_vs_reference_golden(native, dev, name):
+    """divrec_bpr_step (forward + backward in one pass over the rows) against the reference's loss.backward()."""
+    g = load_golden(name)
+    U, V = g["U"].to(dev), g["V"].to(dev)
+    u, p, n = g["u"].to(dev), g["p"].to(dev), g["n"].to(dev)
+    B = u.numel()
+    gU, gV = torch.zeros_like(U), torch.zeros_like(V)
+    pos, neg, loss_sum, auc_sum = native.bpr_step(U, V, u, p, n, 1.0 / B, gU, gV)
+    pos2, neg2, loss2, auc2 = native.bpr_fwd(U, V, u, p, n)
+    assert torch.equal(pos, pos2) and torch.equal(neg, neg2) and int(auc_sum) == int(auc2)   # same summation order
+    assert float(loss_sum) / B == pytest.approx(float(g["loss"]), rel=REL)
+    assert int(auc_sum) / B == pytest.approx(float(g["auc"]), abs=1.5 / B)
+    for got, want in ((gU.cpu(), g["gU"]), (gV.cpu(), g["gV"])):
+        assert (got - want).abs().max().item() <= REL * float(want.abs().max())
+        assert torch.equal(got == 0, want == 0)
+    # accumulation semantics (a second call doubles the gradient) and the scores-off form
+    _, _, l3, _ = native.bpr_step(U, V, u, p, n, 1.0 / B, gU, gV, want_scores=False)
+    assert (gU.cpu() - 2 * g["gU"]).abs().max().item() <= 2 * REL * float(g["gU"].abs().max())
+    assert float(l3) == pytest.approx(float(loss_sum), rel=1e-6)
+
+
 def test_bpr_permutation_invariance(native, dev):
     g = load_golden("bpr_d64")
     U, V = g["U"].to(dev), g["V"].to(dev)
@@ -438,6 +490,13 @@ def test_shim_end_to_end_matches_reference_golden(native, dev):
     loss2.backward()
     for got, want in ((gU_generic, b["gU"]), (m2.user_embeddings.weight.grad, b["gU"]),
                       (gV_generic, b["gV"]), (m2.item_embeddings.weight.grad, b["gV"])):
+        assert (got.cpu() - want).abs().max().item() <= REL * float(want.abs().max())
+    # the train loop's one-kernel step: loss + gradients accumulated straight into .grad
+    from divrec.train import bpr_train_step
+    m2.zero_grad()
+    loss3, _, _, auc3 = bpr_train_step(m2, u, p, n)
+    assert float(loss3) == pytest.approx(float(b["loss"]), rel=REL)
+    for got, want in ((m2.user_embeddings.weight.grad, b["gU"]), (m2.item_embeddings.weight.grad, b["gV"])):
         assert (got.cpu() - want).abs().max().item() <= REL * float(want.abs().max())
 
 

@@ -43,6 +43,16 @@ class OracleKernels:
     def topk_merge(gs, gi):
         return O.topk_merge(gs, gi, gs.shape[2])
 
+    MERGE_PACKED_MAX = 6144
+
+    @staticmethod
+    def topk_pack(s, i):
+        return O.topk_pack(s, i)
+
+    @staticmethod
+    def topk_merge_packed(g):
+        return O.topk_merge_packed(g)
+
     @staticmethod
     def bpr_fwd(U, V, u, p, n):
         pos, neg, loss, auc = O.bpr_forward(U, V, u, p, n)
@@ -84,6 +94,11 @@ def _worker(rank, world, port, out):
     ia, ib = parallel.shard_range(nI, rank, world)
     ms, mi = parallel.recommend_item_sharded(U, V[ia:ib].contiguous(), ia, k, rowptr, items, kernels=K)
     assert torch.equal(mi, full_i) and torch.equal(ms, full_s)
+
+    class TwoTensorKernels(OracleKernels):   # a backend without the packed exchange: two all-gathers + topk_merge
+        MERGE_PACKED_MAX = 0
+    ms2, mi2 = parallel.recommend_item_sharded(U, V[ia:ib].contiguous(), ia, k, rowptr, items, kernels=TwoTensorKernels())
+    assert torch.equal(mi2, full_i) and torch.equal(ms2, full_s)
     # BPR: triples partitioned by user shard
     B = 400
     u = torch.randint(0, nU, (B,), generator=gen); p = torch.randint(0, nI, (B,), generator=gen); n = torch.randint(0, nI, (B,), generator=gen)
