@@ -6,10 +6,21 @@
 // pick is candidate 0; then, k - 1 times, pick  argmax_c  lambda * score_c - (1 - lambda) * max_{j picked} cos(V_c, V_j)
 // over the unpicked real candidates (fp32, ties -> lowest candidate rank).  Padding ids (< 0) are never picked.
 //
-// One CTA per user (persistent, grid-stride).  The normalised candidate rows E_c = V_c / |V_c| are written once to a
-// per-CTA scratch slab (C x d fp32, L2-resident: 296 CTAs x 256 KB at C = 500, d = 128); every step broadcasts the
-// newly picked row through shared memory, each thread updates max-similarity of its candidates with one dot product
-// per candidate (128-bit loads) and the block reduces the argmax.  Work per user: k C d FMA + the C row gather.
+// mmr_lazy_kernel (the product path): LAZY greedy.  A candidate's objective can only fall as picks are added (its
+// max-similarity only grows), so the objective evaluated against the first `seen_c` picks is an upper bound of the
+// current one (before any evaluation: cos >= -1).  Per step every warp takes the candidate with the largest bound
+// among those it owns, brings it up to date (dot products with the picks it has not seen yet) and repeats until its
+// top candidate is exact; the block then takes the best of the four exact champions, ties -> lowest rank -- the same
+// pick as the eager arg-max, with only the candidates that can still win ever being gathered and evaluated (eager
+// costs k C d FMA per user and re-reads every candidate row k times).
+// One CTA of 4 warps per user (persistent).  Candidate c belongs to warp c % 4; its score, bound, state live in that
+// warp's registers.  The normalised picked rows sit in shared memory (row stride d + 4 floats: conflict-free 128-bit
+// reads with one lane per pick), each warp caches the normalised row of its current champion (which is also the
+// row copied to the pick list when it wins).  Refreshes against many picks run one lane per pick; against a few,
+// one pick at a time with a shuffle reduction.
+// mmr_kernel: the eager form (any d, any C), kept for shapes the lazy kernel does not take.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -145,6 +156,222 @@ mmr_kernel(const MmrParams p) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// lazy greedy
+// ---------------------------------------------------------------------------------------------------------
+constexpr int LW = 4;             // warps per user
+constexpr int LAZY_LANE_MIN = 12; // refreshes against more picks than this run one lane per pick
+
+template <int DT>
+__device__ __forceinline__ float4 ld_row4(const void* V, int64_t row, int d, int c4) {
+  if (DT == 0) {
+    return __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(V) + row * d) + c4);
+  } else {
+    const uint2 raw = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(V) + row * d) + c4);
+    return make_float4(__uint_as_float(raw.x << 16), __uint_as_float(raw.x & 0xffff0000u),
+                       __uint_as_float(raw.y << 16), __uint_as_float(raw.y & 0xffff0000u));
+  }
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// S = candidate slots per lane (C <= 128 S); NV = float4 chunks of a row per lane (d <= 128 NV); DT = table dtype
+template <int S, int NV, int DT>
+__global__ void __launch_bounds__(LW * 32, 4)
+mmr_lazy_kernel(const MmrParams p) {
+  extern __shared__ __align__(16) float dyn[];  // picks [k][ds] | champion-row cache [LW][ds]
+  __shared__ float ch_obj[LW];
+  __shared__ int ch_idx[LW];
+  __shared__ int ch_cnt[LW];
+  const int w = threadIdx.x >> 5;
+  const uint32_t lane = lane_id();
+  const int C = p.C, d = p.d, k = p.k, ds = d + 4, nvec = d >> 2;
+  float* picks = dyn;
+  float* cache = dyn + (size_t)k * ds + (size_t)w * ds;
+  const float lam = p.lambda, om = 1.0f - p.lambda;
+
+  for (int64_t u = blockIdx.x; u < p.nU; u += gridDim.x) {
+    // ---- this warp's candidates: c = 4 (32 s + lane) + w ----
+    float sc[S], ms[S];
+    int seen[S], st[S], id[S];
+    int nv = 0;
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      const int c = LW * (s * 32 + (int)lane) + w;
+      sc[s] = -INFINITY; ms[s] = -1.0001f; seen[s] = 0; st[s] = 2; id[s] = -1;  // cos >= -1: the bound before any evaluation
+      if (c < C) {
+        const int64_t it = p.cand_items[u * C + c];
+        if (it >= 0 && it < p.nI) { id[s] = (int)it; st[s] = 0; sc[s] = p.cand_scores[u * C + c]; ++nv; }
+      }
+    }
+    nv = __reduce_add_sync(0xffffffffu, nv);
+    if (lane == 0) ch_cnt[w] = nv;
+    __syncthreads();
+    int n_valid = 0;
+#pragma unroll
+    for (int i = 0; i < LW; ++i) n_valid += ch_cnt[i];
+    const int n_pick = min(k, n_valid);
+    int cache_c = -1;  // candidate whose normalised row is in this warp's cache (warp-uniform)
+
+    // normalised row of candidate `c` (item `item`) -> this warp's cache
+    auto load_cache = [&](int c, int item) {
+      float4 v[NV];
+      float ss = 0.f;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const int c4 = (int)lane + 32 * j;
+        v[j] = c4 < nvec ? ld_row4<DT>(p.V, item, d, c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        ss = fmaf(v[j].x, v[j].x, ss); ss = fmaf(v[j].y, v[j].y, ss); ss = fmaf(v[j].z, v[j].z, ss); ss = fmaf(v[j].w, v[j].w, ss);
+      }
+      const float nrm = sqrtf(warp_sum(ss));
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const int c4 = (int)lane + 32 * j;
+        if (c4 < nvec) reinterpret_cast<float4*>(cache)[c4] = make_float4(v[j].x / nrm, v[j].y / nrm, v[j].z / nrm, v[j].w / nrm);
+      }
+      __syncwarp();
+      cache_c = c;
+    };
+
+    for (int r = 0; r < k; ++r) {
+      if (r >= n_pick) {  // fewer real candidates than k: pad
+        if (threadIdx.x == 0) { p.out_items[u * k + r] = -1; if (p.out_scores) p.out_scores[u * k + r] = -INFINITY; }
+        continue;
+      }
+      float best = -INFINITY;
+      int bidx = 0x7fffffff;
+      if (r > 0) {
+        // ---- lazy loop: until this warp's top candidate (by bound) is exact ----
+        for (;;) {
+          best = -INFINITY; bidx = 0x7fffffff;
+#pragma unroll
+          for (int s = 0; s < S; ++s) {
+            if (st[s] == 0) {
+              const float ub = lam * sc[s] - om * ms[s];
+              const int c = LW * (s * 32 + (int)lane) + w;
+              if (ub > best || (ub == best && c < bidx)) { best = ub; bidx = c; }
+            }
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+            if (ov > best || (ov == best && oi < bidx)) { best = ov; bidx = oi; }
+          }
+          if (bidx == 0x7fffffff) break;  // nothing left in this warp
+          const int slot = bidx >> 7, ln = (bidx >> 2) & 31;
+          int my_seen = 0, my_id = 0;
+          float my_ms = 0.f;
+#pragma unroll
+          for (int s = 0; s < S; ++s) if (s == slot) { my_seen = seen[s]; my_id = id[s]; my_ms = ms[s]; }
+          const int cs = __shfl_sync(0xffffffffu, my_seen, ln);
+          if (cs == r) break;  // exact: bound == objective
+          const int item = __shfl_sync(0xffffffffu, my_id, ln);
+          float m = __shfl_sync(0xffffffffu, my_ms, ln);
+          if (cs == 0) m = -INFINITY;
+          if (cache_c != bidx) load_cache(bidx, item);
+          if (r - cs > LAZY_LANE_MIN) {
+            // one lane per pick: full dot products, the champion's row broadcast from the cache
+            for (int t0 = cs; t0 < r; t0 += 32) {
+              const int t = t0 + (int)lane;
+              float dot = -INFINITY;
+              if (t < r) {
+                const float4* pr = reinterpret_cast<const float4*>(picks + (size_t)t * ds);
+                const float4* cr = reinterpret_cast<const float4*>(cache);
+                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+                for (int x = 0; x < nvec; ++x) {
+                  const float4 a = cr[x], b = pr[x];
+                  s0 = fmaf(a.x, b.x, s0); s1 = fmaf(a.y, b.y, s1); s2 = fmaf(a.z, b.z, s2); s3 = fmaf(a.w, b.w, s3);
+                }
+                dot = (s0 + s1) + (s2 + s3);
+              }
+              m = fmaxf(m, warp_max(dot));
+            }
+          } else {
+            float4 e[NV];
+#pragma unroll
+            for (int j = 0; j < NV; ++j) {
+              const int c4 = (int)lane + 32 * j;
+              e[j] = c4 < nvec ? reinterpret_cast<const float4*>(cache)[c4] : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            for (int t = cs; t < r; ++t) {
+              const float4* pr = reinterpret_cast<const float4*>(picks + (size_t)t * ds);
+              float s0 = 0.f;
+#pragma unroll
+              for (int j = 0; j < NV; ++j) {
+                const int c4 = (int)lane + 32 * j;
+                if (c4 < nvec) {
+                  const float4 b = pr[c4];
+                  s0 = fmaf(e[j].x, b.x, s0); s0 = fmaf(e[j].y, b.y, s0); s0 = fmaf(e[j].z, b.z, s0); s0 = fmaf(e[j].w, b.w, s0);
+                }
+              }
+              m = fmaxf(m, warp_sum(s0));
+            }
+          }
+          if ((int)lane == ln) {
+#pragma unroll
+            for (int s = 0; s < S; ++s) if (s == slot) { ms[s] = m; seen[s] = r; }
+          }
+        }
+        if (lane == 0) { ch_obj[w] = best; ch_idx[w] = bidx; }
+        __syncthreads();
+        best = ch_obj[0]; bidx = ch_idx[0];
+#pragma unroll
+        for (int i = 1; i < LW; ++i) {
+          const float ov = ch_obj[i];
+          const int oi = ch_idx[i];
+          if (ov > best || (ov == best && oi < bidx)) { best = ov; bidx = oi; }
+        }
+      } else {
+        bidx = 0;  // the first pick is the best-scored candidate
+      }
+      // ---- commit pick j: its owner copies the normalised row to the pick list ----
+      const int j = bidx;
+      if (j != 0x7fffffff && (j & (LW - 1)) == w) {
+        const int slot = j >> 7, ln = (j >> 2) & 31;
+        int my_id = -1;
+#pragma unroll
+        for (int s = 0; s < S; ++s) if (s == slot) my_id = id[s];
+        const int item = __shfl_sync(0xffffffffu, my_id, ln);
+        if (item >= 0) {
+          if (cache_c != j) load_cache(j, item);
+          for (int x = lane; x < nvec; x += 32)
+            reinterpret_cast<float4*>(picks + (size_t)r * ds)[x] = reinterpret_cast<const float4*>(cache)[x];
+        } else {
+          for (int x = lane; x < nvec; x += 32) reinterpret_cast<float4*>(picks + (size_t)r * ds)[x] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if ((int)lane == ln) {
+#pragma unroll
+          for (int s = 0; s < S; ++s) if (s == slot) st[s] = 1;
+          p.out_items[u * k + r] = p.cand_items[u * C + j];
+          if (p.out_scores) p.out_scores[u * k + r] = p.cand_scores[u * C + j];
+        }
+      }
+      __syncthreads();
+    }
+    __syncthreads();
+  }
+}
+
+template <int S, int NV>
+cudaError_t launch_mmr_lazy_t(const MmrParams& p, int grid, size_t smem, cudaStream_t stream) {
+  cudaError_t e;
+  if (p.dtype == 0) {
+    e = cudaFuncSetAttribute(mmr_lazy_kernel<S, NV, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    mmr_lazy_kernel<S, NV, 0><<<grid, LW * 32, smem, stream>>>(p);
+  } else {
+    e = cudaFuncSetAttribute(mmr_lazy_kernel<S, NV, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    mmr_lazy_kernel<S, NV, 1><<<grid, LW * 32, smem, stream>>>(p);
+  }
+  return cudaGetLastError();
+}
+
 }  // namespace
 
 size_t mmr_scratch_bytes(int C, int d, int* grid_out) {
@@ -156,6 +383,26 @@ size_t mmr_scratch_bytes(int C, int d, int* grid_out) {
 }
 
 cudaError_t launch_mmr(MmrParams p, cudaStream_t stream) {
+  // lazy greedy for the shapes it takes: 128-bit rows, C <= 1024, pick list + caches within shared memory
+  const size_t lazy_smem = ((size_t)p.k + LW) * (size_t)(p.d + 4) * sizeof(float);
+  if ((p.d & 3) == 0 && p.d <= 512 && p.C <= 1024 && lazy_smem <= 200 * 1024 && p.nI < ((int64_t)1 << 31) &&
+      !getenv("DIVREC_DEBUG_MMR_EAGER")) {
+    int per_sm = (int)((220 * 1024) / (lazy_smem + 1024));
+    if (per_sm > 4) per_sm = 4;
+    if (per_sm < 1) per_sm = 1;
+    int64_t g = (int64_t)148 * per_sm;
+    if (g > p.nU) g = p.nU;
+    const int S = p.C <= 128 ? 1 : p.C <= 256 ? 2 : p.C <= 512 ? 4 : 8;
+    const int NV = p.d <= 128 ? 1 : p.d <= 256 ? 2 : 4;
+    cudaError_t e = cudaErrorInvalidValue;
+#define DIVREC_MMR(SS, NN) if (S == SS && NV == NN) e = launch_mmr_lazy_t<SS, NN>(p, (int)g, lazy_smem, stream)
+    DIVREC_MMR(1, 1); DIVREC_MMR(2, 1); DIVREC_MMR(4, 1); DIVREC_MMR(8, 1);
+    DIVREC_MMR(1, 2); DIVREC_MMR(2, 2); DIVREC_MMR(4, 2); DIVREC_MMR(8, 2);
+    DIVREC_MMR(1, 4); DIVREC_MMR(2, 4); DIVREC_MMR(4, 4); DIVREC_MMR(8, 4);
+#undef DIVREC_MMR
+    count_launch();
+    return e;
+  }
   int grid = 0;
   mmr_scratch_bytes(p.C, p.d, &grid);
   if ((int64_t)grid > p.nU) grid = (int)p.nU;

@@ -500,20 +500,31 @@ def test_shim_end_to_end_matches_reference_golden(native, dev):
         assert (got.cpu() - want).abs().max().item() <= REL * float(want.abs().max())
 
 
-def test_mmr_rerank_vs_oracle(native, dev):
+@pytest.mark.parametrize("nU,nI,d,C,k,lams,table", [
+    (24, 4000, 64, 120, 30, (1.0, 0.5, 0.2), "f32"),
+    (10, 6000, 128, 500, 100, (0.5, 0.02), "f32"),    # BASELINE.json config 5: top-500 -> 100; lam = 0.02: diversity dominates
+    (8, 3000, 256, 300, 40, (0.3,), "bf16"),          # bf16 table, two float4 chunks per lane
+    (6, 2000, 36, 700, 25, (0.1,), "f32"),            # C > 512 (8 slots per lane), d not a multiple of 32
+    (5, 1500, 30, 90, 20, (0.4,), "f32"),             # d % 4 != 0: the eager kernel
+])
+def test_mmr_rerank_vs_oracle(native, dev, nU, nI, d, C, k, lams, table):
     """Greedy MMR re-rank (no reference implementation: parity is against the oracle).  Greedy arg-max chains are
     sensitive to last-bit differences, so every pick is checked to be an (almost) maximiser of the oracle's
     objective given the picks made so far, and identical whenever the oracle's margin is clear."""
     from divrec.rerank import mmr_rerank
-    gen = torch.Generator().manual_seed(61)
-    nU, nI, d, C, k = 24, 4000, 64, 120, 30
+    gen = torch.Generator().manual_seed(61 + C)
     U, V = O.make_embeddings(nU, d, "gauss", gen), O.make_embeddings(nI, d, "gauss", gen)
+    if table == "bf16":
+        V = V.bfloat16().float()
+    if lams[-1] < 0.05:
+        U = U * 0.05   # small relevance scores: the similarity term decides most picks
     cand, sc = O.recommendations_dense(U, V, None, None, C)
-    cand[3, 100:] = -1   # a ragged candidate list
-    sc[3, 100:] = float("-inf")
-    for lam in (1.0, 0.5, 0.2):
+    cand[3, C - 20:] = -1   # a ragged candidate list
+    sc[3, C - 20:] = float("-inf")
+    Vd = V.to(dev).bfloat16() if table == "bf16" else V.to(dev)
+    for lam in lams:
         want = O.mmr_rerank(cand, sc, V, k, lam)
-        got, rel = mmr_rerank(V.to(dev), cand.to(dev), sc.to(dev), k, lam)
+        got, rel = mmr_rerank(Vd, cand.to(dev), sc.to(dev), k, lam)
         got, rel = got.cpu(), rel.cpu()
         assert torch.equal(got[:, 0], cand[:, 0])
         if lam == 1.0:
