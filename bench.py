@@ -384,14 +384,33 @@ def bench_cfg3(args):
     loss_buf = torch.zeros(1, dtype=torch.float32, device=dev)
     auc_buf = torch.zeros(1, dtype=torch.int32, device=dev)
 
+    # item-gradient exchange: the dense all-reduce BASELINE.json names, or the sparse form (all-gather of the per-triple
+    # rows g_b U[u_b] + ids, every rank scatter-adds all of them: the same dense gV on every rank) when it moves less
+    sparse = world > 1 and (args.cfg3_item_grad == "sparse" or
+                            (args.cfg3_item_grad == "auto" and world * B * (d + 4) * 4 <= nI * d * 4))
+    if sparse:
+        rows = torch.empty((B, d), dtype=torch.float32, device=dev)
+        all_rows = torch.empty((world * B, d), dtype=torch.float32, device=dev)
+        ids = torch.empty((2, B), dtype=torch.int64, device=dev)
+        all_ids = torch.empty((world * 2, B), dtype=torch.int64, device=dev)
+
     def step(uu, pp, nn):
         # forward + backward in ONE kernel (divrec_bpr_step): the rows of a triple are read once
         loss_buf.zero_(); auc_buf.zero_()
-        _p, _n, loss_sum, auc_sum = N.bpr_step(U, V, uu, pp, nn, 1.0 / Bg, gU, gV, want_scores=False, loss_sum=loss_buf, auc_sum=auc_buf)
+        if sparse:
+            N.bpr_step(U, V, uu, pp, nn, 1.0 / Bg, gU, None, want_scores=False, loss_sum=loss_buf, auc_sum=auc_buf, item_rows=rows)
+            ids[0].copy_(pp); ids[1].copy_(nn)
+            dist.all_gather_into_tensor(all_rows, rows)
+            dist.all_gather_into_tensor(all_ids, ids)
+            g3 = all_ids.view(world, 2, B)
+            N.bpr_apply_rows(all_rows, g3[:, 0].reshape(-1), g3[:, 1].reshape(-1), gV)
+        else:
+            N.bpr_step(U, V, uu, pp, nn, 1.0 / Bg, gU, gV, want_scores=False, loss_sum=loss_buf, auc_sum=auc_buf)
+            if dist is not None:
+                dist.all_reduce(gV)
         if dist is not None:
-            dist.all_reduce(gV)
-            dist.all_reduce(loss_sum)
-        return loss_sum
+            dist.all_reduce(loss_buf)
+        return loss_buf
 
     for _ in range(max(3, args.warmup)):
         step(u, p_, n_)
@@ -442,7 +461,9 @@ def bench_cfg3(args):
                 "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": "cfg3: BPR step, 1M users x 1M items", "d": d, "triples_per_gpu": B,
-                           "sharding": "triples partitioned by user shard; item-gradient all-reduce" if world > 1 else "single GPU",
+                           "sharding": ("triples partitioned by user shard; item gradient: " +
+                                        ("all-gather of per-triple rows + scatter-add on every rank (sparse form of the all-reduce)" if sparse
+                                         else "dense all-reduce")) if world > 1 else "single GPU",
                            "l2": "tables + dense gradients (2 GB) exceed the 126 MB L2"},
                 "clocks": clocks,
                 "e2e": {"value": Bg / (float(e2e) / args.steps * 1e-3), "unit": "triples/s", "h2d_bytes_per_step": 3 * B * 8,
@@ -625,6 +646,7 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS) + ["cfg3", "cfg4", "cfg5"])
     ap.add_argument("--cfg5-users", type=int, default=1_000_000)
     ap.add_argument("--cfg5-candidates", type=int, default=500)
+    ap.add_argument("--cfg3-item-grad", default="auto", choices=["auto", "dense", "sparse"])
     ap.add_argument("--cfg4-items", type=int, default=10_000_000)
     ap.add_argument("--cfg4-queries", type=int, default=65536)
     ap.add_argument("--cpu-sample", type=int, default=32768)

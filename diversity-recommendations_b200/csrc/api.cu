@@ -428,16 +428,28 @@ int divrec_bpr_bwd(const float* U, const float* V, const int64_t* u, const int64
 
 int divrec_bpr_step(const float* U, const float* V, const int64_t* u, const int64_t* p, const int64_t* n, int64_t B, int d,
                     float grad_scale, float* pos, float* neg, float* loss_sum, int32_t* auc_sum, float* gU, float* gV,
-                    void* stream) {
+                    float* item_rows, void* stream) {
   int rc = check_rows(U, V, d, "bpr_step");
   if (rc != DIVREC_OK) return rc;
   if (!u || !p || !n) return fail(DIVREC_ERR_ARG, "bpr_step: null index pointer");
   if (B <= 0) return fail(DIVREC_ERR_ARG, "bpr_step: B must be positive");
   if ((gU && (reinterpret_cast<uintptr_t>(gU) & 15)) || (gV && (reinterpret_cast<uintptr_t>(gV) & 15)))
     return fail(DIVREC_ERR_ARG, "bpr_step: gradient tables must be 16-byte aligned");
-  cudaError_t e = launch_bpr_step(U, V, u, p, n, B, d, grad_scale, pos, neg, loss_sum, auc_sum, gU, gV,
+  if (item_rows && (reinterpret_cast<uintptr_t>(item_rows) & 15)) return fail(DIVREC_ERR_ARG, "bpr_step: item_rows must be 16-byte aligned");
+  cudaError_t e = launch_bpr_step(U, V, u, p, n, B, d, grad_scale, pos, neg, loss_sum, auc_sum, gU, gV, item_rows,
                                   reinterpret_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "bpr_step launch");
+  return DIVREC_OK;
+}
+
+int divrec_bpr_apply_rows(const float* rows, const int64_t* p, const int64_t* n, int64_t N, int d, float* gV, void* stream) {
+  if (!rows || !p || !n || !gV) return fail(DIVREC_ERR_ARG, "bpr_apply_rows: null pointer");
+  if (N <= 0) return fail(DIVREC_ERR_ARG, "bpr_apply_rows: N must be positive");
+  if (d <= 0 || (d & 3) || d > 1024) return fail(DIVREC_ERR_ARG, "bpr_apply_rows: d must be a multiple of 4, <= 1024");
+  if ((reinterpret_cast<uintptr_t>(rows) & 15) || (reinterpret_cast<uintptr_t>(gV) & 15))
+    return fail(DIVREC_ERR_ARG, "bpr_apply_rows: rows and gV must be 16-byte aligned");
+  cudaError_t e = launch_bpr_apply_rows(rows, p, n, N, d, gV, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "bpr_apply_rows launch");
   return DIVREC_OK;
 }
 

@@ -108,7 +108,8 @@ __global__ void __launch_bounds__(256)
 bpr_step_kernel(const float* __restrict__ U, const float* __restrict__ V, const int64_t* __restrict__ u,
                 const int64_t* __restrict__ p, const int64_t* __restrict__ n, int64_t B, int d, float grad_scale,
                 float* __restrict__ pos, float* __restrict__ neg, float* __restrict__ loss_sum,
-                int32_t* __restrict__ auc_sum, float* __restrict__ gU, float* __restrict__ gV) {
+                int32_t* __restrict__ auc_sum, float* __restrict__ gU, float* __restrict__ gV,
+                float* __restrict__ item_rows) {
   __shared__ float red_loss[8];
   __shared__ int red_auc[8];
   const uint32_t lane = lane_id();
@@ -152,6 +153,8 @@ bpr_step_kernel(const float* __restrict__ U, const float* __restrict__ V, const 
           red_add_v4(gV + ip * d + v * 4, c * a[j].x, c * a[j].y, c * a[j].z, c * a[j].w);
           red_add_v4(gV + in * d + v * 4, -c * a[j].x, -c * a[j].y, -c * a[j].z, -c * a[j].w);
         }
+        // sparse form of the item gradient: row b = c U[u_b], to be added to gV[p_b] and subtracted from gV[n_b]
+        if (item_rows) reinterpret_cast<float4*>(item_rows + b * d)[v] = make_float4(c * a[j].x, c * a[j].y, c * a[j].z, c * a[j].w);
       }
     }
   }
@@ -164,6 +167,23 @@ bpr_step_kernel(const float* __restrict__ U, const float* __restrict__ V, const 
     for (int i = 0; i < 8; ++i) { l += red_loss[i]; au += red_auc[i]; }
     if (loss_sum) atomicAdd(loss_sum, l);
     if (auc_sum) atomicAdd(auc_sum, au);
+  }
+}
+
+// gV[p_j] += rows_j;  gV[n_j] -= rows_j  -- applies item-gradient rows gathered from all ranks (bpr_step's item_rows)
+__global__ void __launch_bounds__(256)
+bpr_apply_rows_kernel(const float* __restrict__ rows, const int64_t* __restrict__ p, const int64_t* __restrict__ n,
+                      int64_t N, int d, float* __restrict__ gV) {
+  const uint32_t lane = lane_id();
+  const int warp = threadIdx.x >> 5;
+  const int nvec = d >> 2;
+  for (int64_t b = (int64_t)blockIdx.x * 8 + warp; b < N; b += (int64_t)gridDim.x * 8) {
+    const int64_t ip = p[b], in = n[b];
+    for (int v = lane; v < nvec; v += 32) {
+      const float4 r = __ldg(reinterpret_cast<const float4*>(rows + b * d) + v);
+      red_add_v4(gV + ip * d + v * 4, r.x, r.y, r.z, r.w);
+      red_add_v4(gV + in * d + v * 4, -r.x, -r.y, -r.z, -r.w);
+    }
   }
 }
 
@@ -256,14 +276,23 @@ cudaError_t launch_bpr_bwd(const float* U, const float* V, const int64_t* u, con
 
 cudaError_t launch_bpr_step(const float* U, const float* V, const int64_t* u, const int64_t* p, const int64_t* n, int64_t B,
                             int d, float grad_scale, float* pos, float* neg, float* loss_sum, int32_t* auc_sum, float* gU,
-                            float* gV, cudaStream_t stream) {
+                            float* gV, float* item_rows, cudaStream_t stream) {
   // every resident warp loops over several triples, so loads of the next triple overlap the scatter-adds of this one
   int64_t g = (B + 7) / 8;
   if (g > 148 * 8) g = 148 * 8;
-  if (d <= 128) bpr_step_kernel<1><<<(unsigned)g, 256, 0, stream>>>(U, V, u, p, n, B, d, grad_scale, pos, neg, loss_sum, auc_sum, gU, gV);
-  else if (d <= 256) bpr_step_kernel<2><<<(unsigned)g, 256, 0, stream>>>(U, V, u, p, n, B, d, grad_scale, pos, neg, loss_sum, auc_sum, gU, gV);
-  else if (d <= 512) bpr_step_kernel<4><<<(unsigned)g, 256, 0, stream>>>(U, V, u, p, n, B, d, grad_scale, pos, neg, loss_sum, auc_sum, gU, gV);
-  else bpr_step_kernel<8><<<(unsigned)g, 256, 0, stream>>>(U, V, u, p, n, B, d, grad_scale, pos, neg, loss_sum, auc_sum, gU, gV);
+  if (d <= 128) bpr_step_kernel<1><<<(unsigned)g, 256, 0, stream>>>(U, V, u, p, n, B, d, grad_scale, pos, neg, loss_sum, auc_sum, gU, gV, item_rows);
+  else if (d <= 256) bpr_step_kernel<2><<<(unsigned)g, 256, 0, stream>>>(U, V, u, p, n, B, d, grad_scale, pos, neg, loss_sum, auc_sum, gU, gV, item_rows);
+  else if (d <= 512) bpr_step_kernel<4><<<(unsigned)g, 256, 0, stream>>>(U, V, u, p, n, B, d, grad_scale, pos, neg, loss_sum, auc_sum, gU, gV, item_rows);
+  else bpr_step_kernel<8><<<(unsigned)g, 256, 0, stream>>>(U, V, u, p, n, B, d, grad_scale, pos, neg, loss_sum, auc_sum, gU, gV, item_rows);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_bpr_apply_rows(const float* rows, const int64_t* p, const int64_t* n, int64_t N, int d, float* gV,
+                                  cudaStream_t stream) {
+  int64_t g = (N + 7) / 8;
+  if (g > 148 * 8) g = 148 * 8;
+  bpr_apply_rows_kernel<<<(unsigned)g, 256, 0, stream>>>(rows, p, n, N, d, gV);
   count_launch();
   return cudaGetLastError();
 }

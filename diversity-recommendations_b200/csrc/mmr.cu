@@ -13,11 +13,11 @@
 // top candidate is exact; the block then takes the best of the four exact champions, ties -> lowest rank -- the same
 // pick as the eager arg-max, with only the candidates that can still win ever being gathered and evaluated (eager
 // costs k C d FMA per user and re-reads every candidate row k times).
-// One CTA of 4 warps per user (persistent).  Candidate c belongs to warp c % 4; its score, bound, state live in that
-// warp's registers.  The normalised picked rows sit in shared memory (row stride d + 4 floats: conflict-free 128-bit
-// reads with one lane per pick), each warp caches the normalised row of its current champion (which is also the
-// row copied to the pick list when it wins).  Refreshes against many picks run one lane per pick; against a few,
-// one pick at a time with a shuffle reduction.
+// One CTA of 8 warps per user (persistent, 4 CTAs per SM).  Candidate c belongs to warp c % 8; its score, bound and
+// state live in that warp's registers.  The normalised picked rows sit in shared memory (row stride d + 4 floats:
+// conflict-free 128-bit reads with one lane per pick); a warp keeps the raw row of its current champion in registers
+// (cos = <V_c, E_t> / |V_c|: one division per refresh).  Refreshes against many picks run one lane per pick; against
+// a few, two picks at a time with shuffle reductions.
 // mmr_kernel: the eager form (any d, any C), kept for shapes the lazy kernel does not take.
 #include <cstdlib>
 
@@ -159,8 +159,8 @@ mmr_kernel(const MmrParams p) {
 // ---------------------------------------------------------------------------------------------------------
 // lazy greedy
 // ---------------------------------------------------------------------------------------------------------
-constexpr int LW = 4;             // warps per user
-constexpr int LAZY_LANE_MIN = 12; // refreshes against more picks than this run one lane per pick
+constexpr int LW = 8;             // warps per user
+constexpr int LAZY_LANE_MIN = 10; // refreshes against more picks than this run one lane per pick
 
 template <int DT>
 __device__ __forceinline__ float4 ld_row4(const void* V, int64_t row, int d, int c4) {
@@ -178,11 +178,13 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-// S = candidate slots per lane (C <= 128 S); NV = float4 chunks of a row per lane (d <= 128 NV); DT = table dtype
+// S = candidate slots per lane (C <= 32 LW S); NV = float4 chunks of a row per lane (d <= 128 NV); DT = table dtype.
+// cos(c, t) = <V_c, E_t> / |V_c| with E_t the normalised pick row: the candidate's row stays raw (registers) and the
+// maximum over the picks is divided by |V_c| once.
 template <int S, int NV, int DT>
 __global__ void __launch_bounds__(LW * 32, 4)
 mmr_lazy_kernel(const MmrParams p) {
-  extern __shared__ __align__(16) float dyn[];  // picks [k][ds] | champion-row cache [LW][ds]
+  extern __shared__ __align__(16) float dyn[];  // picks [k][ds] normalised | champion rows [LW][d] raw
   __shared__ float ch_obj[LW];
   __shared__ int ch_idx[LW];
   __shared__ int ch_cnt[LW];
@@ -190,21 +192,21 @@ mmr_lazy_kernel(const MmrParams p) {
   const uint32_t lane = lane_id();
   const int C = p.C, d = p.d, k = p.k, ds = d + 4, nvec = d >> 2;
   float* picks = dyn;
-  float* cache = dyn + (size_t)k * ds + (size_t)w * ds;
+  float* cache = dyn + (size_t)k * ds + (size_t)w * d;
   const float lam = p.lambda, om = 1.0f - p.lambda;
 
   for (int64_t u = blockIdx.x; u < p.nU; u += gridDim.x) {
-    // ---- this warp's candidates: c = 4 (32 s + lane) + w ----
+    // ---- this warp's candidates: c = LW (32 s + lane) + w ----
     float sc[S], ms[S];
-    int seen[S], st[S], id[S];
+    int seen[S], id[S];   // id < 0: not a candidate (padding, or picked)
     int nv = 0;
 #pragma unroll
     for (int s = 0; s < S; ++s) {
       const int c = LW * (s * 32 + (int)lane) + w;
-      sc[s] = -INFINITY; ms[s] = -1.0001f; seen[s] = 0; st[s] = 2; id[s] = -1;  // cos >= -1: the bound before any evaluation
+      sc[s] = -INFINITY; ms[s] = -1.0001f; seen[s] = 0; id[s] = -1;  // cos >= -1: the bound before any evaluation
       if (c < C) {
         const int64_t it = p.cand_items[u * C + c];
-        if (it >= 0 && it < p.nI) { id[s] = (int)it; st[s] = 0; sc[s] = p.cand_scores[u * C + c]; ++nv; }
+        if (it >= 0 && it < p.nI) { id[s] = (int)it; sc[s] = p.cand_scores[u * C + c]; ++nv; }
       }
     }
     nv = __reduce_add_sync(0xffffffffu, nv);
@@ -214,26 +216,19 @@ mmr_lazy_kernel(const MmrParams p) {
 #pragma unroll
     for (int i = 0; i < LW; ++i) n_valid += ch_cnt[i];
     const int n_pick = min(k, n_valid);
-    int cache_c = -1;  // candidate whose normalised row is in this warp's cache (warp-uniform)
+    int cache_c = -1;      // candidate whose raw row is in this warp's cache / in `e` (warp-uniform)
+    float cache_nrm = 1.f; // its norm
+    float4 e[NV];          // this lane's chunks of that row
 
-    // normalised row of candidate `c` (item `item`) -> this warp's cache
-    auto load_cache = [&](int c, int item) {
-      float4 v[NV];
+    auto load_row = [&](int c, int item) {
       float ss = 0.f;
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
         const int c4 = (int)lane + 32 * j;
-        v[j] = c4 < nvec ? ld_row4<DT>(p.V, item, d, c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        ss = fmaf(v[j].x, v[j].x, ss); ss = fmaf(v[j].y, v[j].y, ss); ss = fmaf(v[j].z, v[j].z, ss); ss = fmaf(v[j].w, v[j].w, ss);
+        e[j] = c4 < nvec ? ld_row4<DT>(p.V, item, d, c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        ss = fmaf(e[j].x, e[j].x, ss); ss = fmaf(e[j].y, e[j].y, ss); ss = fmaf(e[j].z, e[j].z, ss); ss = fmaf(e[j].w, e[j].w, ss);
       }
-      const float nrm = sqrtf(warp_sum(ss));
-      __syncwarp();
-#pragma unroll
-      for (int j = 0; j < NV; ++j) {
-        const int c4 = (int)lane + 32 * j;
-        if (c4 < nvec) reinterpret_cast<float4*>(cache)[c4] = make_float4(v[j].x / nrm, v[j].y / nrm, v[j].z / nrm, v[j].w / nrm);
-      }
-      __syncwarp();
+      cache_nrm = sqrtf(warp_sum(ss));
       cache_c = c;
     };
 
@@ -250,7 +245,7 @@ mmr_lazy_kernel(const MmrParams p) {
           best = -INFINITY; bidx = 0x7fffffff;
 #pragma unroll
           for (int s = 0; s < S; ++s) {
-            if (st[s] == 0) {
+            if (id[s] >= 0) {
               const float ub = lam * sc[s] - om * ms[s];
               const int c = LW * (s * 32 + (int)lane) + w;
               if (ub > best || (ub == best && c < bidx)) { best = ub; bidx = c; }
@@ -263,7 +258,7 @@ mmr_lazy_kernel(const MmrParams p) {
             if (ov > best || (ov == best && oi < bidx)) { best = ov; bidx = oi; }
           }
           if (bidx == 0x7fffffff) break;  // nothing left in this warp
-          const int slot = bidx >> 7, ln = (bidx >> 2) & 31;
+          const int slot = (bidx / LW) >> 5, ln = (bidx / LW) & 31;
           int my_seen = 0, my_id = 0;
           float my_ms = 0.f;
 #pragma unroll
@@ -271,47 +266,66 @@ mmr_lazy_kernel(const MmrParams p) {
           const int cs = __shfl_sync(0xffffffffu, my_seen, ln);
           if (cs == r) break;  // exact: bound == objective
           const int item = __shfl_sync(0xffffffffu, my_id, ln);
-          float m = __shfl_sync(0xffffffffu, my_ms, ln);
-          if (cs == 0) m = -INFINITY;
-          if (cache_c != bidx) load_cache(bidx, item);
+          const float m_old = __shfl_sync(0xffffffffu, my_ms, ln);
+          if (cache_c != bidx) load_row(bidx, item);
+          float mraw = -INFINITY;  // max over the new picks of <V_c, E_t>
           if (r - cs > LAZY_LANE_MIN) {
-            // one lane per pick: full dot products, the champion's row broadcast from the cache
-            for (int t0 = cs; t0 < r; t0 += 32) {
-              const int t = t0 + (int)lane;
-              float dot = -INFINITY;
-              if (t < r) {
-                const float4* pr = reinterpret_cast<const float4*>(picks + (size_t)t * ds);
-                const float4* cr = reinterpret_cast<const float4*>(cache);
-                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-                for (int x = 0; x < nvec; ++x) {
-                  const float4 a = cr[x], b = pr[x];
-                  s0 = fmaf(a.x, b.x, s0); s1 = fmaf(a.y, b.y, s1); s2 = fmaf(a.z, b.z, s2); s3 = fmaf(a.w, b.w, s3);
-                }
-                dot = (s0 + s1) + (s2 + s3);
-              }
-              m = fmaxf(m, warp_max(dot));
-            }
-          } else {
-            float4 e[NV];
+            // one lane per pick: full dot products, the candidate's raw row broadcast from shared memory
+            __syncwarp();
 #pragma unroll
             for (int j = 0; j < NV; ++j) {
               const int c4 = (int)lane + 32 * j;
-              e[j] = c4 < nvec ? reinterpret_cast<const float4*>(cache)[c4] : make_float4(0.f, 0.f, 0.f, 0.f);
+              if (c4 < nvec) reinterpret_cast<float4*>(cache)[c4] = e[j];
             }
-            for (int t = cs; t < r; ++t) {
+            __syncwarp();
+            const float4* cr = reinterpret_cast<const float4*>(cache);
+            for (int t0 = cs; t0 < r; t0 += 32) {
+              const int t = min(t0 + (int)lane, r - 1);  // surplus lanes repeat the last pick (no effect on the maximum)
               const float4* pr = reinterpret_cast<const float4*>(picks + (size_t)t * ds);
-              float s0 = 0.f;
+              float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll 8
+              for (int x = 0; x < nvec; ++x) {
+                const float4 a = cr[x], b = pr[x];
+                s0 = fmaf(a.x, b.x, s0); s1 = fmaf(a.y, b.y, s1); s2 = fmaf(a.z, b.z, s2); s3 = fmaf(a.w, b.w, s3);
+              }
+              mraw = fmaxf(mraw, (s0 + s1) + (s2 + s3));
+            }
+            mraw = warp_max(mraw);
+          } else {
+            int t = cs;
+            for (; t + 1 < r; t += 2) {  // two picks per iteration: independent shuffle chains
+              const float4* pa = reinterpret_cast<const float4*>(picks + (size_t)t * ds);
+              const float4* pb = pa + (ds >> 2);
+              float sa = 0.f, sb = 0.f;
 #pragma unroll
               for (int j = 0; j < NV; ++j) {
                 const int c4 = (int)lane + 32 * j;
                 if (c4 < nvec) {
-                  const float4 b = pr[c4];
-                  s0 = fmaf(e[j].x, b.x, s0); s0 = fmaf(e[j].y, b.y, s0); s0 = fmaf(e[j].z, b.z, s0); s0 = fmaf(e[j].w, b.w, s0);
+                  const float4 x = pa[c4], y = pb[c4];
+                  sa = fmaf(e[j].x, x.x, sa); sa = fmaf(e[j].y, x.y, sa); sa = fmaf(e[j].z, x.z, sa); sa = fmaf(e[j].w, x.w, sa);
+                  sb = fmaf(e[j].x, y.x, sb); sb = fmaf(e[j].y, y.y, sb); sb = fmaf(e[j].z, y.z, sb); sb = fmaf(e[j].w, y.w, sb);
                 }
               }
-              m = fmaxf(m, warp_sum(s0));
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) { sa += __shfl_xor_sync(0xffffffffu, sa, o); sb += __shfl_xor_sync(0xffffffffu, sb, o); }
+              mraw = fmaxf(mraw, fmaxf(sa, sb));
+            }
+            if (t < r) {
+              const float4* pa = reinterpret_cast<const float4*>(picks + (size_t)t * ds);
+              float sa = 0.f;
+#pragma unroll
+              for (int j = 0; j < NV; ++j) {
+                const int c4 = (int)lane + 32 * j;
+                if (c4 < nvec) {
+                  const float4 x = pa[c4];
+                  sa = fmaf(e[j].x, x.x, sa); sa = fmaf(e[j].y, x.y, sa); sa = fmaf(e[j].z, x.z, sa); sa = fmaf(e[j].w, x.w, sa);
+                }
+              }
+              mraw = fmaxf(mraw, warp_sum(sa));
             }
           }
+          const float mnew = mraw / cache_nrm;
+          const float m = cs == 0 ? mnew : fmaxf(m_old, mnew);
           if ((int)lane == ln) {
 #pragma unroll
             for (int s = 0; s < S; ++s) if (s == slot) { ms[s] = m; seen[s] = r; }
@@ -329,24 +343,27 @@ mmr_lazy_kernel(const MmrParams p) {
       } else {
         bidx = 0;  // the first pick is the best-scored candidate
       }
-      // ---- commit pick j: its owner copies the normalised row to the pick list ----
+      // ---- commit pick j: its owner writes the normalised row to the pick list ----
       const int j = bidx;
       if (j != 0x7fffffff && (j & (LW - 1)) == w) {
-        const int slot = j >> 7, ln = (j >> 2) & 31;
+        const int slot = (j / LW) >> 5, ln = (j / LW) & 31;
         int my_id = -1;
 #pragma unroll
         for (int s = 0; s < S; ++s) if (s == slot) my_id = id[s];
         const int item = __shfl_sync(0xffffffffu, my_id, ln);
-        if (item >= 0) {
-          if (cache_c != j) load_cache(j, item);
-          for (int x = lane; x < nvec; x += 32)
-            reinterpret_cast<float4*>(picks + (size_t)r * ds)[x] = reinterpret_cast<const float4*>(cache)[x];
-        } else {
-          for (int x = lane; x < nvec; x += 32) reinterpret_cast<float4*>(picks + (size_t)r * ds)[x] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (item >= 0 && cache_c != j) load_row(j, item);
+#pragma unroll
+        for (int jj = 0; jj < NV; ++jj) {
+          const int c4 = (int)lane + 32 * jj;
+          if (c4 < nvec) {
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (item >= 0) o = make_float4(e[jj].x / cache_nrm, e[jj].y / cache_nrm, e[jj].z / cache_nrm, e[jj].w / cache_nrm);
+            reinterpret_cast<float4*>(picks + (size_t)r * ds)[c4] = o;
+          }
         }
         if ((int)lane == ln) {
 #pragma unroll
-          for (int s = 0; s < S; ++s) if (s == slot) st[s] = 1;
+          for (int s = 0; s < S; ++s) if (s == slot) id[s] = -1;  // picked: no longer a candidate
           p.out_items[u * k + r] = p.cand_items[u * C + j];
           if (p.out_scores) p.out_scores[u * k + r] = p.cand_scores[u * C + j];
         }
@@ -384,21 +401,21 @@ size_t mmr_scratch_bytes(int C, int d, int* grid_out) {
 
 cudaError_t launch_mmr(MmrParams p, cudaStream_t stream) {
   // lazy greedy for the shapes it takes: 128-bit rows, C <= 1024, pick list + caches within shared memory
-  const size_t lazy_smem = ((size_t)p.k + LW) * (size_t)(p.d + 4) * sizeof(float);
+  const size_t lazy_smem = ((size_t)p.k * (size_t)(p.d + 4) + (size_t)LW * p.d) * sizeof(float);
   if ((p.d & 3) == 0 && p.d <= 512 && p.C <= 1024 && lazy_smem <= 200 * 1024 && p.nI < ((int64_t)1 << 31) &&
       !getenv("DIVREC_DEBUG_MMR_EAGER")) {
-    int per_sm = (int)((220 * 1024) / (lazy_smem + 1024));
+    int per_sm = (int)((size_t)232448 / (lazy_smem + 1024 + 128));  // per-SM shared memory / (dynamic + reserved + static)
     if (per_sm > 4) per_sm = 4;
     if (per_sm < 1) per_sm = 1;
     int64_t g = (int64_t)148 * per_sm;
     if (g > p.nU) g = p.nU;
-    const int S = p.C <= 128 ? 1 : p.C <= 256 ? 2 : p.C <= 512 ? 4 : 8;
+    const int S = p.C <= 256 ? 1 : p.C <= 512 ? 2 : 4;   // candidate slots per lane: C <= 32 LW S
     const int NV = p.d <= 128 ? 1 : p.d <= 256 ? 2 : 4;
     cudaError_t e = cudaErrorInvalidValue;
 #define DIVREC_MMR(SS, NN) if (S == SS && NV == NN) e = launch_mmr_lazy_t<SS, NN>(p, (int)g, lazy_smem, stream)
-    DIVREC_MMR(1, 1); DIVREC_MMR(2, 1); DIVREC_MMR(4, 1); DIVREC_MMR(8, 1);
-    DIVREC_MMR(1, 2); DIVREC_MMR(2, 2); DIVREC_MMR(4, 2); DIVREC_MMR(8, 2);
-    DIVREC_MMR(1, 4); DIVREC_MMR(2, 4); DIVREC_MMR(4, 4); DIVREC_MMR(8, 4);
+    DIVREC_MMR(1, 1); DIVREC_MMR(2, 1); DIVREC_MMR(4, 1);
+    DIVREC_MMR(1, 2); DIVREC_MMR(2, 2); DIVREC_MMR(4, 2);
+    DIVREC_MMR(1, 4); DIVREC_MMR(2, 4); DIVREC_MMR(4, 4);
 #undef DIVREC_MMR
     count_launch();
     return e;

@@ -46,7 +46,8 @@ SIGNATURES = {
     "divrec_entropy_from_counts": (_i32, [_vp, _i64, _vp, _vp]),
     "divrec_bpr_fwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp]),
     "divrec_bpr_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _i64, _i32, _vp, _vp, _vp]),
-    "divrec_bpr_step": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "divrec_bpr_step": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "divrec_bpr_apply_rows": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _vp]),
     "divrec_pair_scores": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp]),
     "divrec_pair_scores_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp]),
     "divrec_ild_labels": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _vp]),
@@ -359,9 +360,11 @@ def bpr_fwd(U, V, u, p, n):
 
 
 def bpr_step(U, V, u, p, n, grad_scale: float, gU: Optional[torch.Tensor], gV: Optional[torch.Tensor],
-             want_scores: bool = True, loss_sum: Optional[torch.Tensor] = None, auc_sum: Optional[torch.Tensor] = None):
+             want_scores: bool = True, loss_sum: Optional[torch.Tensor] = None, auc_sum: Optional[torch.Tensor] = None,
+             item_rows: Optional[torch.Tensor] = None):
     """Forward + backward of one batch in one kernel (upstream gradient of the loss = grad_scale * B, i.e. grad_scale = 1/B
     for `mean_loss.backward()`): gradients accumulate into the dense tables gU / gV.
+    item_rows [B,d] (optional) receives the sparse form of the item gradient (row b = g_b U[u_b]; see bpr_apply_rows).
     Returns pos [B] | None, neg [B] | None, loss_sum [1] fp32, auc_sum [1] int32."""
     lib = load_library()
     U = _cuda(U, "U", torch.float32)
@@ -369,11 +372,13 @@ def bpr_step(U, V, u, p, n, grad_scale: float, gU: Optional[torch.Tensor], gV: O
     u = _cuda(u, "user_id", torch.int64)
     p = _cuda(p, "positive_item_id", torch.int64)
     n = _cuda(n, "negative_item_id", torch.int64)
-    for name, t in (("gU", gU), ("gV", gV)):
+    for name, t in (("gU", gU), ("gV", gV), ("item_rows", item_rows)):
         if t is not None and (not t.is_cuda or not t.is_contiguous() or t.dtype != torch.float32):
             raise TypeError(f"{name} must be a contiguous float32 CUDA tensor")
     B = u.numel()
     d = U.shape[1]
+    if item_rows is not None and tuple(item_rows.shape) != (B, d):
+        raise ValueError("item_rows must be [B, d]")
     pos = torch.empty(B, dtype=torch.float32, device=U.device) if want_scores else None
     neg = torch.empty(B, dtype=torch.float32, device=U.device) if want_scores else None
     if loss_sum is None:
@@ -382,9 +387,25 @@ def bpr_step(U, V, u, p, n, grad_scale: float, gU: Optional[torch.Tensor], gV: O
         auc_sum = torch.zeros(1, dtype=torch.int32, device=U.device)
     with torch.cuda.device(U.device):
         rc = lib.divrec_bpr_step(_ptr(U), _ptr(V), _ptr(u), _ptr(p), _ptr(n), B, d, float(grad_scale), _ptr(pos), _ptr(neg),
-                                 _ptr(loss_sum), _ptr(auc_sum), _ptr(gU), _ptr(gV), _stream(U.device))
+                                 _ptr(loss_sum), _ptr(auc_sum), _ptr(gU), _ptr(gV), _ptr(item_rows), _stream(U.device))
     _check(rc, "divrec_bpr_step")
     return pos, neg, loss_sum, auc_sum
+
+
+def bpr_apply_rows(rows: torch.Tensor, p: torch.Tensor, n: torch.Tensor, gV: torch.Tensor) -> None:
+    """gV[p_j] += rows_j; gV[n_j] -= rows_j (duplicates accumulate): applies gathered item-gradient rows."""
+    lib = load_library()
+    rows = _cuda(rows, "rows", torch.float32)
+    p = _cuda(p, "positive_item_id", torch.int64)
+    n = _cuda(n, "negative_item_id", torch.int64)
+    if not gV.is_cuda or not gV.is_contiguous() or gV.dtype != torch.float32:
+        raise TypeError("gV must be a contiguous float32 CUDA tensor")
+    N, d = rows.shape
+    if p.numel() != N or n.numel() != N or gV.shape[1] != d:
+        raise ValueError("rows [N,d], p [N], n [N], gV [nI,d] expected")
+    with torch.cuda.device(rows.device):
+        rc = lib.divrec_bpr_apply_rows(_ptr(rows), _ptr(p), _ptr(n), N, d, _ptr(gV), _stream(rows.device))
+    _check(rc, "divrec_bpr_apply_rows")
 
 
 def bpr_bwd(U, V, u, p, n, pos, neg, grad_scale: float, gU: torch.Tensor, gV: torch.Tensor, g: Optional[torch.Tensor] = None):

@@ -56,6 +56,9 @@ def recommend_user_sharded(U: torch.Tensor, V: torch.Tensor, seen_rowptr: Option
     return items, scores, ild, (stat[0] / stat[1]).to(torch.float32), counts, (a, b)
 
 
+_route_cache = {}
+
+
 def _all_gather_stacked(t: torch.Tensor, world: int, group) -> torch.Tensor:
     """all_gather of equally shaped [n, k] tensors straight into one [world, n, k] buffer (no per-rank copies)."""
     flat = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
@@ -78,30 +81,55 @@ def recommend_item_sharded(U: torch.Tensor, V_shard: torch.Tensor, shard_offset:
     # backend has it and the sizes allow; otherwise the two-tensor form.
     packed = (hasattr(K, "topk_pack") and world * k <= getattr(K, "MERGE_PACKED_MAX", 0)
               and shard_offset + V_shard.shape[0] < 2 ** 32)
-    flag = torch.tensor([1 if packed else 0], dtype=torch.int32, device=s.device)
-    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)  # every rank must take the same route
-    if int(flag) == 1:
+    key = (id(group), world, k, int(shard_offset), int(V_shard.shape[0]), bool(packed))
+    route = _route_cache.get(key)
+    if route is None:  # every rank must take the same route: agreed once per configuration (a host sync), then cached
+        flag = torch.tensor([1 if packed else 0], dtype=torch.int32, device=s.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        route = _route_cache[key] = int(flag)
+    if route == 1:
         mine = K.topk_pack(s, i)
         return K.topk_merge_packed(_all_gather_stacked(mine, world, group))
     return K.topk_merge(_all_gather_stacked(s, world, group), _all_gather_stacked(i, world, group))
 
 
 def bpr_step_sharded(U: torch.Tensor, V: torch.Tensor, u: torch.Tensor, p: torch.Tensor, n: torch.Tensor,
-                     global_batch: int, group=None, kernels=None):
+                     global_batch: int, group=None, kernels=None, item_grad: str = "auto"):
     """One BPR forward/backward on this rank's triples (its users only).  Gradients are those of the GLOBAL
     mean loss: every rank scales by 1 / global_batch, the item-table gradient is summed over ranks, the user
     gradient needs no communication because a user's triples live on one rank.
+
+    item_grad: "dense" all-reduces the [nI, d] item gradient (BASELINE.json config 3 as stated); "sparse"
+    all-gathers the per-triple rows g_b U[u_b] with their (positive, negative) ids and every rank scatter-adds all of
+    them -- the same dense result on every rank for world * B * (d + 4) * 4 gathered bytes instead of the ring
+    all-reduce's 2 nI d 4; "auto" picks sparse when the gathered rows are at most half of that (needs equal batch
+    sizes on all ranks).
     Returns (loss_global, auc_global, gU_local_rows_dense, gV_global)."""
     K = _kernels(kernels)
     rank, world = _world(group)
+    B, d = u.numel(), U.shape[1]
+    sparse = False
+    if world > 1 and item_grad != "dense" and hasattr(K, "bpr_apply_rows"):
+        sparse = item_grad == "sparse" or world * B * (d + 4) * 4 <= V.shape[0] * d * 4
     gU, gV = torch.zeros_like(U), torch.zeros_like(V)
-    if hasattr(K, "bpr_step"):  # forward + backward in one pass over the rows
+    if sparse:
+        rows = torch.empty((B, d), dtype=torch.float32, device=U.device)
+        _pos, _neg, loss_sum, auc_sum = K.bpr_step(U, V, u, p, n, 1.0 / global_batch, gU, None, want_scores=False, item_rows=rows)
+        ids = torch.stack([p.to(torch.int64), n.to(torch.int64)])                       # [2, B]
+        all_rows = torch.empty((world * B, d), dtype=torch.float32, device=U.device)
+        all_ids = torch.empty((world * 2, B), dtype=torch.int64, device=U.device)
+        dist.all_gather_into_tensor(all_rows, rows, group=group)
+        dist.all_gather_into_tensor(all_ids, ids.contiguous(), group=group)
+        all_ids = all_ids.view(world, 2, B)
+        K.bpr_apply_rows(all_rows, all_ids[:, 0].reshape(-1), all_ids[:, 1].reshape(-1), gV)
+    elif hasattr(K, "bpr_step"):  # forward + backward in one pass over the rows
         _pos, _neg, loss_sum, auc_sum = K.bpr_step(U, V, u, p, n, 1.0 / global_batch, gU, gV, want_scores=False)
     else:
         pos, neg, loss_sum, auc_sum = K.bpr_fwd(U, V, u, p, n)
         K.bpr_bwd(U, V, u, p, n, pos, neg, 1.0 / global_batch, gU, gV)
     stat = torch.stack([loss_sum.reshape(()).to(torch.float64), auc_sum.reshape(()).to(torch.float64)])
     if world > 1:
-        dist.all_reduce(gV, group=group)
+        if not sparse:
+            dist.all_reduce(gV, group=group)
         dist.all_reduce(stat, group=group)
     return (stat[0] / global_batch).to(torch.float32), (stat[1] / global_batch).to(torch.float32), gU, gV

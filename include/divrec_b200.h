@@ -189,10 +189,17 @@ int divrec_bpr_bwd(const float* U, const float* V, const int64_t* u, const int64
  *   divrec/train/utils.py:149 has upstream gradient 1, so g_b = -sigmoid(-(pos_b-neg_b)) * grad_scale
  *   is known as soon as the scores are; grad_scale = 1/B for the mean loss): rows are read once, DRAM
  *   traffic = 3 row reads + 3 row read-modify-writes per triple.  pos / neg may be NULL; loss_sum and
- *   auc_sum as in divrec_bpr_fwd; gU / gV accumulate (dense tables, caller-owned, either may be NULL). */
+ *   auc_sum as in divrec_bpr_fwd; gU / gV accumulate (dense tables, caller-owned, either may be NULL).
+ *   item_rows (nullable, [B,d]): the SPARSE form of the item gradient -- row b = g_b U[u_b], to be added to
+ *   gV[p_b] and subtracted from gV[n_b].  Multi-GPU steps whose batch touches few rows all-gather these rows (+ ids)
+ *   instead of all-reducing the dense [nI,d] table and apply them with divrec_bpr_apply_rows. */
 int divrec_bpr_step(const float* U, const float* V, const int64_t* u, const int64_t* p,
                     const int64_t* n, int64_t B, int d, float grad_scale, float* pos, float* neg,
-                    float* loss_sum, int32_t* auc_sum, float* gU, float* gV, void* stream);
+                    float* loss_sum, int32_t* auc_sum, float* gU, float* gV, float* item_rows,
+                    void* stream);
+/* gV[p_j] += rows_j;  gV[n_j] -= rows_j   for j < N (duplicates accumulate) */
+int divrec_bpr_apply_rows(const float* rows, const int64_t* p, const int64_t* n, int64_t N, int d,
+                          float* gV, void* stream);
 
 /* paired scoring  out[l] = <U[user_id[l]], V[item_id[l]]>
  *   replaces: divrec/models/matrix_factorization.py:19-28 (MatrixFactorization.forward) */

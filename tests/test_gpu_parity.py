@@ -427,6 +427,14 @@ def test_bpr_one_kernel_step_vs_reference_golden(native, dev, name):
     _, _, l3, _ = native.bpr_step(U, V, u, p, n, 1.0 / B, gU, gV, want_scores=False)
     assert (gU.cpu() - 2 * g["gU"]).abs().max().item() <= 2 * REL * float(g["gU"].abs().max())
     assert float(l3) == pytest.approx(float(loss_sum), rel=1e-6)
+    # sparse form of the item gradient (multi-GPU exchange): rows g_b U[u_b], applied by divrec_bpr_apply_rows
+    rows = torch.empty((B, U.shape[1]), dtype=torch.float32, device=dev)
+    gU2, gV2 = torch.zeros_like(U), torch.zeros_like(V)
+    native.bpr_step(U, V, u, p, n, 1.0 / B, gU2, None, want_scores=False, item_rows=rows)
+    native.bpr_apply_rows(rows, p, n, gV2)
+    assert (gV2.cpu() - g["gV"]).abs().max().item() <= REL * float(g["gV"].abs().max())
+    assert (gU2.cpu() - g["gU"]).abs().max().item() <= REL * float(g["gU"].abs().max())
+    assert torch.equal(gV2.cpu() == 0, g["gV"] == 0)
 
 
 def test_bpr_permutation_invariance(native, dev):

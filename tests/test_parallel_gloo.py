@@ -60,6 +60,24 @@ class OracleKernels:
         return pos, neg, (loss * B).reshape(1), (auc * B).round().int().reshape(1)
 
     @staticmethod
+    def bpr_step(U, V, u, p, n, scale, gU, gV, want_scores=True, loss_sum=None, auc_sum=None, item_rows=None):
+        pos, neg, loss, auc = O.bpr_forward(U, V, u, p, n)
+        B = u.numel()
+        a, b = O.bpr_backward(U, V, u, p, n, upstream=scale * B)
+        if gU is not None:
+            gU += a
+        if gV is not None:
+            gV += b
+        if item_rows is not None:   # row b = g_b U[u_b], g_b = -sigmoid(-(pos - neg)) * scale
+            item_rows.copy_((-torch.sigmoid(-(pos - neg).double()) * scale)[:, None].float() * U[u])
+        return pos, neg, (loss * B).reshape(1), (auc * B).round().int().reshape(1)
+
+    @staticmethod
+    def bpr_apply_rows(rows, p, n, gV):
+        gV.index_add_(0, p, rows)
+        gV.index_add_(0, n, -rows)
+
+    @staticmethod
     def bpr_bwd(U, V, u, p, n, pos, neg, scale, gU, gV):
         a, b = O.bpr_backward(U, V, u, p, n, upstream=scale * u.numel())
         gU += a
@@ -111,6 +129,22 @@ def _worker(rank, world, port, out):
     torch.testing.assert_close(gV, o_gV, rtol=0, atol=1e-6 * float(o_gV.abs().max()))
     torch.testing.assert_close(gU[a:b], o_gU[a:b], rtol=0, atol=1e-6 * float(o_gU.abs().max()))
     assert float(gU[:a].abs().sum()) == 0 and float(gU[b:].abs().sum()) == 0    # other shards' users untouched
+    # sparse item-gradient exchange (rows + ids all-gathered, every rank scatter-adds all of them): equal batch sizes
+    per_rank = []
+    for r in range(world):
+        ra, rb = parallel.shard_range(nU, r, world)
+        per_rank.append(((u >= ra) & (u < rb)).nonzero().flatten())
+    m = min(t.numel() for t in per_rank)
+    sel = torch.cat([t[:m] for t in per_rank])
+    me = per_rank[rank][:m]
+    loss_s, auc_s, gU_s, gV_s = parallel.bpr_step_sharded(Ug, Vg, u[me], p[me], n[me], world * m, kernels=K, item_grad="sparse")
+    _, _, o_loss, o_auc = O.bpr_forward(Ug, Vg, u[sel], p[sel], n[sel])
+    o_gU, o_gV = O.bpr_backward(Ug, Vg, u[sel], p[sel], n[sel])
+    assert abs(float(loss_s) - float(o_loss)) < 1e-5 * abs(float(o_loss)) and abs(float(auc_s) - float(o_auc)) < 1e-6
+    torch.testing.assert_close(gV_s, o_gV, rtol=0, atol=1e-6 * float(o_gV.abs().max()))
+    torch.testing.assert_close(gU_s[a:b], o_gU[a:b], rtol=0, atol=1e-6 * float(o_gU.abs().max()))
+    loss_d, _, _, gV_d = parallel.bpr_step_sharded(Ug, Vg, u[me], p[me], n[me], world * m, kernels=K, item_grad="dense")
+    torch.testing.assert_close(gV_d, gV_s, rtol=0, atol=1e-6 * float(o_gV.abs().max()))
     dist.barrier()
     dist.destroy_process_group()
     out.put(rank)
