@@ -8,16 +8,18 @@
 //
 // mmr_lazy_kernel (the product path): LAZY greedy.  A candidate's objective can only fall as picks are added (its
 // max-similarity only grows), so the objective evaluated against the first `seen_c` picks is an upper bound of the
-// current one (before any evaluation: cos >= -1).  Per step every warp takes the candidate with the largest bound
-// among those it owns, brings it up to date (dot products with the picks it has not seen yet) and repeats until its
-// top candidate is exact; the block then takes the best of the four exact champions, ties -> lowest rank -- the same
-// pick as the eager arg-max, with only the candidates that can still win ever being gathered and evaluated (eager
-// costs k C d FMA per user and re-reads every candidate row k times).
+// current one (before any evaluation: cos >= -1).  Per step every warp nominates the candidate with the largest bound
+// among those it owns; stale nominees are brought up to date (dot products with the picks they have not seen yet) and
+// the nomination repeats until every warp's top candidate is exact; the block then takes the best of the eight exact
+// champions, ties -> lowest rank -- the same pick as the eager arg-max, with only the candidates that can still win
+// ever being gathered and evaluated (eager costs k C d FMA per user and re-reads every candidate row k times).
+// The refreshes of a round are done by the WHOLE block, one thread per (nominee, unseen pick) pair, so a candidate
+// that is far behind (first evaluation, or long ignored) costs one pass instead of a long serial loop in one warp
+// while seven wait at the barrier (ncu on the per-warp version: 55 % of the stall samples at that barrier).
 // One CTA of 8 warps per user (persistent, 4 CTAs per SM).  Candidate c belongs to warp c % 8; its score, bound and
 // state live in that warp's registers.  The normalised picked rows sit in shared memory (row stride d + 4 floats:
 // conflict-free 128-bit reads with one lane per pick); a warp keeps the raw row of its current champion in registers
-// (cos = <V_c, E_t> / |V_c|: one division per refresh).  Refreshes against many picks run one lane per pick; against
-// a few, two picks at a time with shuffle reductions.
+// (cos = <V_c, E_t> / |V_c|: one division per refresh) and copies it to shared memory when it asks for a refresh.
 // mmr_kernel: the eager form (any d, any C), kept for shapes the lazy kernel does not take.
 #include <cstdlib>
 
@@ -160,7 +162,6 @@ mmr_kernel(const MmrParams p) {
 // lazy greedy
 // ---------------------------------------------------------------------------------------------------------
 constexpr int LW = 8;             // warps per user
-constexpr int LAZY_LANE_MIN = 10; // refreshes against more picks than this run one lane per pick
 
 template <int DT>
 __device__ __forceinline__ float4 ld_row4(const void* V, int64_t row, int d, int c4) {
@@ -172,12 +173,6 @@ __device__ __forceinline__ float4 ld_row4(const void* V, int64_t row, int d, int
                        __uint_as_float(raw.y << 16), __uint_as_float(raw.y & 0xffff0000u));
   }
 }
-__device__ __forceinline__ float warp_max(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
-}
-
 // S = candidate slots per lane (C <= 32 LW S); NV = float4 chunks of a row per lane (d <= 128 NV); DT = table dtype.
 // cos(c, t) = <V_c, E_t> / |V_c| with E_t the normalised pick row: the candidate's row stays raw (registers) and the
 // maximum over the picks is divided by |V_c| once.
@@ -187,7 +182,9 @@ mmr_lazy_kernel(const MmrParams p) {
   extern __shared__ __align__(16) float dyn[];  // picks [k][ds] normalised | champion rows [LW][d] raw
   __shared__ float ch_obj[LW];
   __shared__ int ch_idx[LW];
-  __shared__ int ch_cnt[LW];
+  __shared__ int rq_need[LW];        // refresh requests of the current round: picks the nominee has not seen ...
+  __shared__ int rq_cs[LW];          // ... starting at this pick
+  __shared__ unsigned rq_max[LW];    // max over those picks of <V_c, E_t> as an ordered key
   const int w = threadIdx.x >> 5;
   const uint32_t lane = lane_id();
   const int C = p.C, d = p.d, k = p.k, ds = d + 4, nvec = d >> 2;
@@ -210,11 +207,11 @@ mmr_lazy_kernel(const MmrParams p) {
       }
     }
     nv = __reduce_add_sync(0xffffffffu, nv);
-    if (lane == 0) ch_cnt[w] = nv;
+    if (lane == 0) rq_need[w] = nv;
     __syncthreads();
     int n_valid = 0;
 #pragma unroll
-    for (int i = 0; i < LW; ++i) n_valid += ch_cnt[i];
+    for (int i = 0; i < LW; ++i) n_valid += rq_need[i];
     const int n_pick = min(k, n_valid);
     int cache_c = -1;      // candidate whose raw row is in this warp's cache / in `e` (warp-uniform)
     float cache_nrm = 1.f; // its norm
@@ -240,99 +237,86 @@ mmr_lazy_kernel(const MmrParams p) {
       float best = -INFINITY;
       int bidx = 0x7fffffff;
       if (r > 0) {
-        // ---- lazy loop: until this warp's top candidate (by bound) is exact ----
+        // ---- rounds: every warp nominates its top candidate by bound; the stale nominees are brought up to date by
+        // the WHOLE block (one thread per (nominee, unseen pick) pair), until every warp's top candidate is exact ----
+        bool fresh = true;       // the nominee has to be (re)determined
+        int cs = 0, slot = 0, ln = 0;
+        float m_old = 0.f;
         for (;;) {
-          best = -INFINITY; bidx = 0x7fffffff;
+          if (fresh) {
+            best = -INFINITY; bidx = 0x7fffffff;
 #pragma unroll
-          for (int s = 0; s < S; ++s) {
-            if (id[s] >= 0) {
-              const float ub = lam * sc[s] - om * ms[s];
-              const int c = LW * (s * 32 + (int)lane) + w;
-              if (ub > best || (ub == best && c < bidx)) { best = ub; bidx = c; }
+            for (int s = 0; s < S; ++s) {
+              if (id[s] >= 0) {
+                const float ub = lam * sc[s] - om * ms[s];
+                const int c = LW * (s * 32 + (int)lane) + w;
+                if (ub > best || (ub == best && c < bidx)) { best = ub; bidx = c; }
+              }
             }
-          }
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
-            if (ov > best || (ov == best && oi < bidx)) { best = ov; bidx = oi; }
-          }
-          if (bidx == 0x7fffffff) break;  // nothing left in this warp
-          const int slot = (bidx / LW) >> 5, ln = (bidx / LW) & 31;
-          int my_seen = 0, my_id = 0;
-          float my_ms = 0.f;
+            for (int o = 16; o > 0; o >>= 1) {
+              const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+              const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+              if (ov > best || (ov == best && oi < bidx)) { best = ov; bidx = oi; }
+            }
+            cs = r;  // "nothing to refresh" when the warp has no candidate left
+            if (bidx != 0x7fffffff) {
+              slot = (bidx / LW) >> 5; ln = (bidx / LW) & 31;
+              int my_seen = 0, my_id = 0;
+              float my_ms = 0.f;
 #pragma unroll
-          for (int s = 0; s < S; ++s) if (s == slot) { my_seen = seen[s]; my_id = id[s]; my_ms = ms[s]; }
-          const int cs = __shfl_sync(0xffffffffu, my_seen, ln);
-          if (cs == r) break;  // exact: bound == objective
-          const int item = __shfl_sync(0xffffffffu, my_id, ln);
-          const float m_old = __shfl_sync(0xffffffffu, my_ms, ln);
-          if (cache_c != bidx) load_row(bidx, item);
-          float mraw = -INFINITY;  // max over the new picks of <V_c, E_t>
-          if (r - cs > LAZY_LANE_MIN) {
-            // one lane per pick: full dot products, the candidate's raw row broadcast from shared memory
-            __syncwarp();
+              for (int s = 0; s < S; ++s) if (s == slot) { my_seen = seen[s]; my_id = id[s]; my_ms = ms[s]; }
+              cs = __shfl_sync(0xffffffffu, my_seen, ln);
+              m_old = __shfl_sync(0xffffffffu, my_ms, ln);
+              if (cs < r && cache_c != bidx) load_row(bidx, __shfl_sync(0xffffffffu, my_id, ln));
+            }
+            fresh = false;
+          }
+          const int need = r - cs;  // picks the nominee has not seen (0: exact)
+          if (need > 0) {
 #pragma unroll
             for (int j = 0; j < NV; ++j) {
               const int c4 = (int)lane + 32 * j;
               if (c4 < nvec) reinterpret_cast<float4*>(cache)[c4] = e[j];
             }
-            __syncwarp();
-            const float4* cr = reinterpret_cast<const float4*>(cache);
-            for (int t0 = cs; t0 < r; t0 += 32) {
-              const int t = min(t0 + (int)lane, r - 1);  // surplus lanes repeat the last pick (no effect on the maximum)
-              const float4* pr = reinterpret_cast<const float4*>(picks + (size_t)t * ds);
-              float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll 8
-              for (int x = 0; x < nvec; ++x) {
-                const float4 a = cr[x], b = pr[x];
-                s0 = fmaf(a.x, b.x, s0); s1 = fmaf(a.y, b.y, s1); s2 = fmaf(a.z, b.z, s2); s3 = fmaf(a.w, b.w, s3);
-              }
-              mraw = fmaxf(mraw, (s0 + s1) + (s2 + s3));
-            }
-            mraw = warp_max(mraw);
-          } else {
-            int t = cs;
-            for (; t + 1 < r; t += 2) {  // two picks per iteration: independent shuffle chains
-              const float4* pa = reinterpret_cast<const float4*>(picks + (size_t)t * ds);
-              const float4* pb = pa + (ds >> 2);
-              float sa = 0.f, sb = 0.f;
-#pragma unroll
-              for (int j = 0; j < NV; ++j) {
-                const int c4 = (int)lane + 32 * j;
-                if (c4 < nvec) {
-                  const float4 x = pa[c4], y = pb[c4];
-                  sa = fmaf(e[j].x, x.x, sa); sa = fmaf(e[j].y, x.y, sa); sa = fmaf(e[j].z, x.z, sa); sa = fmaf(e[j].w, x.w, sa);
-                  sb = fmaf(e[j].x, y.x, sb); sb = fmaf(e[j].y, y.y, sb); sb = fmaf(e[j].z, y.z, sb); sb = fmaf(e[j].w, y.w, sb);
-                }
-              }
-#pragma unroll
-              for (int o = 16; o > 0; o >>= 1) { sa += __shfl_xor_sync(0xffffffffu, sa, o); sb += __shfl_xor_sync(0xffffffffu, sb, o); }
-              mraw = fmaxf(mraw, fmaxf(sa, sb));
-            }
-            if (t < r) {
-              const float4* pa = reinterpret_cast<const float4*>(picks + (size_t)t * ds);
-              float sa = 0.f;
-#pragma unroll
-              for (int j = 0; j < NV; ++j) {
-                const int c4 = (int)lane + 32 * j;
-                if (c4 < nvec) {
-                  const float4 x = pa[c4];
-                  sa = fmaf(e[j].x, x.x, sa); sa = fmaf(e[j].y, x.y, sa); sa = fmaf(e[j].z, x.z, sa); sa = fmaf(e[j].w, x.w, sa);
-                }
-              }
-              mraw = fmaxf(mraw, warp_sum(sa));
-            }
           }
-          const float mnew = mraw / cache_nrm;
-          const float m = cs == 0 ? mnew : fmaxf(m_old, mnew);
-          if ((int)lane == ln) {
+          if (lane == 0) { rq_need[w] = need; rq_cs[w] = cs; rq_max[w] = 0u; ch_obj[w] = best; ch_idx[w] = bidx; }
+          __syncthreads();
+          int pre[LW + 1];
+          pre[0] = 0;
 #pragma unroll
-            for (int s = 0; s < S; ++s) if (s == slot) { ms[s] = m; seen[s] = r; }
+          for (int i = 0; i < LW; ++i) pre[i + 1] = pre[i] + rq_need[i];
+          const int tot = pre[LW];
+          if (tot == 0) break;  // every nominee is exact (block-uniform)
+          for (int T = threadIdx.x; T < tot; T += LW * 32) {
+            int q = 0, base = 0;
+#pragma unroll
+            for (int i = 1; i < LW; ++i) { if (T >= pre[i]) { q = i; base = pre[i]; } }
+            const int t = rq_cs[q] + (T - base);
+            const float4* pr = reinterpret_cast<const float4*>(picks + (size_t)t * ds);
+            const float4* cr = reinterpret_cast<const float4*>(dyn + (size_t)k * ds + (size_t)q * d);
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll 8
+            for (int x = 0; x < nvec; ++x) {
+              const float4 a4 = cr[x], b4 = pr[x];
+              s0 = fmaf(a4.x, b4.x, s0); s1 = fmaf(a4.y, b4.y, s1); s2 = fmaf(a4.z, b4.z, s2); s3 = fmaf(a4.w, b4.w, s3);
+            }
+            const float dot = (s0 + s1) + (s2 + s3);
+            atomicMax(&rq_max[q], f32_to_key(__float_as_uint(dot + 0.0f)));
+          }
+          __syncthreads();
+          if (need > 0) {
+            const float mnew = __uint_as_float(key_to_f32(rq_max[w])) / cache_nrm;
+            const float m = cs == 0 ? mnew : fmaxf(m_old, mnew);
+            if ((int)lane == ln) {
+#pragma unroll
+              for (int s = 0; s < S; ++s) if (s == slot) { ms[s] = m; seen[s] = r; }
+            }
+            // bound unchanged: the nominee is still this warp's top candidate, now exact; otherwise nominate again
+            fresh = !(cs != 0 && m == m_old);
+            cs = r;
           }
         }
-        if (lane == 0) { ch_obj[w] = best; ch_idx[w] = bidx; }
-        __syncthreads();
         best = ch_obj[0]; bidx = ch_idx[0];
 #pragma unroll
         for (int i = 1; i < LW; ++i) {
@@ -348,8 +332,9 @@ mmr_lazy_kernel(const MmrParams p) {
       if (j != 0x7fffffff && (j & (LW - 1)) == w) {
         const int slot = (j / LW) >> 5, ln = (j / LW) & 31;
         int my_id = -1;
+        float my_sc = -INFINITY;
 #pragma unroll
-        for (int s = 0; s < S; ++s) if (s == slot) my_id = id[s];
+        for (int s = 0; s < S; ++s) if (s == slot) { my_id = id[s]; my_sc = sc[s]; }
         const int item = __shfl_sync(0xffffffffu, my_id, ln);
         if (item >= 0 && cache_c != j) load_row(j, item);
 #pragma unroll
@@ -364,8 +349,9 @@ mmr_lazy_kernel(const MmrParams p) {
         if ((int)lane == ln) {
 #pragma unroll
           for (int s = 0; s < S; ++s) if (s == slot) id[s] = -1;  // picked: no longer a candidate
-          p.out_items[u * k + r] = p.cand_items[u * C + j];
-          if (p.out_scores) p.out_scores[u * k + r] = p.cand_scores[u * C + j];
+          // outputs straight from the registers (a dependent global load here would sit on every step's critical path)
+          p.out_items[u * k + r] = my_id >= 0 ? (int64_t)my_id : p.cand_items[u * C + j];
+          if (p.out_scores) p.out_scores[u * k + r] = my_id >= 0 ? my_sc : p.cand_scores[u * C + j];
         }
       }
       __syncthreads();
@@ -404,7 +390,7 @@ cudaError_t launch_mmr(MmrParams p, cudaStream_t stream) {
   const size_t lazy_smem = ((size_t)p.k * (size_t)(p.d + 4) + (size_t)LW * p.d) * sizeof(float);
   if ((p.d & 3) == 0 && p.d <= 512 && p.C <= 1024 && lazy_smem <= 200 * 1024 && p.nI < ((int64_t)1 << 31) &&
       !getenv("DIVREC_DEBUG_MMR_EAGER")) {
-    int per_sm = (int)((size_t)232448 / (lazy_smem + 1024 + 128));  // per-SM shared memory / (dynamic + reserved + static)
+    int per_sm = (int)((size_t)232448 / (lazy_smem + 1024 + 160));  // per-SM shared memory / (dynamic + reserved + static)
     if (per_sm > 4) per_sm = 4;
     if (per_sm < 1) per_sm = 1;
     int64_t g = (int64_t)148 * per_sm;
