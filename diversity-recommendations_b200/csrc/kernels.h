@@ -27,10 +27,12 @@ struct FilterParams {
   int use_hint;
   float hint_sigma;  // safety of the sampled threshold hint in standard deviations (set by the launcher)
   int hint_extra;    // extra ranks on top
+  float hint_eps;    // > 0 (large catalogues): exact binomial tail bound on a too-high hint per row, instead of sigma + extra
   int debug_mode;  // 0 = normal; 1 = skip the filter (pipeline timing); 2 = filter without stores
   int cap;      // = LIST_CAP
   // filled by the launcher
   int n_ublocks, n_tiles, b_stages, acc_stages, n_sample, sample_stride;
+  int sample_tpg;   // sample tiles folded into one hint maximum (large catalogues sample more tiles)
   const void* a16;             // [nU, K] 16-bit user plane (read row-wise into TMEM)
   long long* stats;            // [grid][8] MMA-issuer cycles: total, blocked on A, on accumulators, on B; [4] tightening events, [5] their cycles (null = off)
   const int64_t* seen_rowptr;  // [nU+1] or null (only the per-row counts are used here)

@@ -55,6 +55,7 @@ constexpr int NUM_THREADS = (W_ALLOC + 1) * 32;
 constexpr int COLS_PER_THREAD = BN / 2;
 constexpr int GROUPS_PER_TILE = COLS_PER_THREAD / GROUP;  // 8 groups of 8 columns per thread per tile
 constexpr int HS = 2 * N_SAMPLE;   // 32-column group maxima per thread in the hint phase
+constexpr int SAMPLE_ITEMS_PER_TPG = 156250;  // catalogues >= TIGHTEN_MIN_ITEMS sample 16 * ceil(nI / this) tiles (8 per hint maximum at 1.25M items: 1.3 % of the pass)
 
 struct Smem {
   uint64_t b_full[16];
@@ -216,6 +217,7 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmap_b, const FilterPara
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&sm->tmem_base);
 
+  const int TPG = TIGHTEN ? p.sample_tpg : 1;  // sample tiles folded into one hint maximum
   const int kblocks = p.kblocks;
   const int n_sample = p.n_sample;
   const int n_sched = n_sample + p.n_tiles;
@@ -337,23 +339,31 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmap_b, const FilterPara
       // ---------------- phase 1: threshold hint from sampled tiles (set 0 scores them, both sets use the result) ----------------
       if (n_sample > 0) {
         if (pset == 0) {
+          // hs[] = maxima of 32-column groups, each followed through TPG consecutive sample tiles (large catalogues sample
+          // 4x the tiles so that the hint resolves their much smaller quantiles; the number of maxima stays HS)
           float hs[HS];
 #pragma unroll
-          for (int s = 0; s < N_SAMPLE; ++s) {
-            const uint32_t seq = base_seq + s, acc = seq % acc_stages, acc_phase = (seq / acc_stages) & 1;
-            mbar_wait(smem_u32(&sm->acc_full[acc]), acc_phase);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + h * COLS_PER_THREAD;
-            uint32_t v0[32];
-            tmem_ld_32x32b_x32(taddr, v0);
-            tmem_wait_ld();
-            hs[2 * s] = max32(v0);
-            tmem_ld_32x32b_x32(taddr + 32, v0);
-            tmem_wait_ld();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&sm->acc_empty[acc]));
-            hs[2 * s + 1] = max32(v0);
+          for (int sg = 0; sg < N_SAMPLE; ++sg) {
+            float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll 1
+            for (int tt = 0; tt < TPG; ++tt) {
+              const uint32_t seq = base_seq + (uint32_t)(sg * TPG + tt), acc = seq % acc_stages, acc_phase = (seq / acc_stages) & 1;
+              mbar_wait(smem_u32(&sm->acc_full[acc]), acc_phase);
+              tc_fence_after();
+              const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + h * COLS_PER_THREAD;
+              uint32_t v0[32];
+              tmem_ld_32x32b_x32(taddr, v0);
+              tmem_wait_ld();
+              m0 = fmaxf(m0, max32(v0));
+              tmem_ld_32x32b_x32(taddr + 32, v0);
+              tmem_wait_ld();
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(smem_u32(&sm->acc_empty[acc]));
+              m1 = fmaxf(m1, max32(v0));
+            }
+            hs[2 * sg] = m0;
+            hs[2 * sg + 1] = m1;
           }
           // bitonic sort, descending, fully unrolled in registers
 #pragma unroll
@@ -384,9 +394,22 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmap_b, const FilterPara
           const float f0 = ((float)p.k + (float)seen_u + 8.0f) / (float)p.nI;  // needed fraction of the catalogue
           int r = 2 * HS + 1;                                                   // "no hint"
           if (f0 < 0.25f) {
-            const float pg = 1.0f - __expf(32.0f * log1pf(-f0));  // P(a 32-column group maximum is in that fraction)
+            const float pg = 1.0f - __expf((float)(32 * TPG) * log1pf(-f0));  // P(the maximum of a group's 32 TPG sampled scores is in that fraction)
             const float n = (float)(2 * HS);
-            r = (int)ceilf(n * pg + p.hint_sigma * sqrtf(n * pg * (1.0f - pg))) + p.hint_extra;
+            if (TIGHTEN && p.hint_eps > 0.0f) {
+              // exact binomial tail (the normal approximation is far off when n pg < 1: "5 sigma" at n pg = 0.7 is a 1e-5
+              // tail, and an uncertified row of a multi-million-item catalogue costs hundreds of ms in the exact kernel):
+              // smallest r past the mode with P(Bin(n, pg) >= r) <= pmf(r) / (1 - ratio_r) <= eps
+              const float qq = pg / (1.0f - pg);
+              float pmf = __expf(n * log1pf(-pg));
+              for (int j = 0; j <= 2 * HS; ++j) {
+                const float ratio = (n - (float)j) / ((float)j + 1.0f) * qq;  // pmf(j + 1) / pmf(j), decreasing in j
+                if ((float)j > n * pg && ratio < 0.5f && pmf <= p.hint_eps * (1.0f - ratio)) { r = j; break; }
+                pmf *= ratio;
+              }
+            } else {
+              r = (int)ceilf(n * pg + p.hint_sigma * sqrtf(n * pg * (1.0f - pg))) + p.hint_extra;
+            }
           }
           if (r <= 2 * HS - 4) {
             const int ea = row_local, eb = row_local + 128;  // the row's two column halves in `sorted`
@@ -559,15 +582,27 @@ cudaError_t launch_score_filter(const void* A16, const void* B16, FilterParams p
   p.n_tiles = (p.nI + BN - 1) / BN;
   p.b_stages = score_filter_b_stages(p.kblocks);
   p.acc_stages = (TMEM_COLS - K / 2) / BN;
-  // Large catalogues: 2048 sampled scores cannot resolve a 1e-5 quantile, so the hint only trims the warm-up of the
-  // online tightening (measured on a 1.25M-item shard: starting from thr = -inf appends ~11k groups per row and the
-  // stores are 55 % of the kernel).  An uncertified row would cost an exact pass over millions of items there, so the
-  // hint is taken 5 sigma (+2 ranks) on the safe side instead of 3 (+1): ~1e-6 failures per row.
+  // Large catalogues: an uncertified row costs an exact pass over millions of items (measured: 522 ms for ONE row of a
+  // 10M-item catalogue), so the hint's failure probability is bounded by the exact binomial tail (hint_eps per row;
+  // the kernel's "sigma" rule is a normal approximation, fine for the common shape where n pg ~ 17 and a failed row is
+  // cheap, but a 1e-5 tail at n pg < 1), and more tiles are sampled (below) so that such a safe hint is still tight.
+  p.hint_eps = p.nI >= TIGHTEN_MIN_ITEMS ? 1.0e-9f : 0.0f;  // per-row probability that the sampled hint is too high
   p.hint_sigma = p.nI >= TIGHTEN_MIN_ITEMS ? 5.0f : 3.0f;
   p.hint_extra = p.nI >= TIGHTEN_MIN_ITEMS ? 2 : 1;
+  const bool tighten = p.nI >= TIGHTEN_MIN_ITEMS && !getenv("DIVREC_DEBUG_NO_TIGHTEN");
   if (p.use_hint && p.n_tiles >= HINT_MIN_TILES) {
-    p.n_sample = N_SAMPLE;
-    p.sample_stride = (p.n_tiles - 1) / N_SAMPLE;  // sample tiles are full tiles (never the ragged last one)
+    // large catalogues: the number of sample tiles grows with the catalogue (1.3 % of the pass), so that the hint -- the
+    // r-th largest of 64 group maxima with a 1e-9 exact binomial tail -- sits where ~1200 groups per row pass it whatever
+    // the size (1.25M-item shard with 16 tiles: ~3000 groups and 1395 tightenings per CTA, filter 52.1 ms; with the hint
+    // at ~1000 groups: 67 tightenings, 39.6 ms -- each tightening stalls the CTA's accumulator ring for ~25k cycles)
+    p.sample_tpg = 1;
+    if (tighten) {
+      p.sample_tpg = (int)((p.nI + SAMPLE_ITEMS_PER_TPG - 1) / SAMPLE_ITEMS_PER_TPG);
+      if (p.sample_tpg > 64) p.sample_tpg = 64;
+      while (p.sample_tpg > 1 && N_SAMPLE * p.sample_tpg > (p.n_tiles - 1) / 2) --p.sample_tpg;
+    }
+    p.n_sample = N_SAMPLE * p.sample_tpg;
+    p.sample_stride = (p.n_tiles - 1) / p.n_sample;  // sample tiles are full tiles (never the ragged last one)
   } else {
     p.n_sample = 0;
     p.sample_stride = 1;
@@ -576,7 +611,7 @@ cudaError_t launch_score_filter(const void* A16, const void* B16, FilterParams p
   int grid = p.n_ublocks < sm_count ? p.n_ublocks : sm_count;
   if (const char* g = getenv("DIVREC_DEBUG_FILTER_GRID")) { const int v = atoi(g); if (v > 0 && v < grid) grid = v; }  // measurement aid
   cudaError_t e;
-  if (p.nI >= TIGHTEN_MIN_ITEMS && !getenv("DIVREC_DEBUG_NO_TIGHTEN")) {
+  if (tighten) {
     e = cudaFuncSetAttribute(score_filter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     score_filter_kernel<true><<<grid, NUM_THREADS, smem, stream>>>(tb, p);
