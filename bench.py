@@ -11,8 +11,9 @@ sharded); the only collectives are the metric reductions (coverage histogram + I
 
 One JSON line on stdout (rank 0).  `value` = users/s with inputs resident in HBM; `e2e` = the same
 through the reference-facing Python API with HOST buffers (pinned), host<->device copies inside the
-timed region; `roofline` = the dominant kernel (tcgen05 score + filter) against the measured bf16
-tensor peak; `cpu_baseline` = the CPU oracle port timed on this box's host cores on a bounded sample.
+timed region; `roofline` = the dominant kernel by time (selection: mask + exact top-k + ILD gather) against the
+measured HBM bandwidth, `roofline_filter` = the tcgen05 score + filter kernel against the measured bf16 tensor peak;
+`cpu_baseline` = the CPU oracle port timed on this box's host cores on a bounded sample.
 
 `--impl reference` times the reference's CPU algorithm (oracle port, all host threads) on a bounded
 sample of the same workload; under torchrun only rank 0 works.
@@ -38,8 +39,8 @@ WORKLOADS = {
 }
 METRIC = "users/sec scored (score+top-k+ILD)"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch at cfg2, from the committed ncu --set full capture
-# (profiles/r01_ncu_filter_select_v5.txt); bench.py cannot run ncu itself
-NCU_DRAM_TRAFFIC_CFG2 = {"score_filter_kernel": 0.171565e9 + 2.365629e9, "select_topk_kernel": 2.551790e9 + 0.166450e9}
+# (profiles/r01_ncu_filter_select_v6.txt); bench.py cannot run ncu itself
+NCU_DRAM_TRAFFIC_CFG2 = {"score_filter2_kernel": 0.109167e9 + 2.306356e9, "select_topk_kernel": 2.518991e9 + 0.165455e9}
 
 
 def peaks():
@@ -232,12 +233,15 @@ def bench_ours(args):
         "e2e": {"value": e2e_value, "unit": "users/s", "h2d_bytes_per_step": res["h2d_bytes"], "d2h_bytes_per_step": res["d2h_bytes"],
                 "api": "divrec.train.host_recommend_and_score (pinned host buffers -> C ABI -> host results)"},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                     "traffic": NCU_DRAM_TRAFFIC_CFG2["score_filter_kernel"] if args.workload == "cfg2" else None,
-                     "kernel": "score_filter_kernel", "kernel_ms": kms,
-                     "algorithmic_flop_per_launch": flop, "peak_source": pk["source"] + " bf16 sustained (kernel timed inside a long step)"},
-        # the selection kernel is the other large share of the step (ncu launch list: profiles/r01_ncu_launches_v5.txt)
-        "roofline_select": select_roofline(phases, nU, d, k, pk, args.workload),
+        # the dominant kernel by time (ncu launch list profiles/r01_ncu_launches_v6.txt: 59 % of the step) is the selection
+        # kernel (mask + exact top-k + ILD gather + coverage): HBM/gather-bound stage S2+S3 of SURVEY.md 8d
+        "roofline": select_roofline(phases, nU, d, k, pk, args.workload, float(items.numel()) / nU, ms_per_step),
+        # the tcgen05 score + filter kernel (36 % of the step) against the measured tensor peak
+        "roofline_filter": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                            "traffic": NCU_DRAM_TRAFFIC_CFG2["score_filter2_kernel"] if args.workload == "cfg2" else None,
+                            "kernel": "score_filter2_kernel" if d <= 128 else "score_filter_kernel", "kernel_ms": kms,
+                            "share_of_step": kms / ms_per_step, "algorithmic_flop_per_launch": flop,
+                            "peak_source": pk["source"] + " bf16 sustained (kernel timed inside a long step)"},
         "cpu_baseline": cpu,
         "phases_ms": {name: sorted(ph[name] for ph in phases)[len(phases) // 2] for name in phases[0]},
         "rescued_rows_per_step": stats["rescued_rows"],
@@ -470,7 +474,8 @@ def bench_cfg3(args):
                         "d2h_bytes_per_step": 4, "api": "divrec._native.bpr_step (triples from pinned host memory, loss back)"},
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
-                             "traffic": None, "kernel": "bpr_step_kernel", "kernel_ms": kms,
+                             "traffic": (194.578176e6 + 47.259392e6) if B == 65536 else None,  # ncu --set full, profiles/r01_ncu_bpr_step.txt
+                             "kernel": "bpr_step_kernel", "kernel_ms": kms,
                              "algorithmic_bytes_per_launch": B * bytes_per_triple, "peak_source": pk["source"] + " copy bandwidth"},
                 "cpu_baseline": None}
         print(json.dumps(line))
@@ -570,17 +575,20 @@ def bench_cfg5(args):
         dist.destroy_process_group()
 
 
-def select_roofline(phases, nU, d, k, pk, workload):
-    """HBM view of select_topk_kernel: candidate groups (~490 x 36 B per user at cfg2) + k row gathers + outputs."""
+def select_roofline(phases, nU, d, k, pk, workload, avg_seen, ms_per_step):
+    """HBM view of select_topk_kernel with the ALGORITHMIC bytes of its stage (SURVEY.md 8d, S2 + S3 and the top-k side
+    traffic of S1): per user the k item rows gathered for the exact scores and the cosine ILD (k (8 + 4 d) + 4), the
+    top-k outputs (12 k), the seen list (4 seen_u + 8).  The candidate groups handed over by the filter are this
+    implementation's own intermediate data and are NOT counted; `traffic` is the measured DRAM traffic (the 13.7 MB item
+    table is L2-resident, so the row gathers are mostly L2 hits)."""
     ms = sorted(ph["select_ms"] for ph in phases)[len(phases) // 2]
-    groups = 490 if workload == "cfg2" else None
-    if groups is None:
-        return {"kernel": "select_topk_kernel", "kernel_ms": ms}
-    algo = nU * (groups * 36 + k * d * 4 + k * 12 + 4)
+    algo = nU * (k * (8 + 4 * d) + 4 + 12 * k + 4 * avg_seen + 8)
     ach = algo / (ms * 1e-3) / 1e9
     return {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
-            "traffic": NCU_DRAM_TRAFFIC_CFG2["select_topk_kernel"], "kernel": "select_topk_kernel", "kernel_ms": ms,
-            "algorithmic_bytes_per_launch": algo, "note": "issue-bound, not bandwidth-bound (ncu: issue slots 58 % busy, row gathers hit L2)"}
+            "traffic": NCU_DRAM_TRAFFIC_CFG2["select_topk_kernel"] if workload == "cfg2" else None,
+            "kernel": "select_topk_kernel", "kernel_ms": ms, "share_of_step": ms / ms_per_step,
+            "algorithmic_bytes_per_launch": algo, "peak_source": pk["source"] + " copy bandwidth",
+            "note": "issue-bound rather than bandwidth-bound (ncu: issue slots 60 % busy, 2.36 inst/cycle/SM; row gathers hit L2)"}
 
 
 def cpu_baseline(workload, sample_users):
