@@ -94,23 +94,30 @@ def recommend_item_sharded(U: torch.Tensor, V_shard: torch.Tensor, shard_offset:
 
 
 def bpr_step_sharded(U: torch.Tensor, V: torch.Tensor, u: torch.Tensor, p: torch.Tensor, n: torch.Tensor,
-                     global_batch: int, group=None, kernels=None, item_grad: str = "auto"):
+                     global_batch: int, group=None, kernels=None, item_grad: str = "dense"):
     """One BPR forward/backward on this rank's triples (its users only).  Gradients are those of the GLOBAL
     mean loss: every rank scales by 1 / global_batch, the item-table gradient is summed over ranks, the user
     gradient needs no communication because a user's triples live on one rank.
 
-    item_grad: "dense" all-reduces the [nI, d] item gradient (BASELINE.json config 3 as stated); "sparse"
-    all-gathers the per-triple rows g_b U[u_b] with their (positive, negative) ids and every rank scatter-adds all of
-    them -- the same dense result on every rank for world * B * (d + 4) * 4 gathered bytes instead of the ring
-    all-reduce's 2 nI d 4; "auto" picks sparse when the gathered rows are at most half of that (needs equal batch
-    sizes on all ranks).
+    item_grad: "dense" (default) all-reduces the [nI, d] item gradient (BASELINE.json config 3 as stated).
+    "sparse" all-gathers the per-triple rows g_b U[u_b] with their (positive, negative) ids and every rank
+    scatter-adds all of them -- the same dense result on every rank for world * B * (d + 4) * 4 gathered bytes instead
+    of the ring all-reduce's 2 nI d 4; the caller guarantees EQUAL batch sizes on all ranks (no check, no host sync).
+    "auto" agrees on the batch sizes first (one tiny all-reduce and a host sync per call) and takes the sparse route
+    when they are equal and the gathered rows are at most half the all-reduce volume.
     Returns (loss_global, auc_global, gU_local_rows_dense, gV_global)."""
     K = _kernels(kernels)
     rank, world = _world(group)
     B, d = u.numel(), U.shape[1]
     sparse = False
     if world > 1 and item_grad != "dense" and hasattr(K, "bpr_apply_rows"):
-        sparse = item_grad == "sparse" or world * B * (d + 4) * 4 <= V.shape[0] * d * 4
+        if item_grad == "sparse":
+            sparse = True
+        else:
+            mm = torch.tensor([B, -B], dtype=torch.int64, device=U.device)
+            dist.all_reduce(mm, op=dist.ReduceOp.MAX, group=group)
+            bmax, bmin = int(mm[0]), -int(mm[1])
+            sparse = bmax == bmin and world * B * (d + 4) * 4 <= V.shape[0] * d * 4
     gU, gV = torch.zeros_like(U), torch.zeros_like(V)
     if sparse:
         rows = torch.empty((B, d), dtype=torch.float32, device=U.device)

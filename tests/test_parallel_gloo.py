@@ -145,6 +145,11 @@ def _worker(rank, world, port, out):
     torch.testing.assert_close(gU_s[a:b], o_gU[a:b], rtol=0, atol=1e-6 * float(o_gU.abs().max()))
     loss_d, _, _, gV_d = parallel.bpr_step_sharded(Ug, Vg, u[me], p[me], n[me], world * m, kernels=K, item_grad="dense")
     torch.testing.assert_close(gV_d, gV_s, rtol=0, atol=1e-6 * float(o_gV.abs().max()))
+    # "auto": equal batches and a small volume -> sparse; unequal batches (the first call's split) -> dense, no mismatch
+    _, _, _, gV_a = parallel.bpr_step_sharded(Ug, Vg, u[me], p[me], n[me], world * m, kernels=K, item_grad="auto")
+    torch.testing.assert_close(gV_a, gV_s, rtol=0, atol=1e-6 * float(o_gV.abs().max()))
+    _, _, _, gV_u = parallel.bpr_step_sharded(Ug, Vg, u[mine], p[mine], n[mine], B, kernels=K, item_grad="auto")
+    torch.testing.assert_close(gV_u, gV, rtol=0, atol=1e-6 * float(gV.abs().max()))
     dist.barrier()
     dist.destroy_process_group()
     out.put(rank)
