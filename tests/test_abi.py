@@ -53,6 +53,10 @@ def test_version_and_errors_without_gpu(native):
     assert lib.divrec_coverage_hist(None, 10, 10, None, None) == -1
     assert lib.divrec_ild_cosine(None, 10, 8, 0, None, 1, 4, 0, None, None, None) == -1
     assert lib.divrec_bpr_fwd(None, None, None, None, None, 4, 8, None, None, None, None, None) == -1
+    assert lib.divrec_bpr_step(None, None, None, None, None, 4, 8, 0.25, None, None, None, None, None, None, None, None) == -1
+    assert lib.divrec_bpr_apply_rows(None, None, None, 4, 8, None, None) == -1
+    assert lib.divrec_topk_pack(None, None, 10, None, None) == -1
+    assert lib.divrec_topk_merge_packed(None, 2, 10, 5, None, None, None) == -1
     assert lib.divrec_score_topk_workspace(0, 10, 8, 0, 4) == 0
     assert lib.divrec_score_topk_workspace(1000, 5000, 128, 0, 100) > 0
 
