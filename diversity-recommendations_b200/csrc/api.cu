@@ -442,6 +442,18 @@ int divrec_bpr_step(const float* U, const float* V, const int64_t* u, const int6
   return DIVREC_OK;
 }
 
+int divrec_bpr_sample_triples(const int64_t* pos_rowptr, const int32_t* pos_items, const int64_t* excl_rowptr,
+                              const int32_t* excl_items, int64_t nU, int64_t nI, int max_sampled, uint64_t seed,
+                              int64_t* out_u, int64_t* out_p, int64_t* out_n, void* stream) {
+  if (!pos_rowptr || !excl_rowptr || !out_u || !out_p || !out_n) return fail(DIVREC_ERR_ARG, "bpr_sample_triples: null pointer");
+  if (nU <= 0 || nI <= 0) return fail(DIVREC_ERR_ARG, "bpr_sample_triples: nU, nI must be positive");
+  if (max_sampled <= 0 || max_sampled > 256) return fail(DIVREC_ERR_ARG, "bpr_sample_triples: max_sampled must be in [1, 256]");
+  cudaError_t e = launch_bpr_sample(pos_rowptr, pos_items, excl_rowptr, excl_items, nU, nI, max_sampled, seed, out_u, out_p,
+                                    out_n, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "bpr_sample_triples launch");
+  return DIVREC_OK;
+}
+
 int divrec_bpr_apply_rows(const float* rows, const int64_t* p, const int64_t* n, int64_t N, int d, float* gV, void* stream) {
   if (!rows || !p || !n || !gV) return fail(DIVREC_ERR_ARG, "bpr_apply_rows: null pointer");
   if (N <= 0) return fail(DIVREC_ERR_ARG, "bpr_apply_rows: N must be positive");

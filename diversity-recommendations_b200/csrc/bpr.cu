@@ -249,6 +249,69 @@ bpr_loss_bwd_kernel(const float* __restrict__ pos, const float* __restrict__ neg
   }
 }
 
+// ---- device-side BPR triple sampler ----------------------------------------------------------
+// Replaces PairWiseDataset.__iter__ (divrec/datasets/base_datasets.py:70-107): per user, max_sampled positives drawn
+// with replacement from the user's items and max_sampled negatives drawn with replacement from
+// items - positives - frozen (random.choices, :88-90), then the cross product in the reference's order (positive-major,
+// :92-107).  The reference scans all interactions per user (O(U nnz)) and builds Python sets; here both item sets come
+// as CSR rows (sorted, unique).  Draws are counter-based (splitmix64 of seed, user, draw index): reproducible for a seed,
+// not bit-compatible with CPython's Mersenne twister -- parity is distributional.  A negative is drawn WITHOUT
+// rejection: r uniform in [0, nI - n_excl), the r-th item not in the exclusion list is r + t with t the smallest index
+// such that excl[t] - t > r (binary search).  Users without a positive or without a negative get (-1, -1, -1) rows
+// (the reference raises IndexError there).
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+__device__ __forceinline__ long long uniform_below(unsigned long long h, long long n) {
+  return (long long)__umul64hi(h, (unsigned long long)n);  // floor(h n / 2^64)
+}
+
+__global__ void __launch_bounds__(256)
+bpr_sample_kernel(const int64_t* __restrict__ pos_rowptr, const int32_t* __restrict__ pos_items,
+                  const int64_t* __restrict__ excl_rowptr, const int32_t* __restrict__ excl_items, int64_t nU, int64_t nI,
+                  int m, unsigned long long seed, int64_t* __restrict__ out_u, int64_t* __restrict__ out_p,
+                  int64_t* __restrict__ out_n) {
+  extern __shared__ int64_t samp[];  // per warp: [m] positives | [m] negatives
+  const uint32_t lane = lane_id();
+  const int warp = threadIdx.x >> 5;
+  int64_t* sp = samp + (size_t)warp * 2 * m;
+  int64_t* sn = sp + m;
+  for (int64_t u = (int64_t)blockIdx.x * 8 + warp; u < nU; u += (int64_t)gridDim.x * 8) {
+    const int64_t p0 = pos_rowptr[u], np = pos_rowptr[u + 1] - p0;
+    const int64_t e0 = excl_rowptr[u], ne = excl_rowptr[u + 1] - e0;
+    const int64_t nneg = nI - ne;
+    const bool ok = np > 0 && nneg > 0;
+    for (int j = lane; j < m; j += 32) {
+      int64_t pj = -1, nj = -1;
+      if (ok) {
+        const unsigned long long base = splitmix64(seed ^ splitmix64((unsigned long long)u));
+        pj = (int64_t)pos_items[p0 + uniform_below(splitmix64(base + 2ull * j), np)];
+        const int64_t r = uniform_below(splitmix64(base + 2ull * j + 1ull), nneg);
+        int64_t lo = 0, hi = ne;  // smallest t in [0, ne] with excl[t] - t > r (t = ne: none)
+        while (lo < hi) {
+          const int64_t mid = (lo + hi) >> 1;
+          if ((int64_t)excl_items[e0 + mid] - mid > r) hi = mid; else lo = mid + 1;
+        }
+        nj = r + lo;
+      }
+      sp[j] = pj;
+      sn[j] = nj;
+    }
+    __syncwarp();
+    const int64_t out0 = u * (int64_t)m * m;
+    for (int t = lane; t < m * m; t += 32) {
+      const int a = t / m, b = t - a * m;
+      out_u[out0 + t] = ok ? u : -1;
+      out_p[out0 + t] = sp[a];
+      out_n[out0 + t] = sn[b];
+    }
+    __syncwarp();
+  }
+}
+
 inline unsigned warp_grid(int64_t items) {
   int64_t g = (items + 7) / 8;
   if (g > 148 * 16) g = 148 * 16;
@@ -284,6 +347,18 @@ cudaError_t launch_bpr_step(const float* U, const float* V, const int64_t* u, co
   else if (d <= 256) bpr_step_kernel<2><<<(unsigned)g, 256, 0, stream>>>(U, V, u, p, n, B, d, grad_scale, pos, neg, loss_sum, auc_sum, gU, gV, item_rows);
   else if (d <= 512) bpr_step_kernel<4><<<(unsigned)g, 256, 0, stream>>>(U, V, u, p, n, B, d, grad_scale, pos, neg, loss_sum, auc_sum, gU, gV, item_rows);
   else bpr_step_kernel<8><<<(unsigned)g, 256, 0, stream>>>(U, V, u, p, n, B, d, grad_scale, pos, neg, loss_sum, auc_sum, gU, gV, item_rows);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_bpr_sample(const int64_t* pos_rowptr, const int32_t* pos_items, const int64_t* excl_rowptr,
+                              const int32_t* excl_items, int64_t nU, int64_t nI, int m, uint64_t seed, int64_t* out_u,
+                              int64_t* out_p, int64_t* out_n, cudaStream_t stream) {
+  const size_t smem = (size_t)8 * 2 * m * sizeof(int64_t);
+  int64_t g = (nU + 7) / 8;
+  if (g > 148 * 8) g = 148 * 8;
+  bpr_sample_kernel<<<(unsigned)g, 256, smem, stream>>>(pos_rowptr, pos_items, excl_rowptr, excl_items, nU, nI, m,
+                                                        (unsigned long long)seed, out_u, out_p, out_n);
   count_launch();
   return cudaGetLastError();
 }

@@ -48,6 +48,7 @@ SIGNATURES = {
     "divrec_bpr_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _i64, _i32, _vp, _vp, _vp]),
     "divrec_bpr_step": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "divrec_bpr_apply_rows": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _vp]),
+    "divrec_bpr_sample_triples": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _c.c_uint64, _vp, _vp, _vp, _vp]),
     "divrec_pair_scores": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp]),
     "divrec_pair_scores_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp]),
     "divrec_ild_labels": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _vp]),
@@ -406,6 +407,29 @@ def bpr_apply_rows(rows: torch.Tensor, p: torch.Tensor, n: torch.Tensor, gV: tor
     with torch.cuda.device(rows.device):
         rc = lib.divrec_bpr_apply_rows(_ptr(rows), _ptr(p), _ptr(n), N, d, _ptr(gV), _stream(rows.device))
     _check(rc, "divrec_bpr_apply_rows")
+
+
+def bpr_sample_triples(pos_rowptr: torch.Tensor, pos_items: torch.Tensor, excl_rowptr: torch.Tensor, excl_items: torch.Tensor,
+                       n_items: int, max_sampled: int, seed: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """PairWiseDataset's sampler on the device: (user, positive, negative) int64 [nU * max_sampled^2] in the
+    reference's iteration order; rows of users without a positive or a negative are (-1, -1, -1)."""
+    lib = load_library()
+    pos_rowptr = _cuda(pos_rowptr, "pos_rowptr", torch.int64)
+    excl_rowptr = _cuda(excl_rowptr, "excl_rowptr", torch.int64)
+    nU = pos_rowptr.numel() - 1
+    if excl_rowptr.numel() != nU + 1:
+        raise ValueError("pos_rowptr and excl_rowptr must have the same length")
+    pos_items = _cuda(pos_items, "pos_items", torch.int32) if pos_items.numel() else pos_items
+    excl_items = _cuda(excl_items, "excl_items", torch.int32) if excl_items.numel() else excl_items
+    n = nU * max_sampled * max_sampled
+    dev = pos_rowptr.device
+    out = [torch.empty(n, dtype=torch.int64, device=dev) for _ in range(3)]
+    with torch.cuda.device(dev):
+        rc = lib.divrec_bpr_sample_triples(_ptr(pos_rowptr), _ptr(pos_items) if pos_items.numel() else None, _ptr(excl_rowptr),
+                                           _ptr(excl_items) if excl_items.numel() else None, nU, int(n_items), int(max_sampled),
+                                           int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _stream(dev))
+    _check(rc, "divrec_bpr_sample_triples")
+    return out[0], out[1], out[2]
 
 
 def bpr_bwd(U, V, u, p, n, pos, neg, grad_scale: float, gU: torch.Tensor, gV: torch.Tensor, g: Optional[torch.Tensor] = None):

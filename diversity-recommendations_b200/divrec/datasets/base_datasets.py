@@ -57,13 +57,36 @@ class PointWiseDataset(Dataset):
 
 class PairWiseDataset(IterableDataset):
     """BPR triple sampler: per user, max_sampled positives x max_sampled negatives drawn with
-    replacement (reference: base_datasets.py:70-107).  Host-side Python, as in the reference."""
+    replacement (reference: base_datasets.py:70-107).  `__iter__` is host-side Python, as in the reference;
+    `sample_triples` draws the same thing for every user at once on the GPU (divrec_bpr_sample_triples)."""
 
     def __init__(self, data: UserItemInteractionsDataset, frozen: Optional[UserItemInteractionsDataset] = None,
                  max_sampled: int = 100):
         self.data = data
         self.frozen = frozen
         self.max_sampled = max_sampled
+        self._csr = {}
+
+    def sample_triples(self, device, seed: int = 0):
+        """One pass of `__iter__` as three int64 tensors (user, positive, negative) on `device`, in the reference's
+        iteration order (user-major, positive-major): max_sampled^2 triples per user, sampled with replacement from
+        the user's positives and from items - positives - frozen.  Users without a positive or a negative are dropped
+        (the reference raises IndexError on them).  Deterministic for a seed; not CPython's random stream."""
+        from .. import _native
+        if not (0 < self.max_sampled <= 256):
+            raise ValueError("sample_triples needs 0 < max_sampled <= 256")
+        key = str(device)
+        if key not in self._csr:
+            n_users = int(self.data.number_of_users)
+            pos = self.data.interactions.to(device)
+            excl = pos if self.frozen is None else torch.cat([pos, self.frozen.interactions.to(device)])
+            self._csr[key] = interactions_to_csr(pos, n_users) + interactions_to_csr(excl, n_users)
+        prp, pit, erp, eit = self._csr[key]
+        u, p, n = _native.bpr_sample_triples(prp, pit, erp, eit, int(self.data.number_of_items), self.max_sampled, seed)
+        keep = u >= 0
+        if not bool(keep.all()):
+            u, p, n = u[keep], p[keep], n[keep]
+        return u, p, n
 
     def __iter__(self) -> Iterator[PairWiseRow]:
         everything = frozenset(range(int(self.data.number_of_items)))

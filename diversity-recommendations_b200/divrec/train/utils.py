@@ -191,7 +191,20 @@ def pair_wise_train_loop(dataset: PairWiseDataset, model: RankingModel, loss: Pa
     scores = scores or []
     fused = isinstance(model, MatrixFactorization) and type(loss) is LogSigmoidDifferenceLoss
     n, loss_total, score_totals = 0, 0.0, [0.0] * len(scores)
-    for user_id, pos, neg, user_features, pos_features, neg_features in dataset.loader(**loader_params):
+    # Datasets without features (on which the reference's own loop raises in default_collate) with a MatrixFactorization
+    # model take the device path end to end: triples sampled on the GPU (divrec_bpr_sample_triples), cut into batches in
+    # the reference's iteration order.  Anything else walks the Python sampler through a DataLoader as the reference does.
+    device_sampler = (fused and dev.type == "cuda" and not dataset.data.has_user_features() and not dataset.data.has_item_features()
+                      and 0 < dataset.max_sampled <= 256 and not loader_params.get("shuffle", False))
+    if device_sampler:
+        tu, tp, tn = dataset.sample_triples(dev, seed=int(torch.randint(0, 2 ** 31 - 1, (1,)).item()))
+        bs = int(loader_params.get("batch_size", 1) or 1)
+        batches = ((tu[a:a + bs], tp[a:a + bs], tn[a:a + bs], None, None, None) for a in range(0, tu.numel(), bs))
+        if loader_params.get("drop_last", False):
+            batches = (b for b in batches if b[0].numel() == bs)
+    else:
+        batches = dataset.loader(**loader_params)
+    for user_id, pos, neg, user_features, pos_features, neg_features in batches:
         if fused:  # forward + backward in one pass over the rows
             value, positives, negatives, auc_sum = bpr_train_step(model, user_id, pos, neg)
         else:

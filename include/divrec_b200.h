@@ -197,6 +197,18 @@ int divrec_bpr_step(const float* U, const float* V, const int64_t* u, const int6
                     const int64_t* n, int64_t B, int d, float grad_scale, float* pos, float* neg,
                     float* loss_sum, int32_t* auc_sum, float* gU, float* gV, float* item_rows,
                     void* stream);
+/* BPR triple sampler on the device
+ *   replaces: PairWiseDataset.__iter__, divrec/datasets/base_datasets.py:70-107 -- per user max_sampled positives drawn
+ *             with replacement from the user's items, max_sampled negatives with replacement from
+ *             items - positives - frozen (random.choices, :88-90), cross product positive-major (:92-107).
+ *   pos_* : CSR of the users' positive items; excl_* : CSR of positives + frozen items (the exclusion list of the
+ *   negatives), both sorted and unique per row.  Outputs are [nU * max_sampled^2] in the reference's iteration order;
+ *   users without a positive or without a negative get (-1,-1,-1) rows (the reference raises IndexError).
+ *   Draws are counter-based on (seed, user, draw): reproducible, not bit-compatible with CPython's generator. */
+int divrec_bpr_sample_triples(const int64_t* pos_rowptr, const int32_t* pos_items, const int64_t* excl_rowptr,
+                              const int32_t* excl_items, int64_t nU, int64_t nI, int max_sampled, uint64_t seed,
+                              int64_t* out_u, int64_t* out_p, int64_t* out_n, void* stream);
+
 /* gV[p_j] += rows_j;  gV[n_j] -= rows_j   for j < N (duplicates accumulate) */
 int divrec_bpr_apply_rows(const float* rows, const int64_t* p, const int64_t* n, int64_t N, int d,
                           float* gV, void* stream);

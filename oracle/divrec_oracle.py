@@ -313,6 +313,35 @@ def mmr_rerank(cand_items: torch.Tensor, cand_scores: torch.Tensor, V: torch.Ten
     return out
 
 
+def pairwise_triples(interactions: torch.Tensor, frozen: Optional[torch.Tensor], n_users: int, n_items: int,
+                     max_sampled: int, rng) -> torch.Tensor:
+    """PairWiseDataset.__iter__ (divrec/datasets/base_datasets.py:70-107) restated: per user, the positives are the
+    user's items (a frozenset filled in interaction order, :73-77), the negatives are all items minus the positives
+    minus the user's frozen items (:79-86); max_sampled of each are drawn with replacement by `rng.choices` over the
+    sets' iteration order (:88-90, `rng` = the `random` module or a random.Random), and the cross product is emitted
+    positive-major (:92-107).  Returns int64 [U * max_sampled^2, 3]."""
+    universe = frozenset(range(n_items))
+    users = interactions[:, 0].tolist()
+    its = interactions[:, 1].tolist()
+    f_users = frozen[:, 0].tolist() if frozen is not None else []
+    f_its = frozen[:, 1].tolist() if frozen is not None else []
+    out = []
+    for user in range(n_users):
+        liked = frozenset([i for uu, i in zip(users, its) if uu == user])
+        if frozen is not None:
+            blocked = frozenset([i for uu, i in zip(f_users, f_its) if uu == user])
+            rest = universe - liked - blocked
+        else:
+            rest = universe - liked
+        if max_sampled > 0:
+            liked = rng.choices(list(liked), k=max_sampled)
+            rest = rng.choices(list(rest), k=max_sampled)
+        for a in liked:
+            for b in rest:
+                out.append((user, a, b))
+    return torch.tensor(out, dtype=torch.int64).reshape(-1, 3)
+
+
 # --------------------------------------------------------------------------------------------
 # synthetic inputs (SURVEY.md 8d) -- shared by tests, smoke and bench so oracle and kernels see the same bits
 # --------------------------------------------------------------------------------------------

@@ -452,6 +452,73 @@ def test_bpr_permutation_invariance(native, dev):
         assert (a - b).abs().max().item() <= 1e-6 * float(a.abs().max())
 
 
+def test_device_triple_sampler_structure_and_distribution(native, dev):
+    """divrec_bpr_sample_triples against the sets the reference's sampler draws from (pinned by the golden of the real
+    PairWiseDataset in tests/test_oracle_golden.py): iteration order and cross-product structure exactly, membership
+    exactly, uniformity statistically (the random stream itself cannot match CPython's)."""
+    from divrec.datasets.base_datasets import interactions_to_csr
+    g = load_golden("pairwise_small")
+    nU, nI, m = int(g["n_users"]), int(g["n_items"]), int(g["max_sampled"])
+    inter, frozen = g["interactions"], g["frozen"]
+    prp, pit = interactions_to_csr(inter.to(dev), nU)
+    erp, eit = interactions_to_csr(torch.cat([inter, frozen]).to(dev), nU)
+    pos_sets = [set(inter[inter[:, 0] == u, 1].tolist()) for u in range(nU)]
+    excl_sets = [pos_sets[u] | set(frozen[frozen[:, 0] == u, 1].tolist()) for u in range(nU)]
+    u, p, n = (t.cpu() for t in native.bpr_sample_triples(prp, pit, erp, eit, nI, m, seed=5))
+    assert torch.equal(u, torch.arange(nU).repeat_interleave(m * m))                 # user-major, m^2 triples each
+    P, N = p.view(nU, m, m), n.view(nU, m, m)
+    assert torch.equal(P, P[:, :, :1].expand(-1, -1, m)) and torch.equal(N, N[:, :1, :].expand(-1, m, -1))  # positive-major cross product
+    assert torch.equal(g["triples"][:, 0], u)                                        # same layout as the reference's iteration
+    for uu in range(nU):
+        assert set(P[uu, :, 0].tolist()) <= pos_sets[uu]
+        assert not (set(N[uu, 0, :].tolist()) & excl_sets[uu])
+        assert all(0 <= x < nI for x in N[uu, 0, :].tolist())
+    again = native.bpr_sample_triples(prp, pit, erp, eit, nI, m, seed=5)
+    other = native.bpr_sample_triples(prp, pit, erp, eit, nI, m, seed=6)
+    assert torch.equal(again[1].cpu(), p) and torch.equal(again[2].cpu(), n) and not torch.equal(other[2].cpu(), n)
+    # uniformity over many seeds: every positive / every allowed negative of a user equally often (5 sigma)
+    S = 600
+    pc = torch.zeros((nU, nI)); nc = torch.zeros((nU, nI))
+    for seed in range(S):
+        _, p2, n2 = native.bpr_sample_triples(prp, pit, erp, eit, nI, m, seed=1000 + seed)
+        P2, N2 = p2.view(nU, m, m)[:, :, 0].cpu(), n2.view(nU, m, m)[:, 0, :].cpu()
+        pc.scatter_add_(1, P2, torch.ones_like(P2, dtype=torch.float32))
+        nc.scatter_add_(1, N2, torch.ones_like(N2, dtype=torch.float32))
+    for uu in range(nU):
+        for counts, allowed in ((pc[uu], sorted(pos_sets[uu])), (nc[uu], sorted(set(range(nI)) - excl_sets[uu]))):
+            q = 1.0 / len(allowed)
+            exp, sd = S * m * q, math.sqrt(S * m * q * (1 - q)) + 1e-9
+            got = counts[allowed]
+            assert float(counts.sum()) == S * m and float(got.sum()) == S * m        # nothing outside the allowed set
+            assert float((got - exp).abs().max()) <= 5 * sd + 1
+    # a user without positives, and one who has seen everything, are skipped by the shim (the reference raises)
+    from divrec.datasets import PairWiseDataset, UserItemInteractionsDataset
+    inter2 = torch.cat([inter[inter[:, 0] != 3], torch.stack([torch.full((nI,), 7), torch.arange(nI)], 1)])
+    ds = PairWiseDataset(UserItemInteractionsDataset(interactions=inter2, number_of_users=nU, number_of_items=nI), max_sampled=m)
+    u3, p3, n3 = ds.sample_triples(dev, seed=1)
+    assert u3.numel() == (nU - 2) * m * m and 3 not in u3.tolist() and 7 not in u3.tolist()
+
+
+def test_train_loop_on_the_device_sampler(native, dev):
+    """pair_wise_train_loop on a feature-less dataset (where the reference's own loop raises in default_collate): triples
+    from the device sampler, one-kernel BPR steps, loss falls over a few epochs."""
+    from divrec.datasets import PairWiseDataset, UserItemInteractionsDataset
+    from divrec.losses import LogSigmoidDifferenceLoss
+    from divrec.metrics import AUCScore
+    from divrec.models import MatrixFactorization
+    from divrec.train import pair_wise_train_loop
+    g = load_golden("pairwise_small")
+    nU, nI = int(g["n_users"]), int(g["n_items"])
+    torch.manual_seed(0)
+    data = UserItemInteractionsDataset(interactions=g["interactions"], number_of_users=nU, number_of_items=nI)
+    ds = PairWiseDataset(data, max_sampled=8)
+    model = MatrixFactorization(nU, nI, 16).to(dev)
+    opt = torch.optim.Adam(model.parameters(), lr=0.05)
+    hist = [pair_wise_train_loop(ds, model, LogSigmoidDifferenceLoss(), opt, [AUCScore()], batch_size=64) for _ in range(6)]
+    losses, aucs = [h[0] for h in hist], [h[1][0] for h in hist]
+    assert all(math.isfinite(x) for x in losses) and losses[-1] < losses[0] and aucs[-1] > aucs[0]
+
+
 # ------------------------------------------------------------------------------------------------
 # the reference-facing Python API on top of the C ABI
 # ------------------------------------------------------------------------------------------------

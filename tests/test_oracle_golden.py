@@ -144,3 +144,14 @@ def test_mmr_rerank_properties():
     for u in range(8):
         assert len(set(out[u].tolist())) == 10 and set(out[u].tolist()) <= set(cand[u].tolist())
     assert float(O.ild_cosine(out, V).mean()) >= float(O.ild_cosine(cand[:, :10], V).mean())
+
+
+def test_pairwise_sampler_oracle_replays_the_reference_stream():
+    """The BPR triple sampler's restatement under the same `random.seed` must emit the reference's exact sequence
+    (PairWiseDataset.__iter__, base_datasets.py:70-107) -- this pins the sets, their iteration order and the
+    positive-major cross product that the device sampler is then checked against."""
+    import random
+    g = load_golden("pairwise_small")
+    rng = random.Random(int(g["py_seed"]))
+    got = O.pairwise_triples(g["interactions"], g["frozen"], int(g["n_users"]), int(g["n_items"]), int(g["max_sampled"]), rng)
+    assert torch.equal(got, g["triples"])
