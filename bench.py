@@ -115,6 +115,27 @@ def run_step_device(N, model_U, V, rowptr, items, k, nI, counts):
     return s, i, ild
 
 
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout, but C libraries write there too (NCCL prints its version banner on the
+    first communicator whatever NCCL_DEBUG says on some boxes).  From here on file descriptor 1 points at stderr; the
+    JSON line goes to a private duplicate of the original stdout."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        _JSON_OUT = os.fdopen(saved, "w")
+
+
+def emit(line):
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def _quiet_nccl():
     """NCCL prints its version banner on stdout when NCCL_DEBUG=VERSION/INFO; the contract is ONE JSON line."""
     if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE") and not os.environ.get("DIVREC_KEEP_NCCL_DEBUG"):
@@ -246,7 +267,7 @@ def bench_ours(args):
         "phases_ms": {name: sorted(ph[name] for ph in phases)[len(phases) // 2] for name in phases[0]},
         "rescued_rows_per_step": stats["rescued_rows"],
     }
-    print(json.dumps(line))
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
@@ -344,7 +365,7 @@ def bench_cfg4(args):
                              "frac": ach / pk["bf16_tflops_sustained"], "traffic": None, "kernel": "score_filter_kernel", "kernel_ms": kms,
                              "algorithmic_flop_per_launch": flop, "peak_source": pk["source"] + " bf16 sustained"},
                 "cpu_baseline": None, "phases_ms": phases, "rescued_rows_per_step": stats["rescued_rows"]}
-        print(json.dumps(line))
+        emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
@@ -478,7 +499,7 @@ def bench_cfg3(args):
                              "kernel": "bpr_step_kernel", "kernel_ms": kms,
                              "algorithmic_bytes_per_launch": B * bytes_per_triple, "peak_source": pk["source"] + " copy bandwidth"},
                 "cpu_baseline": None}
-        print(json.dumps(line))
+        emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
@@ -570,7 +591,7 @@ def bench_cfg5(args):
                              "note": "lazy greedy: only candidates whose upper bound can still win are gathered and evaluated, so the kernel "
                                      "moves fewer bytes than the algorithmic figure; the rest is per-step latency (two block barriers per pick)"},
                 "cpu_baseline": None}
-        print(json.dumps(line))
+        emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
@@ -642,7 +663,7 @@ def bench_reference(args):
                        "users_per_step": min(args.cpu_sample, nU), "items": nI, "d": d, "k": k},
             "cpu_baseline": c,
             "e2e": {"value": v, "unit": "users/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():
@@ -661,6 +682,7 @@ def main():
     ap.add_argument("--e2e-chunks", type=int, default=4, help="user ranges the host-buffer pipeline overlaps")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU-baseline leg (profiling runs)")
     args = ap.parse_args()
+    claim_stdout()
     if args.impl == "reference":
         bench_reference(args)
     else:
