@@ -73,7 +73,8 @@ struct WsLayout {
   bool convA, convB;  // operands have to be rewritten into the workspace (fp32 -> fp16, or bf16 padding)
   int64_t chunk;
   int rescue_grid;
-  size_t offA, offB, offNormU, offInvV, offListS, offListI, offCounts, offThr, offFail, offScalars, offRescue, total;
+  size_t offA, offB, offNormU, offInvV, offListS, offListI, offCounts, offThr, offFail, offScalars, offRescue, offHintMask, total;
+  bool two_blocks;
 };
 static WsLayout ws_layout(int64_t nU, int64_t nI, int d, int dtype) {
   WsLayout w{};
@@ -95,6 +96,10 @@ static WsLayout ws_layout(int64_t nU, int64_t nI, int d, int dtype) {
   w.offFail = off; off += align_up(cpad * sizeof(int32_t), 1024);
   w.offScalars = off; off += 1024;  // u32[0..1] amax bits (U,V), i32[2..3] scale exps, u32[4] max item norm, i32[5] fail count
   w.offRescue = off; off += align_up(rescue_scratch_bytes(nI, &w.rescue_grid), 1024);
+  // the common shape (d <= 128, catalogue below the online-tightening threshold) scores two user blocks per CTA and
+  // takes its hint on unmasked sample maxima: the rows' seen pattern over the sample tiles
+  w.two_blocks = w.K <= 128 && nI < TIGHTEN_MIN_ITEMS;
+  w.offHintMask = off; if (w.two_blocks) off += align_up(hint_mask_bytes((int64_t)cpad), 1024);
   w.total = off;
   return w;
 }
@@ -255,8 +260,15 @@ static int score_topk_impl(const void* U, const void* V, int64_t nU, int64_t nI,
       const char* err = "";
       prof_mark(PROF_FILTER, 0, st);
       // the common shape (d <= 128, catalogue below the online-tightening threshold) scores two user blocks per CTA
-      const bool two_blocks = w.K <= 128 && nI < TIGHTEN_MIN_ITEMS && !getenv("DIVREC_DEBUG_ONE_BLOCK");
+      const bool two_blocks = w.two_blocks && !getenv("DIVREC_DEBUG_ONE_BLOCK");
       sp.merged_lists = two_blocks ? 1 : 0;
+      if (two_blocks && rp != nullptr && !getenv("DIVREC_DEBUG_NO_HINT_MASK")) {
+        unsigned long long* hmask = reinterpret_cast<unsigned long long*>(ws + w.offHintMask);
+        const int64_t rows_padded = (int64_t)align_up((size_t)w.chunk, 128);
+        e = launch_hint_mask(rp, seen_items, cu, rows_padded, (int32_t)nI, item_id_offset, hmask, st);
+        if (e != cudaSuccess) return cuda_fail(e, "hint mask launch");
+        fp.hint_mask = hmask; fp.hint_mask_stride = rows_padded;
+      }
       e = two_blocks ? launch_score_filter2(A16, B16, fp, device_info().sm_count, st, &err)
                      : launch_score_filter(A16, B16, fp, device_info().sm_count, st, &err);
       if (e != cudaSuccess) return cuda_fail(e, err[0] ? err : "score_filter launch");

@@ -47,6 +47,9 @@ struct FilterParams {
   const int32_t* scale_exps;
   float c_margin;
   int d;
+  // two-block kernel only: seen-item pattern of the rows over the sample tiles (hint_mask_kernel), or null
+  const unsigned long long* hint_mask;
+  int64_t hint_mask_stride;    // rows (padded) between consecutive words of a row
 };
 
 int score_filter_b_stages(int kblocks);
@@ -57,6 +60,9 @@ cudaError_t launch_score_filter(const void* A16, const void* B16, FilterParams p
 // slots (h,0)+(h,1) hold ONE list of 2 * cap groups, list_count[h*2+1] = 0
 cudaError_t launch_score_filter2(const void* A16, const void* B16, FilterParams p, int sm_count,
                                  cudaStream_t stream, const char** err);
+size_t hint_mask_bytes(int64_t rows_padded);
+cudaError_t launch_hint_mask(const int64_t* seen_rowptr, const int32_t* seen_items, int64_t nU, int64_t rows_padded, int32_t nI,
+                             int64_t item_id_offset, unsigned long long* out, cudaStream_t stream);
 
 // fp32 [rows,d] -> one fp16 plane [rows,d_pad] of X * 2^scale_exp (max |x| scaled into [2^13, 2^14)),
 // plus fp32 row norms of X and (optionally) the maximum row norm as float bits.
@@ -112,6 +118,8 @@ struct RescueParams {
   const int32_t* fail_count;
   uint32_t* scratch;           // [grid][nI_pad] ordered score keys
   int grid;
+  int prescored;               // set by the launcher: rows f < prescored arrive with their keys already in slot f
+  int keys_in_smem;            // set by the launcher: the row's keys fit the CTA's shared memory for the selection passes
   float* out_scores;
   int64_t* out_items;
   float* out_ild;              // fused metrics for the rows re-done here (null = off)

@@ -24,7 +24,7 @@ constexpr int RSORT = 128;     // >= MAX_K
 struct RescueSmem {
   unsigned int hist[256];
   unsigned int warp_tot[RT / 32];
-  unsigned int prefix, kmask, k_rem, n_win, tie_base;
+  unsigned int prefix, kmask, k_rem, n_win, tie_base, n_eq;
   unsigned long long srt[RSORT];
   float inv[RSORT];
   float red[RT / 32];
@@ -33,6 +33,76 @@ struct RescueSmem {
 __device__ __forceinline__ float rd(const void* T, int dtype, int64_t idx) {
   if (dtype == 0) return __ldg(reinterpret_cast<const float*>(T) + idx);
   return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(T)[idx]);
+}
+
+// Exact fp32 scores of items [i0, i1) against the user row staged in u_s -> ordered keys (0 = not recommendable).
+// The summation order replays the select kernel's exactly (same partial sums, same butterfly), so a row gets the same
+// bits whichever kernel scores it: item-sharded, user-sharded, tensor and SIMT routes agree bit for bit.
+__device__ __forceinline__ void score_range(const RescueParams& p, const float* u_s, uint32_t* keys, int64_t i0, int64_t i1,
+                                            int tid) {
+  const int d = p.d;
+  const bool vec = (d & 3) == 0 && d <= 256;  // select_topk.cu: 8 lanes per candidate, float4 chunk c4 = lane + 8 j
+  for (int64_t i = i0 + tid; i < i1; i += RT) {
+    float s;
+    if (vec) {
+      float part[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      const int nvec = d >> 2;
+      for (int c0 = 0; c0 < nvec; c0 += 8) {  // partial l owns the float4 chunks l, l + 8, ...: same chains as select
+#pragma unroll
+        for (int l = 0; l < 8; ++l) {
+          const int c4 = c0 + l;
+          if (c4 < nvec) {
+            float4 x;
+            if (p.dtype == 0) {
+              x = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.V) + i * d) + c4);
+            } else {
+              const uint2 raw = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.V) + i * d) + c4);
+              x = make_float4(__uint_as_float(raw.x << 16), __uint_as_float(raw.x & 0xffff0000u),
+                              __uint_as_float(raw.y << 16), __uint_as_float(raw.y & 0xffff0000u));
+            }
+            const float4 y = *reinterpret_cast<const float4*>(u_s + 4 * c4);
+            float acc = part[l];
+            acc = fmaf(y.x, x.x, acc); acc = fmaf(y.y, x.y, acc); acc = fmaf(y.z, x.z, acc); acc = fmaf(y.w, x.w, acc);
+            part[l] = acc;
+          }
+        }
+      }
+      s = ((part[0] + part[1]) + (part[2] + part[3])) + ((part[4] + part[5]) + (part[6] + part[7]));  // xor 1, 2, 4
+    } else {
+      float part[32];  // scalar path: lane l takes columns l, l + 32, ...; butterfly xor 16, 8, 4, 2, 1
+#pragma unroll
+      for (int l = 0; l < 32; ++l) {
+        float acc = 0.f;
+        for (int c = l; c < d; c += 32) acc = fmaf(u_s[c], rd(p.V, p.dtype, i * d + c), acc);
+        part[l] = acc;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int l = 0; l < o; ++l) part[l] = part[l] + part[l + o];
+      s = part[0];
+    }
+    uint32_t kk = f32_to_key(__float_as_uint(s + 0.0f));
+    if (kk <= KEY_NEG_INF || !(s == s)) kk = 0;
+    keys[i] = kk;
+  }
+}
+
+// Scores of the first `gridDim.y` uncertified rows, spread over the whole chip (blockIdx.x = item range): one CTA
+// scoring a whole catalogue on its own takes 0.7 ms for 27k items and 65 ms for 1.25M, which made every uncertified
+// row expensive; rescue_kernel then only masks, selects and sorts these rows.
+__global__ void __launch_bounds__(RT)
+rescue_score_kernel(const RescueParams p, int64_t items_per_cta) {
+  extern __shared__ __align__(16) float u_s[];
+  const int f = blockIdx.y;
+  if (f >= *p.fail_count) return;
+  const int64_t row = p.fail_rows[f];
+  for (int c = threadIdx.x; c < p.d; c += RT) u_s[c] = rd(p.U, p.dtype, row * p.d + c);
+  __syncthreads();
+  uint32_t* keys = p.scratch + (size_t)f * (size_t)(((int64_t)p.nI + 31) & ~(int64_t)31);
+  const int64_t i0 = (int64_t)blockIdx.x * items_per_cta;
+  const int64_t i1 = i0 + items_per_cta < (int64_t)p.nI ? i0 + items_per_cta : (int64_t)p.nI;
+  score_range(p, u_s, keys, i0, i1, threadIdx.x);
 }
 
 __global__ void __launch_bounds__(RT)
@@ -52,61 +122,24 @@ rescue_kernel(const RescueParams p) {
     __syncthreads();
     for (int c = tid; c < d; c += RT) u_s[c] = rd(p.U, p.dtype, row * d + c);
     __syncthreads();
-    // 1. exact scores -> ordered keys (0 is reserved for "not recommendable").  The summation order replays the
-    //    select kernel's exactly (same partial sums, same butterfly), so a row gets the same bits whichever
-    //    kernel scores it: item-sharded, user-sharded, tensor and SIMT routes agree bit for bit.
-    const bool vec = (d & 3) == 0 && d <= 256;  // select_topk.cu: 8 lanes per candidate, float4 chunk c4 = lane + 8 j
-    for (int64_t i = tid; i < nI; i += RT) {
-      float s;
-      if (vec) {
-        float part[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        const int nvec = d >> 2;
-        for (int c0 = 0; c0 < nvec; c0 += 8) {  // partial l owns the float4 chunks l, l + 8, ...: same chains as select
-#pragma unroll
-          for (int l = 0; l < 8; ++l) {
-            const int c4 = c0 + l;
-            if (c4 < nvec) {
-              float4 x;
-              if (p.dtype == 0) {
-                x = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.V) + i * d) + c4);
-              } else {
-                const uint2 raw = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.V) + i * d) + c4);
-                x = make_float4(__uint_as_float(raw.x << 16), __uint_as_float(raw.x & 0xffff0000u),
-                                __uint_as_float(raw.y << 16), __uint_as_float(raw.y & 0xffff0000u));
-              }
-              const float4 y = *reinterpret_cast<const float4*>(u_s + 4 * c4);
-              float acc = part[l];
-              acc = fmaf(y.x, x.x, acc); acc = fmaf(y.y, x.y, acc); acc = fmaf(y.z, x.z, acc); acc = fmaf(y.w, x.w, acc);
-              part[l] = acc;
-            }
-          }
-        }
-        s = ((part[0] + part[1]) + (part[2] + part[3])) + ((part[4] + part[5]) + (part[6] + part[7]));  // xor 1, 2, 4
-      } else {
-        float part[32];  // scalar path: lane l takes columns l, l + 32, ...; butterfly xor 16, 8, 4, 2, 1
-#pragma unroll
-        for (int l = 0; l < 32; ++l) {
-          float acc = 0.f;
-          for (int c = l; c < d; c += 32) acc = fmaf(u_s[c], rd(p.V, p.dtype, i * d + c), acc);
-          part[l] = acc;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-          for (int l = 0; l < o; ++l) part[l] = part[l] + part[l + o];
-        s = part[0];
-      }
-      uint32_t kk = f32_to_key(__float_as_uint(s + 0.0f));
-      if (kk <= KEY_NEG_INF || !(s == s)) kk = 0;
-      keys[i] = kk;
-    }
+    // 1. exact scores -> ordered keys; the first p.prescored rows were scored by rescue_score_kernel into this slot
+    if (f >= p.prescored) score_range(p, u_s, keys, 0, nI, tid);
     __syncthreads();
+    // the selection passes below read every key five times with little work per key: from shared memory when the
+    // catalogue fits (independent loads, no synchronisation in the copy), else from the global scratch
+    uint32_t* kr = keys;
+    if (p.keys_in_smem) {
+      uint32_t* ks = reinterpret_cast<uint32_t*>(u_s + ((d + 3) & ~3));
+      for (int64_t i = tid; i < nI; i += RT) ks[i] = keys[i];
+      kr = ks;
+      __syncthreads();
+    }
     // 2. seen-item mask
     if (p.seen_rowptr != nullptr) {
       const int64_t s0 = p.seen_rowptr[row], s1 = p.seen_rowptr[row + 1];
       for (int64_t s = s0 + tid; s < s1; s += RT) {
         const int64_t li = (int64_t)p.seen_items[s] - p.item_id_offset;
-        if (li >= 0 && li < nI) keys[li] = 0;
+        if (li >= 0 && li < nI) kr[li] = 0;
       }
     }
     __syncthreads();
@@ -118,7 +151,7 @@ rescue_kernel(const RescueParams p) {
       __syncthreads();
       const unsigned prefix = sm.prefix, kmask = sm.kmask;
       for (int64_t i = tid; i < nI; i += RT) {
-        const uint32_t kk = keys[i];
+        const uint32_t kk = kr[i];
         // scores cluster in a few digit values: aggregate equal digits inside the warp before touching shared memory
         const bool on = kk != 0 && (kk & kmask) == prefix;
         const uint32_t digit = (kk >> (8 * pass)) & 255u;
@@ -149,30 +182,56 @@ rescue_kernel(const RescueParams p) {
     }
     const uint32_t T = have_k ? sm.prefix : 1u;             // keep keys > T, and `quota` keys == T (lowest ids)
     const unsigned quota = have_k ? sm.k_rem : 0xffffffffu;  // no limit when everything is taken
-    // 4. gather winners in id order (ties ranked by a block-wide ordered scan), then sort
+    // 4. gather the winners, then sort.  Keys above T are winners in any order (the sort fixes it); keys equal to T
+    // compete for `quota` places by lowest id.  Common case: all of them fit -> one unordered sweep with atomic appends.
     for (int i = tid; i < RSORT; i += RT) sm.srt[i] = 0ull;
-    if (tid == 0) { sm.n_win = 0; sm.tie_base = 0; }
+    if (tid == 0) { sm.n_win = 0; sm.tie_base = 0; sm.n_eq = 0; }
     __syncthreads();
-    for (int64_t base = 0; base < nI; base += RT) {
-      const int64_t i = base + tid;
-      const uint32_t kk = i < nI ? keys[i] : 0;
-      const bool gt = kk != 0 && (have_k ? kk > T : true);
-      const bool eq = have_k && kk == T;
-      const uint32_t eb = __ballot_sync(0xffffffffu, eq);
-      if (lane == 0) sm.warp_tot[warp] = __popc(eb);
-      __syncthreads();
-      unsigned before = sm.tie_base;
-      for (int w2 = 0; w2 < warp; ++w2) before += sm.warp_tot[w2];
-      const unsigned my_rank = before + __popc(eb & lanemask_lt());
-      const bool keep = gt || (eq && my_rank < quota);
-      if (keep) {
-        const unsigned slot = atomicAdd(&sm.n_win, 1u);
-        if (slot < RSORT) sm.srt[slot] = ((unsigned long long)kk << 32) | (unsigned long long)(~(uint32_t)i);
+    {
+      unsigned my_eq = 0;
+      for (int64_t i = tid; i < nI; i += RT) {
+        const uint32_t kk = kr[i];
+        if (kk != 0 && (have_k ? kk > T : true)) {
+          const unsigned slot = atomicAdd(&sm.n_win, 1u);
+          if (slot < RSORT) sm.srt[slot] = ((unsigned long long)kk << 32) | (unsigned long long)(~(uint32_t)i);
+        }
+        my_eq += (have_k && kk == T) ? 1u : 0u;
       }
-      __syncthreads();
-      if (tid == 0) { unsigned t = 0; for (int w2 = 0; w2 < RT / 32; ++w2) t += sm.warp_tot[w2]; sm.tie_base += t; }
-      __syncthreads();
+      if (my_eq) atomicAdd(&sm.n_eq, my_eq);
     }
+    __syncthreads();
+    const bool ties_fit = sm.n_eq <= quota;
+    if (have_k && ties_fit) {
+      for (int64_t i = tid; i < nI; i += RT) {
+        const uint32_t kk = kr[i];
+        if (kk == T) {
+          const unsigned slot = atomicAdd(&sm.n_win, 1u);
+          if (slot < RSORT) sm.srt[slot] = ((unsigned long long)kk << 32) | (unsigned long long)(~(uint32_t)i);
+        }
+      }
+    } else if (have_k) {
+      // more ties than places: the `quota` lowest ids win -- ranked by a block-wide ordered scan in id order
+      for (int64_t base = 0; base < nI; base += RT) {
+        const int64_t i = base + tid;
+        const uint32_t kk = i < nI ? kr[i] : 0;
+        const bool eq = kk == T;
+        const uint32_t eb = __ballot_sync(0xffffffffu, eq);
+        if (lane == 0) sm.warp_tot[warp] = __popc(eb);
+        __syncthreads();
+        unsigned before = sm.tie_base;
+        for (int w2 = 0; w2 < warp; ++w2) before += sm.warp_tot[w2];
+        const unsigned my_rank = before + __popc(eb & lanemask_lt());
+        if (eq && my_rank < quota) {
+          const unsigned slot = atomicAdd(&sm.n_win, 1u);
+          if (slot < RSORT) sm.srt[slot] = ((unsigned long long)kk << 32) | (unsigned long long)(~(uint32_t)i);
+        }
+        __syncthreads();
+        if (tid == 0) { unsigned t = 0; for (int w2 = 0; w2 < RT / 32; ++w2) t += sm.warp_tot[w2]; sm.tie_base += t; }
+        __syncthreads();
+        if (sm.tie_base >= quota) break;  // block-uniform: every place is taken
+      }
+    }
+    __syncthreads();
     // bitonic sort (descending) of RSORT composites by the whole block
     for (int size = 2; size <= RSORT; size <<= 1) {
       for (int stride = size >> 1; stride > 0; stride >>= 1) {
@@ -210,6 +269,7 @@ rescue_kernel(const RescueParams p) {
       float part = 0.f;
       for (int c = tid; c < d; c += RT) {
         float sc = 0.f;
+#pragma unroll 8
         for (int wdx = 0; wdx < n_win; ++wdx) sc = fmaf(rd(p.V, p.dtype, (int64_t)(~(uint32_t)sm.srt[wdx]) * d + c), sm.inv[wdx], sc);
         part = fmaf(sc, sc, part);
       }
@@ -245,9 +305,24 @@ size_t rescue_scratch_bytes(int64_t nI, int* grid_out) {
   return per * (size_t)g;
 }
 
-cudaError_t launch_rescue(const RescueParams& p, cudaStream_t stream) {
+cudaError_t launch_rescue(const RescueParams& p_in, cudaStream_t stream) {
+  RescueParams p = p_in;
   const size_t smem = (size_t)p.d * sizeof(float);
-  rescue_kernel<<<p.grid, RT, smem, stream>>>(p);
+  const size_t keys_bytes = (size_t)(((int64_t)p.nI + 31) & ~(int64_t)31) * sizeof(uint32_t);
+  const size_t smem_sel = (size_t)((p.d + 3) & ~3) * sizeof(float) + keys_bytes;
+  p.keys_in_smem = smem_sel <= 200 * 1024 ? 1 : 0;
+  // the first `slots` uncertified rows are scored by the whole chip (CTAs beyond the device-side count exit at once)
+  const int slots = p.grid < 64 ? p.grid : 64;
+  int64_t chunks = ((int64_t)p.nI + 2047) / 2048;
+  if (chunks > 296) chunks = 296;
+  const int64_t items_per_cta = ((int64_t)p.nI + chunks - 1) / chunks;
+  p.prescored = slots;
+  rescue_score_kernel<<<dim3((unsigned)chunks, (unsigned)slots), RT, smem, stream>>>(p, items_per_cta);
+  count_launch();
+  const size_t smem_main = p.keys_in_smem ? smem_sel : smem;
+  cudaError_t e = cudaFuncSetAttribute(rescue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem_main > 48 * 1024 ? smem_main : 48 * 1024));
+  if (e != cudaSuccess) return e;
+  rescue_kernel<<<p.grid, RT, smem_main, stream>>>(p);
   count_launch();
   return cudaGetLastError();
 }

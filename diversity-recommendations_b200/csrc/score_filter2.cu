@@ -45,6 +45,7 @@ struct Smem2 {
   uint32_t tmem_base;
   uint32_t pad;
   float sorted[NB][HS][EPI_THREADS];
+  int dropped[NB][EPI_THREADS];   // sample groups a thread left out of the hint because they contain seen items
 };
 
 __device__ __forceinline__ float max3(float a, float b, float c) {
@@ -63,6 +64,36 @@ __device__ __forceinline__ float max32(const uint32_t* v) {
 }
 __device__ __forceinline__ int sched_tile(int s, int n_sample, int stride) {
   return s < n_sample ? s * stride : s - n_sample;
+}
+
+// Seen-item pattern of every row over the SAMPLE tiles of the hint phase: out[(2 s + h) * stride_rows + row] has bit c set
+// when item (sample tile s, column 64 h + c) is in the row's seen list.  One warp per row; the 32 words of a row are
+// assembled in shared memory.  35 MB at cfg2, built from one pass over the CSR.
+__global__ void __launch_bounds__(256)
+hint_mask_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ items, int64_t nU, int64_t stride_rows,
+                 int32_t nI, int64_t item_off, int n_sample, int sample_stride, unsigned long long* __restrict__ out) {
+  __shared__ unsigned long long m[8][HS];
+  const int w = threadIdx.x >> 5;
+  const uint32_t lane = lane_id();
+  for (int64_t row = (int64_t)blockIdx.x * 8 + w; row < nU; row += (int64_t)gridDim.x * 8) {
+    m[w][lane] = 0ull;
+    __syncwarp();
+    const int64_t s0 = rowptr[row], s1 = rowptr[row + 1];
+    for (int64_t i = s0 + lane; i < s1; i += 32) {
+      const int64_t id = (int64_t)__ldg(items + i) - item_off;
+      if (id >= 0 && id < nI) {
+        const int tile = (int)(id >> 7);
+        const int s = tile / sample_stride;
+        if (s < n_sample && s * sample_stride == tile) {
+          const int col = (int)(id & 127);
+          atomicOr(&m[w][2 * s + (col >> 6)], 1ull << (col & 63));
+        }
+      }
+    }
+    __syncwarp();
+    out[(size_t)lane * stride_rows + row] = m[w][lane];
+    __syncwarp();
+  }
 }
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -214,9 +245,15 @@ score_filter2_kernel(const __grid_constant__ CUtensorMap tmap_b, const FilterPar
 
       // ---- phase 1: threshold hint (each set samples for its own block) ----
       if (n_sample > 0) {
+        // A sample group (32 columns) that contains one of the row's seen items is left out of the statistic: the
+        // remaining maxima are maxima over UNMASKED items only, so the hint can aim at k unmasked items instead of
+        // provisioning for every seen item outranking them (hint_mask_kernel; null = no mask / not built).
+        const unsigned long long* hm = (p.hint_mask != nullptr && valid_row) ? p.hint_mask + row : nullptr;
+        int dropped = 0;
         float hs[HS];
 #pragma unroll
         for (int s = 0; s < N_SAMPLE; ++s) {
+          const unsigned long long mk = hm != nullptr ? __ldg(hm + (size_t)(2 * s + h) * (size_t)p.hint_mask_stride) : 0ull;
           const uint32_t seq = base_seq + (uint32_t)(NB * s + bset), acc = seq % ACC_STAGES, acc_phase = (seq / ACC_STAGES) & 1;
           mbar_wait(smem_u32(&sm->acc_full[acc]), acc_phase);
           tc_fence_after();
@@ -224,13 +261,15 @@ score_filter2_kernel(const __grid_constant__ CUtensorMap tmap_b, const FilterPar
           uint32_t v0[32];
           tmem_ld_32x32b_x32(taddr, v0);
           tmem_wait_ld();
-          hs[2 * s] = max32(v0);
+          const bool d0 = (uint32_t)mk != 0u, d1 = (uint32_t)(mk >> 32) != 0u;
+          hs[2 * s] = d0 ? -INFINITY : max32(v0);
           tmem_ld_32x32b_x32(taddr + 32, v0);
           tmem_wait_ld();
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&sm->acc_empty[acc]));
-          hs[2 * s + 1] = max32(v0);
+          hs[2 * s + 1] = d1 ? -INFINITY : max32(v0);
+          dropped += (d0 ? 1 : 0) + (d1 ? 1 : 0);
         }
 #pragma unroll
         for (int size = 2; size <= HS; size <<= 1) {
@@ -251,19 +290,27 @@ score_filter2_kernel(const __grid_constant__ CUtensorMap tmap_b, const FilterPar
         }
 #pragma unroll
         for (int i = 0; i < HS; ++i) sm->sorted[bset][i][et] = hs[i];
+        sm->dropped[bset][et] = dropped;
         if (bset == 0) asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
         else asm volatile("bar.sync 2, %0;" ::"n"(EPI_THREADS) : "memory");
         if (valid_row) {
           int64_t seen_u = 0;
           if (p.seen_rowptr != nullptr) seen_u = p.seen_rowptr[row + 1] - p.seen_rowptr[row];
-          const float f0 = ((float)p.k + (float)seen_u + 8.0f) / (float)p.nI;
+          const int n_eff = 2 * HS - (sm->dropped[bset][row_local] + sm->dropped[bset][row_local + 128]);
+          // groups left: maxima over unmasked items only -> aim at k (+ max(16, k/4): the 2 delta certification band)
+          // unmasked items above the hint; too few groups left (heavy users): the worst-case rule on all 64 entries
+          // (the dropped ones read -inf, which can only lower the hint)
+          const bool masked_rule = hm != nullptr && n_eff >= HS && (int64_t)p.nI - seen_u > 0;
+          const float f0 = masked_rule ? ((float)p.k + (float)max(16, p.k >> 2)) / (float)((int64_t)p.nI - seen_u)
+                                       : ((float)p.k + (float)seen_u + 8.0f) / (float)p.nI;
+          const int n_groups = masked_rule ? n_eff : 2 * HS;
           int r = 2 * HS + 1;
           if (f0 < 0.25f) {
             const float pg = 1.0f - __expf(32.0f * log1pf(-f0));
-            const float n = (float)(2 * HS);
+            const float n = (float)n_groups;
             r = (int)ceilf(n * pg + 3.0f * sqrtf(n * pg * (1.0f - pg))) + 1;
           }
-          if (r <= 2 * HS - 4) {
+          if (r <= n_groups - 4) {
             const int ea = row_local, eb = row_local + 128;
             int i = 0, j = 0;
             float pick = INFINITY;
@@ -340,6 +387,27 @@ score_filter2_kernel(const __grid_constant__ CUtensorMap tmap_b, const FilterPar
 
 bool make_tmap_b(CUtensorMap* m, const void* base, int64_t rows, int K, int fmt);  // score_filter.cu
 
+// sample schedule of launch_score_filter2 for a catalogue of nI items (0 tiles: no hint phase)
+static void filter2_sample_schedule(int32_t nI, int* n_sample, int* stride) {
+  const int n_tiles = (nI + BN - 1) / BN;
+  if (n_tiles >= HINT_MIN_TILES) { *n_sample = N_SAMPLE; *stride = (n_tiles - 1) / N_SAMPLE; }
+  else { *n_sample = 0; *stride = 1; }
+}
+
+size_t hint_mask_bytes(int64_t rows_padded) { return (size_t)rows_padded * HS * sizeof(unsigned long long); }
+
+cudaError_t launch_hint_mask(const int64_t* seen_rowptr, const int32_t* seen_items, int64_t nU, int64_t rows_padded, int32_t nI,
+                             int64_t item_id_offset, unsigned long long* out, cudaStream_t stream) {
+  int n_sample, stride;
+  filter2_sample_schedule(nI, &n_sample, &stride);
+  if (n_sample == 0) return cudaSuccess;
+  int64_t g = (nU + 7) / 8;
+  if (g > 148 * 8) g = 148 * 8;
+  hint_mask_kernel<<<(unsigned)g, 256, 0, stream>>>(seen_rowptr, seen_items, nU, rows_padded, nI, item_id_offset, n_sample, stride, out);
+  count_launch();
+  return cudaGetLastError();
+}
+
 cudaError_t launch_score_filter2(const void* A16, const void* B16, FilterParams p, int sm_count, cudaStream_t stream,
                                  const char** err) {
   const int K = p.kblocks * BK;
@@ -357,13 +425,8 @@ cudaError_t launch_score_filter2(const void* A16, const void* B16, FilterParams 
   p.acc_stages = ACC_STAGES;
   p.hint_sigma = 3.0f;
   p.hint_extra = 1;
-  if (p.use_hint && p.n_tiles >= HINT_MIN_TILES) {
-    p.n_sample = N_SAMPLE;
-    p.sample_stride = (p.n_tiles - 1) / N_SAMPLE;
-  } else {
-    p.n_sample = 0;
-    p.sample_stride = 1;
-  }
+  filter2_sample_schedule(p.nI, &p.n_sample, &p.sample_stride);
+  if (!p.use_hint) { p.n_sample = 0; p.sample_stride = 1; }
   const size_t smem = 1024 + (size_t)p.b_stages * SLAB_BYTES + sizeof(Smem2);
   const int n_dblocks = (p.n_ublocks + NB - 1) / NB;
   int grid = n_dblocks < sm_count ? n_dblocks : sm_count;
