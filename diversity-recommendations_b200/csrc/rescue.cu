@@ -41,47 +41,54 @@ __device__ __forceinline__ float rd(const void* T, int dtype, int64_t idx) {
 __device__ __forceinline__ void score_range(const RescueParams& p, const float* u_s, uint32_t* keys, int64_t i0, int64_t i1,
                                             int tid) {
   const int d = p.d;
-  const bool vec = (d & 3) == 0 && d <= 256;  // select_topk.cu: 8 lanes per candidate, float4 chunk c4 = lane + 8 j
-  for (int64_t i = i0 + tid; i < i1; i += RT) {
-    float s;
-    if (vec) {
-      float part[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      const int nvec = d >> 2;
-      for (int c0 = 0; c0 < nvec; c0 += 8) {  // partial l owns the float4 chunks l, l + 8, ...: same chains as select
-#pragma unroll
-        for (int l = 0; l < 8; ++l) {
-          const int c4 = c0 + l;
-          if (c4 < nvec) {
-            float4 x;
-            if (p.dtype == 0) {
-              x = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.V) + i * d) + c4);
-            } else {
-              const uint2 raw = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.V) + i * d) + c4);
-              x = make_float4(__uint_as_float(raw.x << 16), __uint_as_float(raw.x & 0xffff0000u),
-                              __uint_as_float(raw.y << 16), __uint_as_float(raw.y & 0xffff0000u));
-            }
-            const float4 y = *reinterpret_cast<const float4*>(u_s + 4 * c4);
-            float acc = part[l];
-            acc = fmaf(y.x, x.x, acc); acc = fmaf(y.y, x.y, acc); acc = fmaf(y.z, x.z, acc); acc = fmaf(y.w, x.w, acc);
-            part[l] = acc;
+  const bool vec = (d & 3) == 0 && d <= 256;  // select_topk.cu: 8 lanes per candidate, float4 chunk c4 = sub + 8 j
+  if (vec) {
+    // exactly select_topk.cu's arithmetic and layout: 8 lanes per item (coalesced 128-byte pieces of its row), lane
+    // `sub` accumulates the chunks sub, sub + 8, ... in one fma chain, the partial sums are combined by the xor 1, 2, 4
+    // butterfly and lane 0 of the group keeps the result
+    const int sub = tid & 7, grp = tid >> 3, nvec = d >> 2;
+    for (int64_t base = i0; base < i1; base += RT / 8) {  // uniform trip count: the shuffles below need every lane
+      const int64_t i = base + grp;
+      const bool on = i < i1;
+      float s = 0.f;
+      for (int c4 = sub; c4 < nvec; c4 += 8) {
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (on) {
+          if (p.dtype == 0) {
+            x = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.V) + i * d) + c4);
+          } else {
+            const uint2 raw = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.V) + i * d) + c4);
+            x = make_float4(__uint_as_float(raw.x << 16), __uint_as_float(raw.x & 0xffff0000u),
+                            __uint_as_float(raw.y << 16), __uint_as_float(raw.y & 0xffff0000u));
           }
         }
+        const float4 y = *reinterpret_cast<const float4*>(u_s + 4 * c4);
+        s = fmaf(y.x, x.x, s); s = fmaf(y.y, x.y, s); s = fmaf(y.z, x.z, s); s = fmaf(y.w, x.w, s);
       }
-      s = ((part[0] + part[1]) + (part[2] + part[3])) + ((part[4] + part[5]) + (part[6] + part[7]));  // xor 1, 2, 4
-    } else {
-      float part[32];  // scalar path: lane l takes columns l, l + 32, ...; butterfly xor 16, 8, 4, 2, 1
-#pragma unroll
-      for (int l = 0; l < 32; ++l) {
-        float acc = 0.f;
-        for (int c = l; c < d; c += 32) acc = fmaf(u_s[c], rd(p.V, p.dtype, i * d + c), acc);
-        part[l] = acc;
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      s += __shfl_xor_sync(0xffffffffu, s, 4);
+      if (on && sub == 0) {
+        uint32_t kk = f32_to_key(__float_as_uint(s + 0.0f));
+        if (kk <= KEY_NEG_INF || !(s == s)) kk = 0;
+        keys[i] = kk;
       }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-        for (int l = 0; l < o; ++l) part[l] = part[l] + part[l + o];
-      s = part[0];
     }
+    return;
+  }
+  for (int64_t i = i0 + tid; i < i1; i += RT) {
+    float part[32];  // scalar path: lane l takes columns l, l + 32, ...; butterfly xor 16, 8, 4, 2, 1
+#pragma unroll
+    for (int l = 0; l < 32; ++l) {
+      float acc = 0.f;
+      for (int c = l; c < d; c += 32) acc = fmaf(u_s[c], rd(p.V, p.dtype, i * d + c), acc);
+      part[l] = acc;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int l = 0; l < o; ++l) part[l] = part[l] + part[l + o];
+    const float s = part[0];
     uint32_t kk = f32_to_key(__float_as_uint(s + 0.0f));
     if (kk <= KEY_NEG_INF || !(s == s)) kk = 0;
     keys[i] = kk;
