@@ -308,7 +308,9 @@ score_filter2_kernel(const __grid_constant__ CUtensorMap tmap_b, const FilterPar
           if (f0 < 0.25f) {
             const float pg = 1.0f - __expf(32.0f * log1pf(-f0));
             const float n = (float)n_groups;
-            r = (int)ceilf(n * pg + 3.0f * sqrtf(n * pg * (1.0f - pg))) + 1;
+            // 4 sigma on the masked rule: an uncertified row costs a rescue launch (~0.17 ms of latency per call even for a
+            // handful of rows), which at 3 sigma (24 rows per 138k) hits every call of the chunked host pipeline
+            r = (int)ceilf(n * pg + (masked_rule ? 4.0f : 3.0f) * sqrtf(n * pg * (1.0f - pg))) + 1;
           }
           if (r <= n_groups - 4) {
             const int ea = row_local, eb = row_local + 128;
