@@ -39,7 +39,8 @@ WORKLOADS = {
 }
 METRIC = "users/sec scored (score+top-k+ILD)"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch at cfg2, from the committed ncu --set full capture
-# (profiles/r01_ncu_filter_select_v6.txt); bench.py cannot run ncu itself
+# (profiles/r01_ncu_filter_select_v6.txt, taken before the masked hint: ~500 instead of ~360 captured elements per row,
+# so the current build moves somewhat less); bench.py cannot run ncu itself
 NCU_DRAM_TRAFFIC_CFG2 = {"score_filter2_kernel": 0.109167e9 + 2.306356e9, "select_topk_kernel": 2.518991e9 + 0.165455e9}
 
 
@@ -254,10 +255,10 @@ def bench_ours(args):
         "e2e": {"value": e2e_value, "unit": "users/s", "h2d_bytes_per_step": res["h2d_bytes"], "d2h_bytes_per_step": res["d2h_bytes"],
                 "api": "divrec.train.host_recommend_and_score (pinned host buffers -> C ABI -> host results)"},
         "gpu_launches": int(launches),
-        # the dominant kernel by time (ncu launch list profiles/r01_ncu_launches_v6.txt: 59 % of the step) is the selection
+        # the dominant kernel by time (ncu launch list profiles/r01_ncu_launches_v7.txt: 51 % of the launches) is the selection
         # kernel (mask + exact top-k + ILD gather + coverage): HBM/gather-bound stage S2+S3 of SURVEY.md 8d
         "roofline": select_roofline(phases, nU, d, k, pk, args.workload, float(items.numel()) / nU, ms_per_step),
-        # the tcgen05 score + filter kernel (36 % of the step) against the measured tensor peak
+        # the tcgen05 score + filter kernel (35 % of the launches) against the measured tensor peak
         "roofline_filter": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                             "traffic": NCU_DRAM_TRAFFIC_CFG2["score_filter2_kernel"] if args.workload == "cfg2" else None,
                             "kernel": "score_filter2_kernel" if d <= 128 else "score_filter_kernel", "kernel_ms": kms,
