@@ -76,15 +76,17 @@ struct WsLayout {
   size_t offA, offB, offNormU, offInvV, offListS, offListI, offCounts, offThr, offFail, offScalars, offRescue, offHintMask, total;
   bool two_blocks;
 };
-static WsLayout ws_layout(int64_t nU, int64_t nI, int d, int dtype) {
+static WsLayout ws_layout(int64_t nU, int64_t nI, int d, int dtype, int k) {
   WsLayout w{};
   w.d_pad = (int)align_up((size_t)d, 64);
   w.K = w.d_pad;
   w.convA = w.convB = (dtype == DIVREC_F32) || (d != w.d_pad);
   w.chunk = nU < CHUNK_USERS ? nU : CHUNK_USERS;
-  w.cap = nI >= TIGHTEN_MIN_ITEMS ? LIST_CAP_MAX : LIST_CAP;
+  // large k (above MAX_K_SMALL) captures several times more groups per row: the larger lists
+  w.cap = (nI >= TIGHTEN_MIN_ITEMS || k > MAX_K_SMALL) ? LIST_CAP_MAX : LIST_CAP;
   const size_t cpad = align_up((size_t)w.chunk, 128);
   size_t off = 0;
+  w.offScalars = off; off += 1024;  // u32[0..1] amax bits (U,V), i32[2..3] scale exps, u32[4] max item norm, i32[5] fail count, i32[6..11] statistics
   w.offA = off; if (w.convA) off += align_up(cpad * w.K * 2, 1024);
   w.offB = off; if (w.convB) off += align_up((size_t)nI * w.K * 2, 1024);
   w.offNormU = off; off += align_up(cpad * sizeof(float), 1024);
@@ -94,12 +96,11 @@ static WsLayout ws_layout(int64_t nU, int64_t nI, int d, int dtype) {
   w.offCounts = off; off += align_up(cpad * LISTS_PER_ROW * sizeof(int32_t), 1024);
   w.offThr = off; off += align_up(cpad * LISTS_PER_ROW * sizeof(float), 1024);
   w.offFail = off; off += align_up(cpad * sizeof(int32_t), 1024);
-  w.offScalars = off; off += 1024;  // u32[0..1] amax bits (U,V), i32[2..3] scale exps, u32[4] max item norm, i32[5] fail count
   w.offRescue = off; off += align_up(rescue_scratch_bytes(nI, &w.rescue_grid), 1024);
   // the common shape (d <= 128, catalogue below the online-tightening threshold) scores two user blocks per CTA and
   // takes its hint on unmasked sample maxima: the rows' seen pattern over the sample tiles
   w.two_blocks = w.K <= 128 && nI < TIGHTEN_MIN_ITEMS;
-  w.offHintMask = off; if (w.two_blocks) off += align_up(hint_mask_bytes((int64_t)cpad), 1024);
+  w.offHintMask = off; if (w.two_blocks) off += align_up(hint_mask_bytes((int64_t)cpad, (int32_t)nI), 1024);
   w.total = off;
   return w;
 }
@@ -147,9 +148,8 @@ int divrec_profile_read(float* ms_out, int n) {
 }
 
 size_t divrec_score_topk_workspace(int64_t nU, int64_t nI, int d, int dtype, int k) {
-  (void)k;
   if (nU <= 0 || nI <= 0 || d <= 0) return 0;
-  return ws_layout(nU, nI, d, dtype).total;
+  return ws_layout(nU, nI, d, dtype, k).total;
 }
 
 static int score_topk_impl(const void* U, const void* V, int64_t nU, int64_t nI, int d, int dtype, int mode,
@@ -162,11 +162,11 @@ static int score_topk_impl(const void* U, const void* V, int64_t nU, int64_t nI,
     return fail(DIVREC_ERR_ARG, "score_topk_metrics: the fused ILD needs d % 4 == 0, d <= 256 and k >= 2");
   if ((out_ild != nullptr || coverage != nullptr) && item_id_offset != 0)
     return fail(DIVREC_ERR_ARG, "score_topk_metrics: fused metrics need the whole catalogue (item_id_offset == 0)");
-  if (k <= 0 || k > MAX_K) return fail(DIVREC_ERR_ARG, "score_topk: k must be in [1,128]");
+  if (k <= 0 || k > MAX_K) return fail(DIVREC_ERR_ARG, "score_topk: k must be in [1,512]");
   if (!out_scores || !out_items) return fail(DIVREC_ERR_ARG, "score_topk: null output");
   if (seen_rowptr == nullptr && seen_items != nullptr)
     return fail(DIVREC_ERR_ARG, "score_topk: seen_items without seen_rowptr");
-  const WsLayout w = ws_layout(nU, nI, d, dtype);
+  const WsLayout w = ws_layout(nU, nI, d, dtype, k);
   if (!workspace || ws_bytes < w.total) return fail(DIVREC_ERR_WORKSPACE, "score_topk: workspace too small");
   if (reinterpret_cast<uintptr_t>(workspace) & 1023) return fail(DIVREC_ERR_ARG, "score_topk: workspace must be 1024-byte aligned");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -220,7 +220,7 @@ static int score_topk_impl(const void* U, const void* V, int64_t nU, int64_t nI,
     sp.fail_rows = reinterpret_cast<int32_t*>(ws + w.offFail); sp.fail_count = fail_count;
     sp.fail_reasons = reinterpret_cast<int32_t*>(scal) + 8;
     sp.force_fail = tensor ? 0 : 1;
-    const bool no_rescue = getenv("DIVREC_DEBUG_NO_RESCUE") != nullptr;  // debugging aid: leave uncertified rows undone
+    const bool no_rescue = debug_env("DIVREC_DEBUG_NO_RESCUE") != nullptr;  // debugging aid: leave uncertified rows undone
     sp.debug_dump = no_rescue ? 1 : 0;
     sp.out_ild = out_ild ? out_ild + u0 : nullptr; sp.coverage = coverage;
 
@@ -260,9 +260,9 @@ static int score_topk_impl(const void* U, const void* V, int64_t nU, int64_t nI,
       const char* err = "";
       prof_mark(PROF_FILTER, 0, st);
       // the common shape (d <= 128, catalogue below the online-tightening threshold) scores two user blocks per CTA
-      const bool two_blocks = w.two_blocks && !getenv("DIVREC_DEBUG_ONE_BLOCK");
+      const bool two_blocks = w.two_blocks && !debug_env("DIVREC_DEBUG_ONE_BLOCK");
       sp.merged_lists = two_blocks ? 1 : 0;
-      if (two_blocks && rp != nullptr && !getenv("DIVREC_DEBUG_NO_HINT_MASK")) {
+      if (two_blocks && rp != nullptr && !debug_env("DIVREC_DEBUG_NO_HINT_MASK")) {
         unsigned long long* hmask = reinterpret_cast<unsigned long long*>(ws + w.offHintMask);
         const int64_t rows_padded = (int64_t)align_up((size_t)w.chunk, 128);
         e = launch_hint_mask(rp, seen_items, cu, rows_padded, (int32_t)nI, item_id_offset, hmask, st);
@@ -289,12 +289,11 @@ static int score_topk_impl(const void* U, const void* V, int64_t nU, int64_t nI,
     rp2.fail_rows = sp.fail_rows; rp2.fail_count = fail_count;
     rp2.scratch = reinterpret_cast<uint32_t*>(ws + w.offRescue); rp2.grid = w.rescue_grid;
     rp2.out_scores = outs; rp2.out_items = outi; rp2.out_ild = sp.out_ild; rp2.coverage = coverage;
+    rp2.total_fail = reinterpret_cast<int32_t*>(scal) + 6;  // statistics: rows re-done exactly
     prof_mark(PROF_RESCUE, 0, st);
-    e = no_rescue ? cudaSuccess : launch_rescue(rp2, st);
+    e = no_rescue ? cudaSuccess : launch_rescue(rp2, st);  // (a debug build that skips it also skips the statistics)
     if (e != cudaSuccess) return cuda_fail(e, "rescue launch");
     prof_mark(PROF_RESCUE, 1, st);
-    e = launch_add_counter(fail_count, reinterpret_cast<int32_t*>(scal) + 6, st);  // statistics: rows re-done exactly
-    if (e != cudaSuccess) return cuda_fail(e, "counter launch");
   }
   return DIVREC_OK;
 }
@@ -316,12 +315,13 @@ int divrec_score_topk_metrics(const void* U, const void* V, int64_t nU, int64_t 
 
 int divrec_score_topk_rescued(const void* workspace, int64_t nU, int64_t nI, int d, int dtype, int32_t* host_out, void* stream) {
   if (!workspace || !host_out || nU <= 0 || nI <= 0 || d <= 0) return fail(DIVREC_ERR_ARG, "score_topk_rescued: bad argument");
-  const WsLayout w = ws_layout(nU, nI, d, dtype);
+  (void)dtype;
+  const size_t off_scalars = 0;  // the scalar block leads the workspace whatever the shape (ws_layout)
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   // host_out[0] = rows re-done exactly; host_out[1..4] = by reason: list overflow / forced, too many candidates,
   // hint not certified, too few captured
   int32_t tmp[6];
-  cudaError_t e = cudaMemcpyAsync(tmp, reinterpret_cast<const uint8_t*>(workspace) + w.offScalars + 6 * sizeof(int32_t),
+  cudaError_t e = cudaMemcpyAsync(tmp, reinterpret_cast<const uint8_t*>(workspace) + off_scalars + 6 * sizeof(int32_t),
                                   6 * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   if (e == cudaSuccess) { host_out[0] = tmp[0]; for (int i = 0; i < 4; ++i) host_out[1 + i] = tmp[2 + i]; }

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stddef.h>
+#include <stdlib.h>
 
 namespace divrec {
 
@@ -14,9 +15,18 @@ constexpr int GROUP = 8;             // consecutive item columns appended togeth
 constexpr int N_SAMPLE = 16;         // item tiles scored first to seed the per-row threshold hint
 constexpr int HINT_MIN_TILES = 32;   // catalogues with fewer 128-item tiles keep every group (no hint)
 constexpr int TIGHTEN_MIN_ITEMS = 500000;  // catalogues at least this large use the filter variant that tightens lists online
-constexpr int MAX_K = 128;
+constexpr int MAX_K = 512;          // largest k of score_topk (the select / rescue kernels switch to larger buffers above MAX_K_SMALL)
+constexpr int MAX_K_SMALL = 128;
 
 void count_launch();
+
+// Debugging / measurement knobs read from the environment exist only in builds made with -DDIVREC_DEBUG_KNOBS; the release
+// library never consults the environment (a stray variable must not be able to change what a call returns).
+#ifdef DIVREC_DEBUG_KNOBS
+inline const char* debug_env(const char* name) { return getenv(name); }
+#else
+inline const char* debug_env(const char*) { return nullptr; }
+#endif
 
 struct FilterParams {
   int64_t nU;
@@ -50,6 +60,8 @@ struct FilterParams {
   // two-block kernel only: seen-item pattern of the rows over the sample tiles (hint_mask_kernel), or null
   const unsigned long long* hint_mask;
   int64_t hint_mask_stride;    // rows (padded) between consecutive words of a row
+  int mask_words;              // set by the launcher: 64-bit words of the dirty-block bitmap per (row, column half)
+  int ladder_stride;           // set by the launcher: tiles between threshold-ladder checkpoints (0 = no ladder)
 };
 
 int score_filter_b_stages(int kblocks);
@@ -60,7 +72,7 @@ cudaError_t launch_score_filter(const void* A16, const void* B16, FilterParams p
 // slots (h,0)+(h,1) hold ONE list of 2 * cap groups, list_count[h*2+1] = 0
 cudaError_t launch_score_filter2(const void* A16, const void* B16, FilterParams p, int sm_count,
                                  cudaStream_t stream, const char** err);
-size_t hint_mask_bytes(int64_t rows_padded);
+size_t hint_mask_bytes(int64_t rows_padded, int32_t nI);
 cudaError_t launch_hint_mask(const int64_t* seen_rowptr, const int32_t* seen_items, int64_t nU, int64_t rows_padded, int32_t nI,
                              int64_t item_id_offset, unsigned long long* out, cudaStream_t stream);
 
@@ -124,10 +136,10 @@ struct RescueParams {
   int64_t* out_items;
   float* out_ild;              // fused metrics for the rows re-done here (null = off)
   int32_t* coverage;
+  int32_t* total_fail;         // device counter accumulated over the chunks of a call (statistics), may be null
 };
 size_t rescue_scratch_bytes(int64_t nI, int* grid_out);
 cudaError_t launch_rescue(const RescueParams& p, cudaStream_t stream);
-cudaError_t launch_add_counter(const int32_t* src, int32_t* dst, cudaStream_t stream);
 
 cudaError_t launch_topk_merge(const float* gs, const int64_t* gi, int n_shards, int64_t nU, int k,
                               float* out_scores, int64_t* out_items, cudaStream_t stream);

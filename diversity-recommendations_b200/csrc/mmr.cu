@@ -389,7 +389,7 @@ cudaError_t launch_mmr(MmrParams p, cudaStream_t stream) {
   // lazy greedy for the shapes it takes: 128-bit rows, C <= 1024, pick list + caches within shared memory
   const size_t lazy_smem = ((size_t)p.k * (size_t)(p.d + 4) + (size_t)LW * p.d) * sizeof(float);
   if ((p.d & 3) == 0 && p.d <= 512 && p.C <= 1024 && lazy_smem <= 200 * 1024 && p.nI < ((int64_t)1 << 31) &&
-      !getenv("DIVREC_DEBUG_MMR_EAGER")) {
+      !debug_env("DIVREC_DEBUG_MMR_EAGER")) {
     int per_sm = (int)((size_t)232448 / (lazy_smem + 1024 + 160));  // per-SM shared memory / (dynamic + reserved + static)
     if (per_sm > 4) per_sm = 4;
     if (per_sm < 1) per_sm = 1;

@@ -18,8 +18,10 @@ namespace divrec {
 
 namespace {
 
-constexpr int RT = 256;        // threads per CTA
-constexpr int RSORT = 128;     // >= MAX_K
+constexpr int RT = 1024;       // threads per CTA of the selection kernel (one CTA per row: its passes are latency, so go wide)
+constexpr int RT_SCORE = 256;  // threads per CTA of the chip-wide scoring kernel
+constexpr int RSORT = 512;     // >= MAX_K
+static_assert(RSORT >= MAX_K, "sort buffer covers the largest k");
 
 struct RescueSmem {
   unsigned int hist[256];
@@ -38,6 +40,7 @@ __device__ __forceinline__ float rd(const void* T, int dtype, int64_t idx) {
 // Exact fp32 scores of items [i0, i1) against the user row staged in u_s -> ordered keys (0 = not recommendable).
 // The summation order replays the select kernel's exactly (same partial sums, same butterfly), so a row gets the same
 // bits whichever kernel scores it: item-sharded, user-sharded, tensor and SIMT routes agree bit for bit.
+template <int NT>
 __device__ __forceinline__ void score_range(const RescueParams& p, const float* u_s, uint32_t* keys, int64_t i0, int64_t i1,
                                             int tid) {
   const int d = p.d;
@@ -47,7 +50,7 @@ __device__ __forceinline__ void score_range(const RescueParams& p, const float* 
     // `sub` accumulates the chunks sub, sub + 8, ... in one fma chain, the partial sums are combined by the xor 1, 2, 4
     // butterfly and lane 0 of the group keeps the result
     const int sub = tid & 7, grp = tid >> 3, nvec = d >> 2;
-    for (int64_t base = i0; base < i1; base += RT / 8) {  // uniform trip count: the shuffles below need every lane
+    for (int64_t base = i0; base < i1; base += NT / 8) {  // uniform trip count: the shuffles below need every lane
       const int64_t i = base + grp;
       const bool on = i < i1;
       float s = 0.f;
@@ -76,7 +79,7 @@ __device__ __forceinline__ void score_range(const RescueParams& p, const float* 
     }
     return;
   }
-  for (int64_t i = i0 + tid; i < i1; i += RT) {
+  for (int64_t i = i0 + tid; i < i1; i += NT) {
     float part[32];  // scalar path: lane l takes columns l, l + 32, ...; butterfly xor 16, 8, 4, 2, 1
 #pragma unroll
     for (int l = 0; l < 32; ++l) {
@@ -98,18 +101,18 @@ __device__ __forceinline__ void score_range(const RescueParams& p, const float* 
 // Scores of the first `gridDim.y` uncertified rows, spread over the whole chip (blockIdx.x = item range): one CTA
 // scoring a whole catalogue on its own takes 0.7 ms for 27k items and 65 ms for 1.25M, which made every uncertified
 // row expensive; rescue_kernel then only masks, selects and sorts these rows.
-__global__ void __launch_bounds__(RT)
+__global__ void __launch_bounds__(RT_SCORE)
 rescue_score_kernel(const RescueParams p, int64_t items_per_cta) {
   extern __shared__ __align__(16) float u_s[];
   const int f = blockIdx.y;
   if (f >= *p.fail_count) return;
   const int64_t row = p.fail_rows[f];
-  for (int c = threadIdx.x; c < p.d; c += RT) u_s[c] = rd(p.U, p.dtype, row * p.d + c);
+  for (int c = threadIdx.x; c < p.d; c += RT_SCORE) u_s[c] = rd(p.U, p.dtype, row * p.d + c);
   __syncthreads();
   uint32_t* keys = p.scratch + (size_t)f * (size_t)(((int64_t)p.nI + 31) & ~(int64_t)31);
   const int64_t i0 = (int64_t)blockIdx.x * items_per_cta;
   const int64_t i1 = i0 + items_per_cta < (int64_t)p.nI ? i0 + items_per_cta : (int64_t)p.nI;
-  score_range(p, u_s, keys, i0, i1, threadIdx.x);
+  score_range<RT_SCORE>(p, u_s, keys, i0, i1, threadIdx.x);
 }
 
 __global__ void __launch_bounds__(RT)
@@ -120,6 +123,7 @@ rescue_kernel(const RescueParams p) {
   const uint32_t lane = lane_id();
   const int warp = tid >> 5;
   const int n_fail = *p.fail_count;
+  if (blockIdx.x == 0 && tid == 0 && p.total_fail != nullptr) *p.total_fail += n_fail;  // statistics: rows re-done exactly (launches are stream-ordered)
   const int d = p.d, k = p.k;
   const int64_t nI = p.nI;
   uint32_t* keys = p.scratch + (size_t)blockIdx.x * (size_t)((nI + 31) & ~(int64_t)31);
@@ -130,7 +134,7 @@ rescue_kernel(const RescueParams p) {
     for (int c = tid; c < d; c += RT) u_s[c] = rd(p.U, p.dtype, row * d + c);
     __syncthreads();
     // 1. exact scores -> ordered keys; the first p.prescored rows were scored by rescue_score_kernel into this slot
-    if (f >= p.prescored) score_range(p, u_s, keys, 0, nI, tid);
+    if (f >= p.prescored) score_range<RT>(p, u_s, keys, 0, nI, tid);
     __syncthreads();
     // the selection passes below read every key five times with little work per key: from shared memory when the
     // catalogue fits (independent loads, no synchronisation in the copy), else from the global scratch
@@ -154,7 +158,7 @@ rescue_kernel(const RescueParams p) {
     if (tid == 0) { sm.prefix = 0; sm.kmask = 0; sm.k_rem = (unsigned)k; }
     bool have_k = true;
     for (int pass = 3; pass >= 0; --pass) {
-      sm.hist[tid] = 0;  // RT == 256 bins
+      if (tid < 256) sm.hist[tid] = 0;
       __syncthreads();
       const unsigned prefix = sm.prefix, kmask = sm.kmask;
       for (int64_t i = tid; i < nI; i += RT) {
@@ -191,7 +195,9 @@ rescue_kernel(const RescueParams p) {
     const unsigned quota = have_k ? sm.k_rem : 0xffffffffu;  // no limit when everything is taken
     // 4. gather the winners, then sort.  Keys above T are winners in any order (the sort fixes it); keys equal to T
     // compete for `quota` places by lowest id.  Common case: all of them fit -> one unordered sweep with atomic appends.
-    for (int i = tid; i < RSORT; i += RT) sm.srt[i] = 0ull;
+    int nsort = 32;  // sort buffer in use: the smallest power of two >= k (the winners never exceed k)
+    while (nsort < k) nsort <<= 1;
+    for (int i = tid; i < nsort; i += RT) sm.srt[i] = 0ull;
     if (tid == 0) { sm.n_win = 0; sm.tie_base = 0; sm.n_eq = 0; }
     __syncthreads();
     {
@@ -200,7 +206,7 @@ rescue_kernel(const RescueParams p) {
         const uint32_t kk = kr[i];
         if (kk != 0 && (have_k ? kk > T : true)) {
           const unsigned slot = atomicAdd(&sm.n_win, 1u);
-          if (slot < RSORT) sm.srt[slot] = ((unsigned long long)kk << 32) | (unsigned long long)(~(uint32_t)i);
+          if (slot < (unsigned)nsort) sm.srt[slot] = ((unsigned long long)kk << 32) | (unsigned long long)(~(uint32_t)i);
         }
         my_eq += (have_k && kk == T) ? 1u : 0u;
       }
@@ -213,7 +219,7 @@ rescue_kernel(const RescueParams p) {
         const uint32_t kk = kr[i];
         if (kk == T) {
           const unsigned slot = atomicAdd(&sm.n_win, 1u);
-          if (slot < RSORT) sm.srt[slot] = ((unsigned long long)kk << 32) | (unsigned long long)(~(uint32_t)i);
+          if (slot < (unsigned)nsort) sm.srt[slot] = ((unsigned long long)kk << 32) | (unsigned long long)(~(uint32_t)i);
         }
       }
     } else if (have_k) {
@@ -230,7 +236,7 @@ rescue_kernel(const RescueParams p) {
         const unsigned my_rank = before + __popc(eb & lanemask_lt());
         if (eq && my_rank < quota) {
           const unsigned slot = atomicAdd(&sm.n_win, 1u);
-          if (slot < RSORT) sm.srt[slot] = ((unsigned long long)kk << 32) | (unsigned long long)(~(uint32_t)i);
+          if (slot < (unsigned)nsort) sm.srt[slot] = ((unsigned long long)kk << 32) | (unsigned long long)(~(uint32_t)i);
         }
         __syncthreads();
         if (tid == 0) { unsigned t = 0; for (int w2 = 0; w2 < RT / 32; ++w2) t += sm.warp_tot[w2]; sm.tie_base += t; }
@@ -240,9 +246,9 @@ rescue_kernel(const RescueParams p) {
     }
     __syncthreads();
     // bitonic sort (descending) of RSORT composites by the whole block
-    for (int size = 2; size <= RSORT; size <<= 1) {
+    for (int size = 2; size <= nsort; size <<= 1) {
       for (int stride = size >> 1; stride > 0; stride >>= 1) {
-        if (tid < RSORT / 2) {
+        if (tid < nsort / 2) {
           const int a = ((tid & ~(stride - 1)) << 1) | (tid & (stride - 1));
           const int b = a | stride;
           const bool desc = (a & size) == 0;
@@ -293,15 +299,7 @@ rescue_kernel(const RescueParams p) {
   }
 }
 
-__global__ void add_counter_kernel(const int32_t* __restrict__ src, int32_t* __restrict__ dst) { *dst += *src; }
-
 }  // namespace
-
-cudaError_t launch_add_counter(const int32_t* src, int32_t* dst, cudaStream_t stream) {
-  add_counter_kernel<<<1, 1, 0, stream>>>(src, dst);
-  count_launch();
-  return cudaGetLastError();
-}
 
 size_t rescue_scratch_bytes(int64_t nI, int* grid_out) {
   const size_t per = (size_t)((nI + 31) & ~(int64_t)31) * sizeof(uint32_t);
@@ -320,11 +318,12 @@ cudaError_t launch_rescue(const RescueParams& p_in, cudaStream_t stream) {
   p.keys_in_smem = smem_sel <= 200 * 1024 ? 1 : 0;
   // the first `slots` uncertified rows are scored by the whole chip (CTAs beyond the device-side count exit at once)
   const int slots = p.grid < 64 ? p.grid : 64;
-  int64_t chunks = ((int64_t)p.nI + 2047) / 2048;
+  // item ranges of >= 128 items, up to two waves of CTAs per row: one uncertified row (the usual count) is scored by the whole chip
+  int64_t chunks = ((int64_t)p.nI + 127) / 128;
   if (chunks > 296) chunks = 296;
   const int64_t items_per_cta = ((int64_t)p.nI + chunks - 1) / chunks;
   p.prescored = slots;
-  rescue_score_kernel<<<dim3((unsigned)chunks, (unsigned)slots), RT, smem, stream>>>(p, items_per_cta);
+  rescue_score_kernel<<<dim3((unsigned)chunks, (unsigned)slots), RT_SCORE, smem, stream>>>(p, items_per_cta);
   count_launch();
   const size_t smem_main = p.keys_in_smem ? smem_sel : smem;
   cudaError_t e = cudaFuncSetAttribute(rescue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem_main > 48 * 1024 ? smem_main : 48 * 1024));

@@ -589,7 +589,7 @@ cudaError_t launch_score_filter(const void* A16, const void* B16, FilterParams p
   p.hint_eps = p.nI >= TIGHTEN_MIN_ITEMS ? 1.0e-9f : 0.0f;  // per-row probability that the sampled hint is too high
   p.hint_sigma = p.nI >= TIGHTEN_MIN_ITEMS ? 5.0f : 3.0f;
   p.hint_extra = p.nI >= TIGHTEN_MIN_ITEMS ? 2 : 1;
-  const bool tighten = p.nI >= TIGHTEN_MIN_ITEMS && !getenv("DIVREC_DEBUG_NO_TIGHTEN");
+  const bool tighten = p.nI >= TIGHTEN_MIN_ITEMS && !debug_env("DIVREC_DEBUG_NO_TIGHTEN");
   if (p.use_hint && p.n_tiles >= HINT_MIN_TILES) {
     // large catalogues: the number of sample tiles grows with the catalogue (1.3 % of the pass), so that the hint -- the
     // r-th largest of 64 group maxima with a 1e-9 exact binomial tail -- sits where ~1200 groups per row pass it whatever
@@ -609,7 +609,7 @@ cudaError_t launch_score_filter(const void* A16, const void* B16, FilterParams p
   }
   const size_t smem = score_filter_smem_bytes(p.kblocks);
   int grid = p.n_ublocks < sm_count ? p.n_ublocks : sm_count;
-  if (const char* g = getenv("DIVREC_DEBUG_FILTER_GRID")) { const int v = atoi(g); if (v > 0 && v < grid) grid = v; }  // measurement aid
+  if (const char* g = debug_env("DIVREC_DEBUG_FILTER_GRID")) { const int v = atoi(g); if (v > 0 && v < grid) grid = v; }  // measurement aid
   cudaError_t e;
   if (tighten) {
     e = cudaFuncSetAttribute(score_filter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

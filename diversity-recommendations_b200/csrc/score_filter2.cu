@@ -13,6 +13,16 @@
 //             lists (column halves) of 2 x LIST_CAP groups, stored in the four-list layout as slots (h, 0)+(h, 1);
 //   MMA       per tile: 8 k-steps for block 0, 8 for block 1 against the same shared-memory stages, which are
 //             released after the second pass.
+//
+// Threshold ladder (round 2).  The sampled hint has to be safe (4 sigma on ~53 group maxima), so it sits where ~360
+// elements per row pass it while ~118 are needed.  The hint phase therefore also leaves four tighter LEVELS (the same
+// order statistic at 3, 2, 1, 0 sigma); during the main pass every thread counts, per level, the CLEAN 64-column blocks
+// (no seen item: dirty-block bitmap of row_mask_kernel) whose maximum reaches it.  At checkpoints (every ~1/8 of the
+// catalogue) the two threads of a row pool their counts and raise the threshold to the highest value -- interpolated
+// between levels -- whose projected number of unmasked items above it, at a 2.5 sigma lower confidence bound, still
+// covers k + margin.  A threshold only ever rises, and everything at or above the final one was captured at every
+// earlier (lower) one, so the select kernel's certification contract is unchanged (tools/sim/ladder_sim.py: captured
+// elements per row 363 -> ~185, emitted groups 345 -> ~225, no uncertified row in 12 000).
 #include <cstdlib>
 
 #include "common.cuh"
@@ -66,32 +76,36 @@ __device__ __forceinline__ int sched_tile(int s, int n_sample, int stride) {
   return s < n_sample ? s * stride : s - n_sample;
 }
 
-// Seen-item pattern of every row over the SAMPLE tiles of the hint phase: out[(2 s + h) * stride_rows + row] has bit c set
-// when item (sample tile s, column 64 h + c) is in the row's seen list.  One warp per row; the 32 words of a row are
-// assembled in shared memory.  35 MB at cfg2, built from one pass over the CSR.
+// Seen-item patterns of every row, one pass over the CSR (one warp per row, words assembled in shared memory):
+//   words [0, HS):           out[(2 s + h) * stride_rows + row] has bit c set when item (sample tile s, column 64 h + c)
+//                            is in the row's seen list (the hint phase leaves such sample groups out of its statistic);
+//   words [HS, HS + 2 W):    out[(HS + h * W + w) * stride_rows + row] has bit b set when the 64-column block
+//                            (tile 64 w + b, column half h) holds a seen item ("dirty": the ladder counts clean blocks only).
+// 44 MB at cfg2 (W = 4).
 __global__ void __launch_bounds__(256)
-hint_mask_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ items, int64_t nU, int64_t stride_rows,
-                 int32_t nI, int64_t item_off, int n_sample, int sample_stride, unsigned long long* __restrict__ out) {
-  __shared__ unsigned long long m[8][HS];
+row_mask_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ items, int64_t nU, int64_t stride_rows,
+                int32_t nI, int64_t item_off, int n_sample, int sample_stride, int W, unsigned long long* __restrict__ out) {
+  extern __shared__ unsigned long long rm_smem[];
   const int w = threadIdx.x >> 5;
   const uint32_t lane = lane_id();
+  const int nw = HS + 2 * W;
+  unsigned long long* m = rm_smem + (size_t)w * nw;
   for (int64_t row = (int64_t)blockIdx.x * 8 + w; row < nU; row += (int64_t)gridDim.x * 8) {
-    m[w][lane] = 0ull;
+    for (int i = lane; i < nw; i += 32) m[i] = 0ull;
     __syncwarp();
     const int64_t s0 = rowptr[row], s1 = rowptr[row + 1];
     for (int64_t i = s0 + lane; i < s1; i += 32) {
       const int64_t id = (int64_t)__ldg(items + i) - item_off;
       if (id >= 0 && id < nI) {
         const int tile = (int)(id >> 7);
+        const int col = (int)(id & 127);
+        atomicOr(&m[HS + (col >> 6) * W + (tile >> 6)], 1ull << (tile & 63));
         const int s = tile / sample_stride;
-        if (s < n_sample && s * sample_stride == tile) {
-          const int col = (int)(id & 127);
-          atomicOr(&m[w][2 * s + (col >> 6)], 1ull << (col & 63));
-        }
+        if (s < n_sample && s * sample_stride == tile) atomicOr(&m[2 * s + (col >> 6)], 1ull << (col & 63));
       }
     }
     __syncwarp();
-    out[(size_t)lane * stride_rows + row] = m[w][lane];
+    for (int i = lane; i < nw; i += 32) out[(size_t)i * stride_rows + row] = m[i];
     __syncwarp();
   }
 }
@@ -244,10 +258,11 @@ score_filter2_kernel(const __grid_constant__ CUtensorMap tmap_b, const FilterPar
       }
 
       // ---- phase 1: threshold hint (each set samples for its own block) ----
+      float4 lv = make_float4(INFINITY, INFINITY, INFINITY, INFINITY);  // ladder levels (tighter than the hint); +inf = unused
       if (n_sample > 0) {
         // A sample group (32 columns) that contains one of the row's seen items is left out of the statistic: the
         // remaining maxima are maxima over UNMASKED items only, so the hint can aim at k unmasked items instead of
-        // provisioning for every seen item outranking them (hint_mask_kernel; null = no mask / not built).
+        // provisioning for every seen item outranking them (row_mask_kernel; null = no mask / not built).
         const unsigned long long* hm = (p.hint_mask != nullptr && valid_row) ? p.hint_mask + row : nullptr;
         int dropped = 0;
         float hs[HS];
@@ -312,21 +327,46 @@ score_filter2_kernel(const __grid_constant__ CUtensorMap tmap_b, const FilterPar
             // handful of rows), which at 3 sigma (24 rows per 138k) hits every call of the chunked host pipeline
             r = (int)ceilf(n * pg + (masked_rule ? 4.0f : 3.0f) * sqrtf(n * pg * (1.0f - pg))) + 1;
           }
-          if (r <= n_groups - 4) {
+          // ladder levels: the same order statistic at 3, 2, 1, 0 sigma for k + margin UNMASKED items (ranks r_lv[j] <= r);
+          // which of them is safe is decided later from live counts, so their own noise costs tightness, never exactness
+          int r_lv[4] = {0, 0, 0, 0};
+          {
+            const float f1 = ((float)p.k + (float)max(16, p.k >> 2)) / fmaxf(1.0f, (float)((int64_t)p.nI - seen_u));
+            if (f1 < 0.25f) {
+              const float pg = 1.0f - __expf(32.0f * log1pf(-f1));
+              const float n = (float)n_groups, sd = sqrtf(n * pg * (1.0f - pg));
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                int rj = (int)ceilf(n * pg + (float)(3 - j) * sd) + 1;
+                rj = max(1, rj);
+                r_lv[j] = (rj <= n_groups - 4 && (r > n_groups - 4 || rj <= r)) ? rj : 0;
+              }
+            }
+          }
+          const int r_walk = r <= n_groups - 4 ? r : max(max(r_lv[0], r_lv[1]), max(r_lv[2], r_lv[3]));
+          {
             const int ea = row_local, eb = row_local + 128;
             int i = 0, j = 0;
             float pick = INFINITY;
-            for (int c = 0; c < r; ++c) {
+            for (int c = 0; c < r_walk; ++c) {
               const float a = i < HS ? sm->sorted[bset][i][ea] : -INFINITY;
               const float b = j < HS ? sm->sorted[bset][j][eb] : -INFINITY;
               if (a >= b) { pick = a; ++i; } else { pick = b; ++j; }
+              if (c + 1 == r_lv[0]) lv.x = pick;
+              if (c + 1 == r_lv[1]) lv.y = pick;
+              if (c + 1 == r_lv[2]) lv.z = pick;
+              if (c + 1 == r_lv[3]) lv.w = pick;
             }
-            thr = pick;
+            if (r <= n_groups - 4) thr = pick;
           }
         }
         if (bset == 0) asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
         else asm volatile("bar.sync 2, %0;" ::"n"(EPI_THREADS) : "memory");
       }
+      // the row's ladder levels live in shared memory (rows 8, 9 of this set's `sorted` area, dead until the next user
+      // block's hint phase; both threads of a row write the same values)
+      float4* const lv_s = reinterpret_cast<float4*>(&sm->sorted[bset][8][0]);
+      lv_s[row_local] = lv;
 
       // ---- phase 2: fixed-threshold group filter over every tile of this set's block ----
       float* const Ls_blk = p.list_scores + (size_t)ub * (BM * 4) * ((size_t)p.cap * GROUP);
@@ -335,7 +375,18 @@ score_filter2_kernel(const __grid_constant__ CUtensorMap tmap_b, const FilterPar
       const uint32_t cap2 = 2u * (uint32_t)p.cap;
       const uint32_t cap_lim = cap2 - GROUPS_PER_TILE;
       uint32_t cnt = 0;
+      // ladder state: per level, clean 64-column blocks of this thread whose maximum reached it (16-bit fields), and the
+      // clean blocks seen; the dirty-block bitmap is read 32 tiles at a time
+      uint32_t c01 = 0, c23 = 0, ncl = 0, dirty = 0;
+      const uint32_t* const dirty_w = (p.hint_mask != nullptr && valid_row)
+          ? reinterpret_cast<const uint32_t*>(p.hint_mask + (size_t)(HS + h * p.mask_words) * (size_t)p.hint_mask_stride + row)
+          : nullptr;
+      const bool ladder = p.ladder_stride > 0;
+      int next_cp = ladder ? p.ladder_stride : 0x7fffffff;
+      uint32_t* const exch = reinterpret_cast<uint32_t*>(&sm->sorted[bset][0][0]);  // checkpoint exchange: rows 0..5 of `sorted`
       for (int t = 0; t < p.n_tiles; ++t) {
+        if (ladder && (t & 31) == 0)
+          dirty = dirty_w != nullptr ? __ldg(dirty_w + (size_t)(t >> 6) * (size_t)p.hint_mask_stride * 2 + ((t >> 5) & 1)) : 0u;
         const uint32_t seq = base_seq + (uint32_t)(NB * (n_sample + t) + bset), acc = seq % ACC_STAGES, acc_phase = (seq / ACC_STAGES) & 1;
         mbar_wait(smem_u32(&sm->acc_full[acc]), acc_phase);
         tc_fence_after();
@@ -352,6 +403,7 @@ score_filter2_kernel(const __grid_constant__ CUtensorMap tmap_b, const FilterPar
         if (cnt > cap_lim) { thr = INFINITY; cnt = cap2 + 1; }  // overflow: the row goes to the rescue kernel
         const float thr_st = p.debug_mode == 2 ? INFINITY : thr;
         const uint32_t item0 = (uint32_t)(t * BN + h * COLS_PER_THREAD);
+        float mt0 = -INFINITY, mt1 = -INFINITY, mt2 = -INFINITY;  // maximum of the 64-column block
 #pragma unroll
         for (int g = 0; g < GROUPS_PER_TILE; ++g) {
           const uint32_t* v = g < 4 ? &v0[8 * g] : &v1[8 * (g - 4)];
@@ -369,6 +421,63 @@ score_filter2_kernel(const __grid_constant__ CUtensorMap tmap_b, const FilterPar
                 "r"(v[6]), "r"(v[7]), "r"(item0 + 8 * g)
               : "memory");
           cnt += (m >= thr) ? 1u : 0u;
+          if (g % 3 == 0) mt0 = fmaxf(mt0, m); else if (g % 3 == 1) mt1 = fmaxf(mt1, m); else mt2 = fmaxf(mt2, m);
+        }
+        if (ladder) {
+          const float mt = max3(mt0, mt1, mt2);
+          const bool clean = ((dirty >> (t & 31)) & 1u) == 0u;
+          const float4 l4 = lv_s[row_local];
+          ncl += clean ? 1u : 0u;
+          c01 += (clean && mt >= l4.x) ? 1u : 0u;
+          c01 += (clean && mt >= l4.y) ? 0x10000u : 0u;
+          c23 += (clean && mt >= l4.z) ? 1u : 0u;
+          c23 += (clean && mt >= l4.w) ? 0x10000u : 0u;
+          if (t + 1 == next_cp) {
+            next_cp += p.ladder_stride;
+            if (t + 1 < p.n_tiles) {
+              // ---- checkpoint: pool the row's two halves, raise the threshold where the projected count allows ----
+              const uint32_t slot = (uint32_t)(((t + 1) / p.ladder_stride) & 1) * 3u;
+              exch[(slot + 0) * EPI_THREADS + et] = c01;
+              exch[(slot + 1) * EPI_THREADS + et] = c23;
+              exch[(slot + 2) * EPI_THREADS + et] = ncl;
+              if (bset == 0) asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+              else asm volatile("bar.sync 2, %0;" ::"n"(EPI_THREADS) : "memory");
+              const int pe = et ^ 128;  // the row's other column half
+              const uint32_t s01 = c01 + exch[(slot + 0) * EPI_THREADS + pe], s23 = c23 + exch[(slot + 1) * EPI_THREADS + pe];
+              const float nc = (float)(ncl + exch[(slot + 2) * EPI_THREADS + pe]);
+              if (valid_row && nc >= 16.0f) {
+                int64_t seen_u = 0;
+                if (p.seen_rowptr != nullptr) seen_u = p.seen_rowptr[row + 1] - p.seen_rowptr[row];
+                const float n_un = fmaxf(1.0f, (float)((int64_t)p.nI - seen_u));
+                const float need = (float)p.k + (float)max(16, p.k >> 2);
+                const float frac = (float)(t + 1) / (float)p.n_tiles;
+                const float req = need + sqrtf(need * (1.0f - frac));  // + 1 sigma of the part of the catalogue still to come
+                const float cj[4] = {(float)(s01 & 0xffffu), (float)(s01 >> 16), (float)(s23 & 0xffffu), (float)(s23 >> 16)};
+                const float lj[4] = {l4.x, l4.y, l4.z, l4.w};
+                float nlo[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float qh = cj[j] / nc;
+                  const float se = sqrtf(fmaxf(qh * (1.0f - qh), 1e-9f) / nc);
+                  const float qlo = fminf(fmaxf(qh - 2.5f * se, 1e-6f), 0.999f);
+                  nlo[j] = -log1pf(-qlo) * (1.0f / 64.0f) * n_un;  // items above level j, lower confidence bound
+                }
+                float cand = -INFINITY;
+#pragma unroll
+                for (int j = 3; j >= 0; --j) {
+                  if (cand == -INFINITY && lj[j] < 3.0e38f && nlo[j] >= req) {
+                    cand = lj[j];
+                    if (j < 3 && lj[j + 1] < 3.0e38f && lj[j + 1] > lj[j] && nlo[j + 1] < req && nlo[j + 1] > 0.0f) {
+                      // log-linear interpolation of the count between the two levels
+                      const float wgt = (__logf(nlo[j]) - __logf(req)) / fmaxf(__logf(nlo[j]) - __logf(nlo[j + 1]), 1e-6f);
+                      cand += (lj[j + 1] - lj[j]) * fminf(fmaxf(wgt, 0.0f), 1.0f);
+                    }
+                  }
+                }
+                thr = fmaxf(thr, cand);
+              }
+            }
+          }
         }
       }
       if (valid_row) {
@@ -396,7 +505,11 @@ static void filter2_sample_schedule(int32_t nI, int* n_sample, int* stride) {
   else { *n_sample = 0; *stride = 1; }
 }
 
-size_t hint_mask_bytes(int64_t rows_padded) { return (size_t)rows_padded * HS * sizeof(unsigned long long); }
+static int mask_words_for(int32_t nI) { return ((nI + BN - 1) / BN + 63) / 64; }
+
+size_t hint_mask_bytes(int64_t rows_padded, int32_t nI) {
+  return (size_t)rows_padded * (size_t)(HS + 2 * mask_words_for(nI)) * sizeof(unsigned long long);
+}
 
 cudaError_t launch_hint_mask(const int64_t* seen_rowptr, const int32_t* seen_items, int64_t nU, int64_t rows_padded, int32_t nI,
                              int64_t item_id_offset, unsigned long long* out, cudaStream_t stream) {
@@ -405,7 +518,9 @@ cudaError_t launch_hint_mask(const int64_t* seen_rowptr, const int32_t* seen_ite
   if (n_sample == 0) return cudaSuccess;
   int64_t g = (nU + 7) / 8;
   if (g > 148 * 8) g = 148 * 8;
-  hint_mask_kernel<<<(unsigned)g, 256, 0, stream>>>(seen_rowptr, seen_items, nU, rows_padded, nI, item_id_offset, n_sample, stride, out);
+  const int W = mask_words_for(nI);
+  const size_t smem = (size_t)8 * (HS + 2 * W) * sizeof(unsigned long long);
+  row_mask_kernel<<<(unsigned)g, 256, smem, stream>>>(seen_rowptr, seen_items, nU, rows_padded, nI, item_id_offset, n_sample, stride, W, out);
   count_launch();
   return cudaGetLastError();
 }
@@ -429,10 +544,13 @@ cudaError_t launch_score_filter2(const void* A16, const void* B16, FilterParams 
   p.hint_extra = 1;
   filter2_sample_schedule(p.nI, &p.n_sample, &p.sample_stride);
   if (!p.use_hint) { p.n_sample = 0; p.sample_stride = 1; }
+  p.mask_words = mask_words_for(p.nI);
+  // ladder checkpoints every ~1/8 of the catalogue (off without a hint phase: catalogues under HINT_MIN_TILES tiles)
+  p.ladder_stride = p.n_sample > 0 ? ((p.n_tiles + 7) / 8 > 8 ? (p.n_tiles + 7) / 8 : 8) : 0;
   const size_t smem = 1024 + (size_t)p.b_stages * SLAB_BYTES + sizeof(Smem2);
   const int n_dblocks = (p.n_ublocks + NB - 1) / NB;
   int grid = n_dblocks < sm_count ? n_dblocks : sm_count;
-  if (const char* g = getenv("DIVREC_DEBUG_FILTER_GRID")) { const int v = atoi(g); if (v > 0 && v < grid) grid = v; }
+  if (const char* g = debug_env("DIVREC_DEBUG_FILTER_GRID")) { const int v = atoi(g); if (v > 0 && v < grid) grid = v; }  // measurement aid
   cudaError_t e = cudaFuncSetAttribute(score_filter2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   score_filter2_kernel<<<grid, NUM_THREADS, smem, stream>>>(tb, p);

@@ -24,29 +24,38 @@ namespace divrec {
 namespace {
 
 constexpr int SEL_WARPS = 4;
-constexpr int SEL_CAP = 768;              // candidate elements per row held in shared memory
-constexpr int SEEN_CAP = 512;             // seen items of the row staged in shared memory (longer lists stay in global)
-constexpr int SORT_N = 128;               // >= MAX_K, power of two
 
-// Per warp ONE contiguous region of 32-bit words: [key: SEL_CAP][id: SEL_CAP][seen: SEEN_CAP (phase B; reused as the
-// 128-entry sort chunk of phase E)][top: SORT_N 64-bit, the running top list].  The coarse cut of rows that captured
-// more than SEL_CAP elements uses the whole region as a keys-only buffer of SEL_WORDS entries.
-constexpr int SEL_WORDS = 2 * SEL_CAP + SEEN_CAP + 2 * SORT_N;
-struct SelSmem {
-  uint32_t w[SEL_WARPS][SEL_WORDS];
+// Per-warp shared-memory budget by k class.  KB = 0: k <= 128 (the common case, 6 CTAs per SM); KB = 1: k <= 512
+// (BASELINE.json config 5 takes top-500 candidate lists; 2 CTAs per SM).
+//   SEL_CAP   candidate elements per row held in shared memory
+//   SEEN_CAP  seen items of the row staged in shared memory (longer lists stay in global memory)
+//   SORT_N    sort chunk, >= the largest k of the class, power of two
+// One contiguous region of 32-bit words per warp: [key: SEL_CAP][id: SEL_CAP][seen: SEEN_CAP (phase B; reused as the
+// sort chunk of phase E)][top: SORT_N 64-bit, the running top list; phase B borrows it for the seen-item Bloom filter].
+// The coarse cut of rows that captured more than SEL_CAP elements uses the whole region as a keys-only buffer.
+template <int KB>
+struct SelCfg {
+  static constexpr int SEL_CAP = KB ? 2048 : 768;
+  static constexpr int SEEN_CAP = KB ? 1024 : 512;
+  static constexpr int SORT_N = KB ? 512 : 128;
+  static constexpr int SEL_WORDS = 2 * SEL_CAP + SEEN_CAP + 2 * SORT_N;
+  static constexpr int BLOOM_WORDS = 64;                          // 2048-bit Bloom filter over the row's seen ids
+  static constexpr int HIT_CAP = 2 * SORT_N - BLOOM_WORDS;        // candidates the filter flags, verified exactly
+  static_assert(SEEN_CAP * sizeof(int32_t) >= SORT_N * sizeof(unsigned long long), "sort chunk aliases the seen list");
+  static_assert(((2 * SEL_CAP + SEEN_CAP) * 4) % 8 == 0 && (SEL_WORDS * 4) % 16 == 0, "64-bit alignment of the top list");
 };
-static_assert(SEEN_CAP * sizeof(int32_t) >= SORT_N * sizeof(unsigned long long), "sort chunk aliases the seen list");
-static_assert(((2 * SEL_CAP + SEEN_CAP) * 4) % 8 == 0 && (SEL_WORDS * 4) % 16 == 0, "64-bit alignment of the top list");
+static_assert(SelCfg<1>::SORT_N >= MAX_K && SelCfg<0>::SORT_N >= MAX_K_SMALL, "sort chunk covers the k class");
 
-// descending bitonic sort of 128 64-bit keys held in shared memory by one warp
-__device__ __forceinline__ void warp_bitonic_desc_128(unsigned long long* a, uint32_t lane) {
+// descending bitonic sort of N 64-bit keys held in shared memory by one warp
+template <int N>
+__device__ __forceinline__ void warp_bitonic_desc(unsigned long long* a, uint32_t lane) {
 #pragma unroll 1
-  for (int size = 2; size <= SORT_N; size <<= 1) {
+  for (int size = 2; size <= N; size <<= 1) {
 #pragma unroll 1
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
 #pragma unroll
-      for (int r = 0; r < SORT_N / 64; ++r) {
-        const int t = r * 32 + lane;                       // 0..63: one compare-exchange each
+      for (int r = 0; r < N / 64; ++r) {
+        const int t = r * 32 + lane;                       // one compare-exchange each
         const int i = ((t & ~(stride - 1)) << 1) | (t & (stride - 1));
         const int j = i | stride;
         const bool desc = ((i & size) == 0);
@@ -59,11 +68,12 @@ __device__ __forceinline__ void warp_bitonic_desc_128(unsigned long long* a, uin
   }
 }
 // `a` is bitonic (first descending then ascending, or any rotation): make it descending
-__device__ __forceinline__ void warp_bitonic_merge_desc_128(unsigned long long* a, uint32_t lane) {
+template <int N>
+__device__ __forceinline__ void warp_bitonic_merge_desc(unsigned long long* a, uint32_t lane) {
 #pragma unroll 1
-  for (int stride = SORT_N >> 1; stride > 0; stride >>= 1) {
+  for (int stride = N >> 1; stride > 0; stride >>= 1) {
 #pragma unroll
-    for (int r = 0; r < SORT_N / 64; ++r) {
+    for (int r = 0; r < N / 64; ++r) {
       const int t = r * 32 + lane;
       const int i = ((t & ~(stride - 1)) << 1) | (t & (stride - 1));
       const int j = i | stride;
@@ -104,9 +114,10 @@ __device__ __forceinline__ float sum8(float v) {
 //   MODE 1: elements with score >= fmin are written to key[] / id[] (at most SEL_CAP), any order;
 //   MODE 2: their keys only are written to key[0 .. SEL_WORDS) (the warp's whole region);  MODE 0: count only.
 //   Returns how many there are in total.  Scores are compared as floats; -inf never qualifies.
-template <int MODE>
+template <int MODE, int KB>
 __device__ __forceinline__ int scan_groups(const SelectParams& p, int64_t row, const int4 nl, float fmin,
                                            uint32_t* key, uint32_t* id, uint32_t lane) {
+  constexpr int SEL_CAP = SelCfg<KB>::SEL_CAP, SEL_WORDS = SelCfg<KB>::SEL_WORDS;
   int total = 0;
   const float lim = fmaxf(fmin, -3.0e38f);
   // four parallel read streams: the row's four lists, or -- when the two-block filter wrote two lists of
@@ -191,19 +202,30 @@ __device__ __forceinline__ void report_fail(const SelectParams& p, int64_t row, 
   }
 }
 
+// exact membership of global id g32 in the row's sorted seen list staged in shared memory (padded to seen_pow2 with
+// INT_MAX): largest position whose value is <= g32, one conditional add per level (no branches)
+__device__ __forceinline__ bool seen_lookup(const int32_t* seen_s, int seen_pow2, int32_t g32) {
+  int pos = 0;
+  for (int half = seen_pow2 >> 1; half > 0; half >>= 1) pos += (seen_s[pos + half] <= g32) ? half : 0;
+  return seen_s[pos] == g32;
+}
+
 // NJ = float4 chunks of a table row per lane of an 8-lane sub-group: vector path for d <= 32 * NJ, d % 4 == 0.
-// NJ == 0: scalar path for any d (no fused metrics).
-template <int NJ, int DT, bool FULL>
-__global__ void __launch_bounds__(SEL_WARPS * 32, 6)
+// NJ == 0: scalar path for any d (no fused metrics).  NJ == 8 (rows up to d = 256) re-scores one candidate per sub-group
+// and iteration instead of two: the second set of row registers is what used to spill.
+template <int NJ, int DT, bool FULL, int KB>
+__global__ void __launch_bounds__(SEL_WARPS * 32, KB ? 2 : (NJ == 8 ? 4 : 6))
 select_topk_kernel(const SelectParams p) {
+  using Cfg = SelCfg<KB>;
+  constexpr int SEL_CAP = Cfg::SEL_CAP, SEEN_CAP = Cfg::SEEN_CAP, SORT_N = Cfg::SORT_N, SEL_WORDS = Cfg::SEL_WORDS;
+  constexpr bool TWO = NJ != 8;  // candidates per sub-group and re-scoring iteration: two (ra, rb) or one
   extern __shared__ __align__(16) uint8_t sel_smem_raw[];
-  SelSmem* sm = reinterpret_cast<SelSmem*>(sel_smem_raw);
   const int w = threadIdx.x >> 5;
   const uint32_t lane = lane_id();
   const uint32_t lt = lanemask_lt();
   const int64_t row = (int64_t)blockIdx.x * SEL_WARPS + w;
   if (row >= p.nU) return;
-  uint32_t* key = sm->w[w];
+  uint32_t* key = reinterpret_cast<uint32_t*>(sel_smem_raw) + (size_t)w * SEL_WORDS;
   uint32_t* id = key + SEL_CAP;
   int32_t* seen_s = reinterpret_cast<int32_t*>(key + 2 * SEL_CAP);
   unsigned long long* top = reinterpret_cast<unsigned long long*>(key + 2 * SEL_CAP + SEEN_CAP);
@@ -241,7 +263,7 @@ select_topk_kernel(const SelectParams p) {
   uint32_t thr_key = (thr == -INFINITY) ? 0u : f32_to_key(__float_as_uint(thr + 0.0f));  // effective capture threshold
 
   // ---- A: enumerate ----
-  int ne = scan_groups<1>(p, row, nl, thr, key, id, lane);
+  int ne = scan_groups<1, KB>(p, row, nl, thr, key, id, lane);
   if (ne > SEL_CAP) {
     // coarse cut: X = a lower bound of the need-th largest captured score, need = k + seen_u  =>  the k-th best
     // unmasked score is >= X, nothing below X - 2 delta can reach the top-k: the capture threshold is raised to it
@@ -253,7 +275,7 @@ select_topk_kernel(const SelectParams p) {
       // the captured keys fit the warp's shared region: ONE more pass over the lists, then bisect in shared memory
       // (large catalogues leave up to 4 x 512 groups per row; bisecting with passes over global memory cost 7 ms
       // per 65 536 rows on a 1.25M-item shard)
-      scan_groups<2>(p, row, nl, thr, key, id, lane);
+      scan_groups<2, KB>(p, row, nl, thr, key, id, lane);
       uint32_t kmin = 0xffffffffu, kmax = 0;
       for (int i = lane; i < ne; i += 32) { const uint32_t kk = key[i]; kmin = min(kmin, kk); kmax = max(kmax, kk); }
       kmin = __reduce_min_sync(0xffffffffu, kmin);
@@ -282,7 +304,7 @@ select_topk_kernel(const SelectParams p) {
       uint32_t lo = thr_key > KEY_NEG_INF ? thr_key : KEY_NEG_INF + 1, hi = 0xff800000u;  // hi: above every finite key
       while (hi - lo > 1) {
         const uint32_t mid = lo + ((hi - lo) >> 1);
-        const int c = scan_groups<0>(p, row, nl, __uint_as_float(key_to_f32(mid)), key, id, lane);
+        const int c = scan_groups<0, KB>(p, row, nl, __uint_as_float(key_to_f32(mid)), key, id, lane);
         if (c >= need) lo = mid; else hi = mid;
       }
       const float X = __uint_as_float(key_to_f32(lo));
@@ -292,27 +314,64 @@ select_topk_kernel(const SelectParams p) {
     // does not raise the threshold means the row really holds too many near-ties
     if (cut_key <= thr_key) { report_fail(p, row, lane, 1); return; }
     thr_key = cut_key;
-    ne = scan_groups<1>(p, row, nl, __uint_as_float(key_to_f32(thr_key)), key, id, lane);
+    ne = scan_groups<1, KB>(p, row, nl, __uint_as_float(key_to_f32(thr_key)), key, id, lane);
     if (ne > SEL_CAP) { report_fail(p, row, lane, 1); return; }
   }
 
-  // ---- B: seen-item mask (each candidate looked up in the row's sorted seen list) ----
+  // ---- B: seen-item mask ----
+  // Rows whose seen list is staged in shared memory: a 2048-bit Bloom filter over the seen ids (one bit per id, built in
+  // the not-yet-used top-list area) clears most candidates with one shared load; the few it flags (true members plus
+  // ~seen_u / 2048 of the rest) are compacted and verified by the exact search.  Before: every candidate ran the full
+  // fixed-depth search, 14 % of the kernel's instructions.
   if (seen_u > 0) {
-    for (int i = lane; i < ne; i += 32) {
-      const int64_t gid = (int64_t)id[i] + p.item_id_offset;
-      if (seen_in_smem) {
-        const int32_t g32 = (int32_t)gid;  // seen ids are int32
-        // largest position whose value is <= g32, found with one conditional add per level (no branches)
-        int pos = 0;
-        for (int half = seen_pow2 >> 1; half > 0; half >>= 1) pos += (seen_s[pos + half] <= g32) ? half : 0;
-        if (seen_s[pos] == g32 && gid < 0x7fffffffLL) key[i] = 0;
-      } else {
-        int64_t lo = 0, hi = seen_u;
-        while (lo < hi) {
-          const int64_t mid = (lo + hi) >> 1;
-          if ((int64_t)__ldg(p.seen_items + s0 + mid) < gid) lo = mid + 1; else hi = mid;
+    const int32_t off32 = (int32_t)p.item_id_offset;
+    const bool ids32 = p.item_id_offset >= 0 && p.item_id_offset + (int64_t)p.nI < 0x7fffffffLL;  // global ids fit int32 (seen ids do)
+    bool done = false;
+    if (seen_in_smem && ids32) {
+      uint32_t* bloom = reinterpret_cast<uint32_t*>(top);
+      uint32_t* hits = bloom + Cfg::BLOOM_WORDS;
+      bloom[lane] = 0u;
+      bloom[lane + 32] = 0u;
+      __syncwarp();
+      for (int i = lane; i < (int)seen_u; i += 32) {
+        const uint32_t g = (uint32_t)seen_s[i];
+        atomicOr(&bloom[(g >> 5) & (Cfg::BLOOM_WORDS - 1)], 1u << (g & 31u));
+      }
+      __syncwarp();
+      int nh = 0;
+      for (int base = 0; base < ne; base += 32) {
+        const int i = base + lane;
+        bool hit = false;
+        if (i < ne) {
+          const uint32_t g = id[i] + (uint32_t)off32;
+          hit = (bloom[(g >> 5) & (Cfg::BLOOM_WORDS - 1)] >> (g & 31u)) & 1u;
         }
-        if (lo < seen_u && (int64_t)__ldg(p.seen_items + s0 + lo) == gid) key[i] = 0;
+        const uint32_t hb = __ballot_sync(0xffffffffu, hit);
+        if (hit) { const int slot = nh + __popc(hb & lt); if (slot < Cfg::HIT_CAP) hits[slot] = (uint32_t)i; }
+        nh += __popc(hb);
+      }
+      __syncwarp();
+      if (nh <= Cfg::HIT_CAP) {
+        for (int j = lane; j < nh; j += 32) {
+          const uint32_t i = hits[j];
+          if (seen_lookup(seen_s, seen_pow2, (int32_t)(id[i] + (uint32_t)off32))) key[i] = 0;
+        }
+        done = true;
+      }
+    }
+    if (!done) {
+      for (int i = lane; i < ne; i += 32) {
+        const int64_t gid = (int64_t)id[i] + p.item_id_offset;
+        if (seen_in_smem) {
+          if (gid < 0x7fffffffLL && seen_lookup(seen_s, seen_pow2, (int32_t)gid)) key[i] = 0;  // seen ids are int32
+        } else {
+          int64_t lo = 0, hi = seen_u;
+          while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if ((int64_t)__ldg(p.seen_items + s0 + mid) < gid) lo = mid + 1; else hi = mid;
+          }
+          if (lo < seen_u && (int64_t)__ldg(p.seen_items + s0 + lo) == gid) key[i] = 0;
+        }
       }
     }
   }
@@ -390,39 +449,70 @@ select_topk_kernel(const SelectParams p) {
       ur[j] = (FULL || c4 < nvec) ? ld4<DT>(p.U, row, d, c4) : make_float4(0.f, 0.f, 0.f, 0.f);
       acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    for (int r0 = 0; r0 < nr; r0 += 8) {
-      const int ra = r0 + grp, rb = r0 + 4 + grp;
-      const uint32_t ia = id[min(ra, nr - 1)], ib = id[min(rb, nr - 1)];
-      float4 va[NJ > 0 ? NJ : 1], vb[NJ > 0 ? NJ : 1];
-#pragma unroll
-      for (int j = 0; j < NJ; ++j) {
-        const int c4 = sub + 8 * j;
-        if (FULL || 8 * j < nvec) {
-          va[j] = (FULL || c4 < nvec) ? ld4<DT>(p.V, ia, d, c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-          vb[j] = (FULL || c4 < nvec) ? ld4<DT>(p.V, ib, d, c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      }
-      float sa = 0.f, sb = 0.f;
-#pragma unroll
-      for (int j = 0; j < NJ; ++j) {
-        if (FULL || 8 * j < nvec) { sa = dot4(ur[j], va[j], sa); sb = dot4(ur[j], vb[j], sb); }
-      }
-      sa = sum8(sa); sb = sum8(sb);
-      if (want_ild) {
-        const float ia_n = ra < nr ? __ldg(p.inv_norm_v + ia) : 0.f, ib_n = rb < nr ? __ldg(p.inv_norm_v + ib) : 0.f;
+    if (TWO) {
+      for (int r0 = 0; r0 < nr; r0 += 8) {
+        const int ra = r0 + grp, rb = r0 + 4 + grp;
+        const uint32_t ia = id[min(ra, nr - 1)], ib = id[min(rb, nr - 1)];
+        float4 va[NJ > 0 ? NJ : 1], vb[NJ > 0 ? NJ : 1];
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
+          const int c4 = sub + 8 * j;
           if (FULL || 8 * j < nvec) {
-            acc[j].x = fmaf(va[j].x, ia_n, acc[j].x); acc[j].y = fmaf(va[j].y, ia_n, acc[j].y);
-            acc[j].z = fmaf(va[j].z, ia_n, acc[j].z); acc[j].w = fmaf(va[j].w, ia_n, acc[j].w);
-            acc[j].x = fmaf(vb[j].x, ib_n, acc[j].x); acc[j].y = fmaf(vb[j].y, ib_n, acc[j].y);
-            acc[j].z = fmaf(vb[j].z, ib_n, acc[j].z); acc[j].w = fmaf(vb[j].w, ib_n, acc[j].w);
+            va[j] = (FULL || c4 < nvec) ? ld4<DT>(p.V, ia, d, c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            vb[j] = (FULL || c4 < nvec) ? ld4<DT>(p.V, ib, d, c4) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
+        float sa = 0.f, sb = 0.f;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          if (FULL || 8 * j < nvec) { sa = dot4(ur[j], va[j], sa); sb = dot4(ur[j], vb[j], sb); }
+        }
+        sa = sum8(sa); sb = sum8(sb);
+        if (want_ild) {
+          const float ia_n = ra < nr ? __ldg(p.inv_norm_v + ia) : 0.f, ib_n = rb < nr ? __ldg(p.inv_norm_v + ib) : 0.f;
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) {
+            if (FULL || 8 * j < nvec) {
+              acc[j].x = fmaf(va[j].x, ia_n, acc[j].x); acc[j].y = fmaf(va[j].y, ia_n, acc[j].y);
+              acc[j].z = fmaf(va[j].z, ia_n, acc[j].z); acc[j].w = fmaf(va[j].w, ia_n, acc[j].w);
+              acc[j].x = fmaf(vb[j].x, ib_n, acc[j].x); acc[j].y = fmaf(vb[j].y, ib_n, acc[j].y);
+              acc[j].z = fmaf(vb[j].z, ib_n, acc[j].z); acc[j].w = fmaf(vb[j].w, ib_n, acc[j].w);
+            }
+          }
+        }
+        if (sub == 0) {
+          if (ra < nr) key[ra] = f32_to_key(__float_as_uint(sa + 0.0f));
+          if (rb < nr) key[rb] = f32_to_key(__float_as_uint(sb + 0.0f));
+        }
       }
-      if (sub == 0) {
-        if (ra < nr) key[ra] = f32_to_key(__float_as_uint(sa + 0.0f));
-        if (rb < nr) key[rb] = f32_to_key(__float_as_uint(sb + 0.0f));
+    } else {
+      // same lane layout and per-lane fma chain as above (bit-identical scores), one candidate per sub-group
+      for (int r0 = 0; r0 < nr; r0 += 4) {
+        const int ra = r0 + grp;
+        const uint32_t ia = id[min(ra, nr - 1)];
+        float4 va[NJ > 0 ? NJ : 1];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          const int c4 = sub + 8 * j;
+          if (FULL || 8 * j < nvec) va[j] = (FULL || c4 < nvec) ? ld4<DT>(p.V, ia, d, c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        float sa = 0.f;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          if (FULL || 8 * j < nvec) sa = dot4(ur[j], va[j], sa);
+        }
+        sa = sum8(sa);
+        if (want_ild) {
+          const float ia_n = ra < nr ? __ldg(p.inv_norm_v + ia) : 0.f;
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) {
+            if (FULL || 8 * j < nvec) {
+              acc[j].x = fmaf(va[j].x, ia_n, acc[j].x); acc[j].y = fmaf(va[j].y, ia_n, acc[j].y);
+              acc[j].z = fmaf(va[j].z, ia_n, acc[j].z); acc[j].w = fmaf(va[j].w, ia_n, acc[j].w);
+            }
+          }
+        }
+        if (sub == 0 && ra < nr) key[ra] = f32_to_key(__float_as_uint(sa + 0.0f));
       }
     }
   } else {
@@ -436,7 +526,7 @@ select_topk_kernel(const SelectParams p) {
   }
   __syncwarp();
 
-  // ---- E: exact top-k by (E desc, id asc): composite keys are unique, sort chunks of 128 and merge ----
+  // ---- E: exact top-k by (E desc, id asc): composite keys are unique, sort chunks of SORT_N and merge ----
   for (int c0 = 0; c0 < nr || c0 == 0; c0 += SORT_N) {
     unsigned long long* dst = c0 == 0 ? top : chunk;
     for (int i = lane; i < SORT_N; i += 32) {
@@ -449,14 +539,14 @@ select_topk_kernel(const SelectParams p) {
       dst[i] = c;
     }
     __syncwarp();
-    warp_bitonic_desc_128(dst, lane);
+    warp_bitonic_desc<SORT_N>(dst, lane);
     if (c0 > 0) {
       for (int i = lane; i < SORT_N; i += 32) {
         const unsigned long long a = top[i], b = chunk[SORT_N - 1 - i];
         top[i] = a > b ? a : b;
       }
       __syncwarp();
-      warp_bitonic_merge_desc_128(top, lane);
+      warp_bitonic_merge_desc<SORT_N>(top, lane);
     }
   }
   int kv = 0;  // valid results of the row
@@ -478,7 +568,7 @@ select_topk_kernel(const SelectParams p) {
     // fused cosine ILD: sum_{a<b} cos = (|sum e|^2 - kv) / 2 over the winners.  acc holds the sum over ALL
     // re-scored candidates; subtract the few that did not make the top-k.
     kv = __reduce_add_sync(0xffffffffu, kv);
-    const unsigned long long kth = k <= SORT_N ? top[k - 1] : 0ull;  // smallest winning composite (0 when fewer than k)
+    const unsigned long long kth = top[k - 1];  // smallest winning composite (0 when fewer than k)
     const int nvec = d >> 2;
     const int sub = lane & 7, grp = lane >> 3;
     // list the losers (lane per candidate), reusing the front of key[] (the scores are no longer needed)
@@ -651,25 +741,33 @@ cudaError_t launch_topk_merge_packed(const uint64_t* g, int n_shards, int64_t nU
 }
 
 cudaError_t launch_select_topk(const SelectParams& p, cudaStream_t stream) {
-  const size_t smem = sizeof(SelSmem);
   const int64_t grid = (p.nU + SEL_WARPS - 1) / SEL_WARPS;
   const bool vec = (p.d & 3) == 0 && p.d <= 256;  // wider rows take the scalar path (no fused metrics)
+  const bool big = p.k > MAX_K_SMALL;             // k class: larger per-warp buffers, 2 CTAs per SM
   cudaError_t e;
-#define DIVREC_LAUNCH_SELECT(NJ, DT, FULL)                                                                               \
-  do {                                                                                                                   \
-    e = cudaFuncSetAttribute(select_topk_kernel<NJ, DT, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
-    if (e != cudaSuccess) return e;                                                                                      \
-    select_topk_kernel<NJ, DT, FULL><<<(unsigned)grid, SEL_WARPS * 32, smem, stream>>>(p);                               \
+#define DIVREC_LAUNCH_SELECT(NJ, DT, FULL, KB)                                                                              \
+  do {                                                                                                                      \
+    const size_t smem = (size_t)SEL_WARPS * SelCfg<KB>::SEL_WORDS * sizeof(uint32_t);                                       \
+    e = cudaFuncSetAttribute(select_topk_kernel<NJ, DT, FULL, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if (e != cudaSuccess) return e;                                                                                         \
+    select_topk_kernel<NJ, DT, FULL, KB><<<(unsigned)grid, SEL_WARPS * 32, smem, stream>>>(p);                              \
   } while (0)
-  if (!vec) DIVREC_LAUNCH_SELECT(0, 0, false);
-  else if (p.dtype == 0 && p.d == 128) DIVREC_LAUNCH_SELECT(4, 0, true);   // the common full-row shapes get branch-free loads
-  else if (p.dtype == 0 && p.d <= 128) DIVREC_LAUNCH_SELECT(4, 0, false);
-  else if (p.dtype == 0 && p.d == 256) DIVREC_LAUNCH_SELECT(8, 0, true);
-  else if (p.dtype == 0) DIVREC_LAUNCH_SELECT(8, 0, false);
-  else if (p.d == 128) DIVREC_LAUNCH_SELECT(4, 1, true);
-  else if (p.d <= 128) DIVREC_LAUNCH_SELECT(4, 1, false);
-  else if (p.d == 256) DIVREC_LAUNCH_SELECT(8, 1, true);
-  else DIVREC_LAUNCH_SELECT(8, 1, false);
+  if (big) {
+    if (!vec) DIVREC_LAUNCH_SELECT(0, 0, false, 1);
+    else if (p.dtype == 0 && p.d <= 128) DIVREC_LAUNCH_SELECT(4, 0, false, 1);
+    else if (p.dtype == 0) DIVREC_LAUNCH_SELECT(8, 0, false, 1);
+    else if (p.d <= 128) DIVREC_LAUNCH_SELECT(4, 1, false, 1);
+    else DIVREC_LAUNCH_SELECT(8, 1, false, 1);
+  }
+  else if (!vec) DIVREC_LAUNCH_SELECT(0, 0, false, 0);
+  else if (p.dtype == 0 && p.d == 128) DIVREC_LAUNCH_SELECT(4, 0, true, 0);   // the common full-row shapes get branch-free loads
+  else if (p.dtype == 0 && p.d <= 128) DIVREC_LAUNCH_SELECT(4, 0, false, 0);
+  else if (p.dtype == 0 && p.d == 256) DIVREC_LAUNCH_SELECT(8, 0, true, 0);
+  else if (p.dtype == 0) DIVREC_LAUNCH_SELECT(8, 0, false, 0);
+  else if (p.d == 128) DIVREC_LAUNCH_SELECT(4, 1, true, 0);
+  else if (p.d <= 128) DIVREC_LAUNCH_SELECT(4, 1, false, 0);
+  else if (p.d == 256) DIVREC_LAUNCH_SELECT(8, 1, true, 0);
+  else DIVREC_LAUNCH_SELECT(8, 1, false, 0);
 #undef DIVREC_LAUNCH_SELECT
   count_launch();
   return cudaGetLastError();

@@ -19,7 +19,7 @@ LIB_PATH = os.path.join(_PKG_DIR, "libdivrec_b200.so")
 DIVREC_F32, DIVREC_BF16 = 0, 1
 MODE_TENSOR, MODE_SIMT = 0, 2
 ILD_SUMVEC, ILD_PAIRWISE = 0, 1
-MAX_K = 128
+MAX_K = 512
 
 _c = ctypes
 _vp, _i64, _i32, _f32, _sz = _c.c_void_p, _c.c_int64, _c.c_int, _c.c_float, _c.c_size_t
@@ -144,16 +144,21 @@ _ws_cache = {}
 
 
 def _workspace(nbytes: int, dev) -> torch.Tensor:
-    """One cached byte buffer per device, grown on demand (1024-byte aligned by the allocator)."""
+    """One cached byte buffer per device, grown on demand, handed out as a 1024-byte aligned view.
+    The buffer is shared by every call on the device: calls must be issued on ONE stream at a time (the wrappers use
+    the current stream; callers that overlap streams bring their own workspace through the C ABI)."""
     key = (dev.index if dev.index is not None else torch.cuda.current_device())
     buf = _ws_cache.get(key)
-    if buf is None or buf.numel() < nbytes:
+    # the caching allocator only guarantees 512-byte alignment: keep room for the worst-case offset of the aligned view
+    if buf is None or buf.numel() < nbytes + 1024:
         buf = None
         _ws_cache.pop(key, None)
         buf = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
         _ws_cache[key] = buf
     off = (-buf.data_ptr()) % 1024
-    return buf[off:off + nbytes]
+    view = buf[off:off + nbytes]
+    assert view.numel() == nbytes
+    return view
 
 
 def score_topk(U: torch.Tensor, V: torch.Tensor, k: int, seen_rowptr: Optional[torch.Tensor] = None,
@@ -203,10 +208,14 @@ def score_topk_metrics(U: torch.Tensor, V: torch.Tensor, k: int, seen_rowptr: Op
     U = _cuda(U, "U")
     V = _cuda(V, "V", U.dtype)
     dt = _table_dtype(U)
+    if U.dim() != 2 or V.dim() != 2 or U.shape[1] != V.shape[1]:
+        raise ValueError("U and V must be [n,d] with the same d")
     nU, d = U.shape
     nI = V.shape[0]
     if seen_rowptr is not None:
         seen_rowptr = _cuda(seen_rowptr, "seen_rowptr", torch.int64)
+        if seen_rowptr.numel() != nU + 1:
+            raise ValueError("seen_rowptr must have nU + 1 entries")
         if seen_items is not None:
             seen_items = _cuda(seen_items, "seen_items", torch.int32)
             if seen_items.numel() == 0:

@@ -26,7 +26,11 @@ def interactions_to_csr(interactions: Optional[torch.Tensor], n_users: int) -> T
     if interactions is None or interactions.numel() == 0:
         dev = interactions.device if interactions is not None else "cpu"
         return torch.zeros(n_users + 1, dtype=torch.int64, device=dev), torch.zeros(0, dtype=torch.int32, device=dev)
-    pairs = torch.unique(interactions.to(torch.int64), dim=0)
+    pairs = interactions.to(torch.int64)
+    # users outside [0, n_users) have no row here (a frozen / train set may hold users the scored set never mentions:
+    # the reference filters `frozen` per user, base_datasets.py:145-147)
+    pairs = pairs[(pairs[:, 0] >= 0) & (pairs[:, 0] < n_users)]
+    pairs = torch.unique(pairs, dim=0)
     counts = torch.bincount(pairs[:, 0], minlength=n_users)
     rowptr = torch.zeros(n_users + 1, dtype=torch.int64, device=pairs.device)
     rowptr[1:] = torch.cumsum(counts, 0)

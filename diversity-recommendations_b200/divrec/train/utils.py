@@ -26,6 +26,13 @@ def _model_device(model: torch.nn.Module) -> torch.device:
     return torch.device("cuda", torch.cuda.current_device())
 
 
+def _dataset_users(dataset, model) -> int:
+    n_users = int(dataset.data.number_of_users)
+    if n_users > model.no_users:
+        raise IndexError(f"dataset has {n_users} users but the model's user table has {model.no_users} rows")
+    return n_users
+
+
 def _reduce_all(losses, chunks):
     return [loss.reduce_loss_values(torch.concatenate(chunks[i])) for i, loss in enumerate(losses)]
 
@@ -62,8 +69,10 @@ def get_model_recommendations(dataset: RankingDataset, model: RankingModel, numb
         raise TypeError("divrec_b200 computes on a B200 only: move the model with .to('cuda')")
     k = int(number_of_recommendations)
     if isinstance(model, MatrixFactorization):
+        # one row per DATASET user, as the reference's loop over RankingDataset yields (the model's table may be larger)
+        n_users = _dataset_users(dataset, model)
         rowptr, items = dataset.seen_csr(dev)
-        recs, _ = model.recommend(k, rowptr, items if items.numel() else None)
+        recs, _ = model.recommend(k, rowptr, items if items.numel() else None, user_range=(0, n_users))
         return recs
     # generic RankingModel: score each user's candidates with the model, rank on the device
     out = []
@@ -101,8 +110,9 @@ def recommendations_score_loop(dataset: RankingDataset, model: RankingModel, los
         return [loss(interactions, recommendations) for loss in losses]
     with torch.no_grad():
         rowptr, items = dataset.seen_csr(dev)
+        n_users = _dataset_users(dataset, model)
         _scores, recommendations, ild, counts = _native.score_topk_metrics(
-            model.user_embeddings.weight, model.item_embeddings.weight, k, rowptr, items if items.numel() else None,
+            model.user_embeddings.weight[:n_users], model.item_embeddings.weight, k, rowptr, items if items.numel() else None,
             want_ild="ild" in fused.values(), want_coverage="entropy" in fused.values())
     out = []
     for i, loss in enumerate(losses):
@@ -274,12 +284,13 @@ def host_recommend_and_score(U_host: torch.Tensor, V_host: torch.Tensor, seen_ro
             "counts_h": torch.empty(nI, dtype=torch.int32).pin_memory(),
             "ent_h": torch.empty(2, dtype=torch.float32).pin_memory(),
             "bounds": bounds,
-            "rp_list": seen_rowptr_host.tolist() if len(bounds) > 2 else None,
             "s_in": torch.cuda.Stream(dev), "s_out": torch.cuda.Stream(dev),
         }
         _host_pipe.clear()
         _host_pipe[key] = st
     bounds = st["bounds"]
+    # seen-item ranges of the user ranges, from THIS call's row pointers (the cached state is keyed on shapes only)
+    rp_at = [int(seen_rowptr_host[b]) for b in bounds]
     main = torch.cuda.current_stream(dev)
     s_in, s_out = st["s_in"], st["s_out"]
     s_in.wait_stream(main)
@@ -296,7 +307,7 @@ def host_recommend_and_score(U_host: torch.Tensor, V_host: torch.Tensor, seen_ro
             st["U"][a:b].copy_(U_host[a:b], non_blocking=True)
             h2d += (b - a) * d * U_host.element_size()
             if seen_items_host.numel():
-                lo, hi = (st["rp_list"][a], st["rp_list"][b]) if st["rp_list"] is not None else (0, seen_items_host.numel())
+                lo, hi = rp_at[c], rp_at[c + 1]
                 if hi > lo:
                     st["it"][lo:hi].copy_(seen_items_host[lo:hi], non_blocking=True)
                     h2d += (hi - lo) * 4

@@ -76,13 +76,18 @@ def test_score_topk_vs_reference_golden(native, dev, name, exact):
     (300, 1000, 64, 10, 3000, "grid"),
     (257, 1300, 128, 100, 20000, "grid"),     # nU, nI not multiples of the 128-wide tiles
     (129, 127, 32, 16, 500, "grid"),          # fewer items than one tile, d < 64
-    (64, 5000, 100, 128, 10000, "grid"),      # d not a multiple of 64, k = MAX_K
+    (64, 5000, 100, 128, 10000, "grid"),      # d not a multiple of 64, k = the small-k class limit
     (500, 26744, 128, 100, 60000, "gauss"),   # cfg2 catalogue
     (200, 3000, 48, 7, 0, "gauss"),           # no interactions at all
     (1, 300, 16, 5, 10, "grid"),              # a single user
     (128, 4096, 8, 1, 0, "grid"),             # exact tile multiples, tiny d, k = 1
     (300, 6000, 192, 64, 9000, "gauss"),      # d = 192: three k-blocks -> the one-block-per-CTA kernel
     (150, 5000, 512, 32, 0, "gauss"),         # d = 512: the widest tensor-core shape (two accumulator stages)
+    (300, 26744, 128, 500, 40000, "gauss"),   # k = 500 (BASELINE.json config 5's candidate lists): the large-k buffers
+    (130, 9000, 128, 500, 20000, "grid"),     # k = 500 with exact ties
+    (90, 3000, 256, 300, 4000, "gauss"),      # k > 128 on the one-block kernel (d = 256)
+    (70, 2000, 50, 512, 0, "grid"),           # k = MAX_K, scalar re-scoring path (d % 4 != 0), catalogue without a hint
+    (1500, 60000, 128, 100, 150000, "gauss"), # 469 item tiles: threshold-ladder checkpoints every 59 tiles
 ])
 def test_score_topk_vs_oracle(native, dev, nU, nI, d, k, nnz, kind):
     gen = torch.Generator().manual_seed(nU * 7 + nI)
@@ -127,6 +132,18 @@ def test_all_scores_equal_ties_broken_by_lowest_id(native, dev):
     s, i = native.score_topk(U.to(dev), V.to(dev), 10, rowptr.to(dev), items.to(dev))
     expect = torch.stack([torch.arange(u, u + 10) for u in range(70)])
     assert torch.equal(i.cpu(), expect) and (s.cpu() == 64.0).all()
+
+
+def test_simt_mode_large_k(native, dev):
+    """k = 400 through the exact SIMT kernel (rescue path: 512-entry sort buffer)."""
+    gen = torch.Generator().manual_seed(43)
+    nU, nI, d, k = 40, 5000, 64, 400
+    U, V = O.make_embeddings(nU, d, "grid", gen), O.make_embeddings(nI, d, "grid", gen)
+    seen = O.make_seen(nU, nI, 3000, gen)
+    rowptr, items = O.seen_csr(seen, nU)
+    o_i, o_s = O.recommendations_dense(U, V, rowptr, items, k)
+    s, i = native.score_topk(U.to(dev), V.to(dev), k, rowptr.to(dev), items.to(dev), mode=native.MODE_SIMT)
+    assert torch.equal(i.cpu(), o_i) and torch.equal(s.cpu(), o_s)
 
 
 @pytest.mark.parametrize("kind", ["grid", "gauss"])
