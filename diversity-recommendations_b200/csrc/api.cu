@@ -73,7 +73,7 @@ struct WsLayout {
   bool convA, convB;  // operands have to be rewritten into the workspace (fp32 -> fp16, or bf16 padding)
   int64_t chunk;
   int rescue_grid;
-  size_t offA, offB, offNormU, offInvV, offListS, offListI, offCounts, offThr, offFail, offScalars, offRescue, offHintMask, total;
+  size_t offA, offB, offNormU, offInvV, offListS, offCounts, offThr, offFail, offScalars, offRescue, offHintMask, total;
   bool two_blocks;
 };
 static WsLayout ws_layout(int64_t nU, int64_t nI, int d, int dtype, int k) {
@@ -91,8 +91,7 @@ static WsLayout ws_layout(int64_t nU, int64_t nI, int d, int dtype, int k) {
   w.offB = off; if (w.convB) off += align_up((size_t)nI * w.K * 2, 1024);
   w.offNormU = off; off += align_up(cpad * sizeof(float), 1024);
   w.offInvV = off; off += align_up((size_t)nI * sizeof(float), 1024);
-  w.offListS = off; off += align_up(cpad * LISTS_PER_ROW * w.cap * GROUP * sizeof(float), 1024);
-  w.offListI = off; off += align_up(cpad * LISTS_PER_ROW * w.cap * sizeof(uint32_t), 1024);
+  w.offListS = off; off += align_up(cpad * LISTS_PER_ROW * w.cap * REC_FLOATS * sizeof(float), 1024);
   w.offCounts = off; off += align_up(cpad * LISTS_PER_ROW * sizeof(int32_t), 1024);
   w.offThr = off; off += align_up(cpad * LISTS_PER_ROW * sizeof(float), 1024);
   w.offFail = off; off += align_up(cpad * sizeof(int32_t), 1024);
@@ -210,8 +209,7 @@ static int score_topk_impl(const void* U, const void* V, int64_t nU, int64_t nI,
     SelectParams sp{};
     sp.nU = cu; sp.nI = (int32_t)nI; sp.k = k; sp.d = d; sp.dtype = dtype; sp.cap = w.cap;
     sp.U = Uc; sp.V = V;
-    sp.list_scores = reinterpret_cast<float*>(ws + w.offListS);
-    sp.list_item0 = reinterpret_cast<uint32_t*>(ws + w.offListI);
+    sp.lists = reinterpret_cast<float*>(ws + w.offListS);
     sp.list_count = reinterpret_cast<int32_t*>(ws + w.offCounts);
     sp.thr = reinterpret_cast<float*>(ws + w.offThr);
     sp.seen_rowptr = rp; sp.seen_items = seen_items; sp.item_id_offset = item_id_offset;
@@ -220,6 +218,7 @@ static int score_topk_impl(const void* U, const void* V, int64_t nU, int64_t nI,
     sp.fail_rows = reinterpret_cast<int32_t*>(ws + w.offFail); sp.fail_count = fail_count;
     sp.fail_reasons = reinterpret_cast<int32_t*>(scal) + 8;
     sp.force_fail = tensor ? 0 : 1;
+    sp.id_bytes = rec_id_bytes(nI);
     const bool no_rescue = debug_env("DIVREC_DEBUG_NO_RESCUE") != nullptr;  // debugging aid: leave uncertified rows undone
     sp.debug_dump = no_rescue ? 1 : 0;
     sp.out_ild = out_ild ? out_ild + u0 : nullptr; sp.coverage = coverage;
@@ -251,8 +250,7 @@ static int score_topk_impl(const void* U, const void* V, int64_t nU, int64_t nI,
       FilterParams fp{};
       fp.nU = cu; fp.nI = (int32_t)nI; fp.kblocks = w.K / 64; fp.fmt = dtype == DIVREC_F32 ? 0 : 1; fp.k = k;
       fp.use_hint = 1; fp.cap = w.cap; fp.seen_rowptr = rp; fp.debug_mode = g_debug_mode.load(); fp.stats = g_filter_stats.load();
-      fp.list_scores = reinterpret_cast<float*>(ws + w.offListS);
-      fp.list_item0 = reinterpret_cast<uint32_t*>(ws + w.offListI);
+      fp.lists = reinterpret_cast<float*>(ws + w.offListS);
       fp.list_count = reinterpret_cast<int32_t*>(ws + w.offCounts);
       fp.thr_out = reinterpret_cast<float*>(ws + w.offThr);
       fp.norms_u = norms_u; fp.nvmax_bits = nvmax; fp.amax_bits = sp.amax_bits; fp.scale_exps = sp.scale_exps;

@@ -12,6 +12,13 @@ constexpr int LIST_CAP = 256;        // candidate groups per list; a user row ow
 constexpr int LIST_CAP_MAX = 512;    // ... and for catalogues that tighten lists online (fewer, larger tightenings)
 constexpr int LISTS_PER_ROW = 4;     // (column half of a tile) x (tile parity)
 constexpr int GROUP = 8;             // consecutive item columns appended together
+constexpr int REC_FLOATS = GROUP;    // one candidate record = 32 bytes = ONE 256-bit store: the GROUP fp32 scores, whose low mantissa
+                                     // bytes carry the group's index (first item id / GROUP): byte j of the index in score j, for
+                                     // j < id_bytes (2 below 2^19 items, else 4).  The epilogue of the filter is instruction- and
+                                     // store-bound: a separate id store per append cost a second L2 transaction and its address
+                                     // arithmetic.  The carried scores are off by < 2^-15 relative, which the certification
+                                     // margin absorbs (REC_ID_SLACK, select_topk.cu).
+constexpr float REC_ID_SLACK = 3.0f / 32768.0f;  // 3 eps, eps = 2^-15 |u||v|: added to 2 delta wherever record scores are compared
 constexpr int N_SAMPLE = 16;         // item tiles scored first to seed the per-row threshold hint
 constexpr int HINT_MIN_TILES = 32;   // catalogues with fewer 128-item tiles keep every group (no hint)
 constexpr int TIGHTEN_MIN_ITEMS = 500000;  // catalogues at least this large use the filter variant that tightens lists online
@@ -46,8 +53,7 @@ struct FilterParams {
   const void* a16;             // [nU, K] 16-bit user plane (read row-wise into TMEM)
   long long* stats;            // [grid][8] MMA-issuer cycles: total, blocked on A, on accumulators, on B; [4] tightening events, [5] their cycles (null = off)
   const int64_t* seen_rowptr;  // [nU+1] or null (only the per-row counts are used here)
-  float* list_scores;          // [nU_pad][4][cap][GROUP]  tensor-core scores (scaled units)
-  uint32_t* list_item0;        // [nU_pad][4][cap]         local id of the first item of each group
+  float* lists;                // [nU_pad][4][cap][REC_FLOATS]  candidate records: tensor-core scores (scaled units) carrying the group index
   int32_t* list_count;         // [nU_pad][4]              groups appended; cap + 1 = overflow
   float* thr_out;              // [nU_pad][4]              final capture threshold of each list (scaled units, -inf = none)
   // error-bound inputs (the 2 delta margin of list tightening; same values as SelectParams)
@@ -64,6 +70,7 @@ struct FilterParams {
   int ladder_stride;           // set by the launcher: tiles between threshold-ladder checkpoints (0 = no ladder)
 };
 
+__host__ __device__ inline int rec_id_bytes(int64_t nI) { return nI < (int64_t)GROUP * 65536 ? 2 : 4; }
 int score_filter_b_stages(int kblocks);
 size_t score_filter_smem_bytes(int kblocks);
 cudaError_t launch_score_filter(const void* A16, const void* B16, FilterParams p, int sm_count,
@@ -91,8 +98,7 @@ struct SelectParams {
   int k, d, dtype, cap;
   const void* U;               // original tables (fp32 or bf16) for the exact re-scoring
   const void* V;
-  const float* list_scores;
-  const uint32_t* list_item0;
+  const float* lists;          // candidate records written by the filter (REC_FLOATS floats each)
   const int32_t* list_count;
   const float* thr;
   const int64_t* seen_rowptr;
@@ -109,6 +115,7 @@ struct SelectParams {
   int32_t* fail_rows;          // [nU] rows the tensor-core path could not certify
   int32_t* fail_count;         // device counter (zeroed by the caller)
   int32_t* fail_reasons;       // device [4] statistics by reason (see report_fail), may be null
+  int id_bytes;                // low mantissa bytes of a record that carry the group index (2 or 4; set from nI by the launcher)
   int merged_lists;            // 1 = lists written by launch_score_filter2 (slots 0 and 2 hold up to 2 * cap groups)
   int debug_dump;              // 1 = uncertified rows leave their diagnostics in out_scores (env DIVREC_DEBUG_NO_RESCUE)
   int force_fail;              // 1 = send every row to the rescue kernel (DIVREC_MODE_SIMT)

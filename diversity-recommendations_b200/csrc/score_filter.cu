@@ -94,7 +94,14 @@ __device__ __forceinline__ float row_margin2(const FilterParams& p, int64_t row)
     const float au = __uint_as_float(p.amax_bits[0]), av = __uint_as_float(p.amax_bits[1]);
     delta += 3.64e-12f * sqrtf((float)p.d) * (nu * av + nvmax * au);
   }
-  return ldexpf(2.0f * delta, e2) * 1.0001f;
+  return ldexpf(2.0f * delta + REC_ID_SLACK * nu * nvmax, e2) * 1.0001f;
+}
+
+// first item id of a candidate record: the group index rides in the low mantissa bytes of its first scores (kernels.h)
+__device__ __forceinline__ uint32_t rec_item0(const float4& a, int id_bytes) {
+  uint32_t gi = (__float_as_uint(a.x) & 0xffu) | ((__float_as_uint(a.y) & 0xffu) << 8);
+  if (id_bytes > 2) gi |= ((__float_as_uint(a.z) & 0xffu) << 16) | ((__float_as_uint(a.w) & 0xffu) << 24);
+  return gi * GROUP;
 }
 
 // Warp-cooperative tightening of ONE nearly full candidate list (large catalogues: the sampled hint cannot
@@ -103,7 +110,7 @@ __device__ __forceinline__ float row_margin2(const FilterParams& p, int64_t row)
 // the k-th best unmasked score of the row is >= X and nothing below X - 2 delta can reach the top-k.  The
 // threshold is raised to X - 2 delta and the groups that fall below it are dropped, order preserved.
 // Returns the new group count; thr_io is updated.  All 32 lanes call with the same arguments.
-__device__ __noinline__ uint32_t tighten_list(float* Ls, uint32_t* Li, uint32_t n, int need, float margin2, uint32_t nI,
+__device__ __noinline__ uint32_t tighten_list(float* Ls, uint32_t n, int need, float margin2, uint32_t nI, int id_bytes,
                                               float& thr_io) {
   const uint32_t lane = lane_id();
   const uint32_t lt = lanemask_lt();
@@ -117,9 +124,9 @@ __device__ __noinline__ uint32_t tighten_list(float* Ls, uint32_t* Li, uint32_t 
     const uint32_t g = (uint32_t)j * 32 + lane;
     gm[j] = -INFINITY;
     if (g < n) {
-      const uint32_t it0 = Li[g];
-      float4 a = *reinterpret_cast<const float4*>(Ls + (size_t)g * GROUP);
-      float4 b = *reinterpret_cast<const float4*>(Ls + (size_t)g * GROUP + 4);
+      float4 a = *reinterpret_cast<const float4*>(Ls + (size_t)g * REC_FLOATS);
+      float4 b = *reinterpret_cast<const float4*>(Ls + (size_t)g * REC_FLOATS + 4);
+      const uint32_t it0 = rec_item0(a, id_bytes);
       if (it0 + 7 >= nI) {  // columns past the catalogue (zero-filled operand rows) are not items
         if (it0 + 0 >= nI) a.x = -INFINITY; if (it0 + 1 >= nI) a.y = -INFINITY;
         if (it0 + 2 >= nI) a.z = -INFINITY; if (it0 + 3 >= nI) a.w = -INFINITY;
@@ -162,19 +169,16 @@ __device__ __noinline__ uint32_t tighten_list(float* Ls, uint32_t* Li, uint32_t 
     const uint32_t g = (uint32_t)j * 32 + lane;
     const bool keep = g < n && gm[j] >= thr_new;
     float4 a, b;
-    uint32_t it0 = 0;
     if (keep) {
-      it0 = Li[g];
-      a = *reinterpret_cast<const float4*>(Ls + (size_t)g * GROUP);
-      b = *reinterpret_cast<const float4*>(Ls + (size_t)g * GROUP + 4);
+      a = *reinterpret_cast<const float4*>(Ls + (size_t)g * REC_FLOATS);
+      b = *reinterpret_cast<const float4*>(Ls + (size_t)g * REC_FLOATS + 4);
     }
     const uint32_t kb = __ballot_sync(0xffffffffu, keep);
     __syncwarp();
     if (keep) {
       const uint32_t pos = outn + __popc(kb & lt);
-      *reinterpret_cast<float4*>(Ls + (size_t)pos * GROUP) = a;
-      *reinterpret_cast<float4*>(Ls + (size_t)pos * GROUP + 4) = b;
-      Li[pos] = it0;
+      *reinterpret_cast<float4*>(Ls + (size_t)pos * REC_FLOATS) = a;   // the record carries its own index
+      *reinterpret_cast<float4*>(Ls + (size_t)pos * REC_FLOATS + 4) = b;
     }
     outn += __popc(kb);
     __syncwarp();
@@ -428,10 +432,10 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmap_b, const FilterPara
 
       // ---------------- phase 2: fixed-threshold group filter over this set's tiles ----------------
       // block-relative 32-bit offsets (a user block's lists span 128 * 4 * cap groups) on uniform 64-bit bases
-      float* const Ls_blk = p.list_scores + (size_t)ub * (BM * 4) * ((size_t)p.cap * GROUP);
-      uint32_t* const Li_blk = p.list_item0 + (size_t)ub * (BM * 4) * (size_t)p.cap;
+      float* const Ls_blk = p.lists + (size_t)ub * (BM * 4) * ((size_t)p.cap * REC_FLOATS);
       const uint32_t goff = (uint32_t)((row_local * 4 + h * 2 + pset) * p.cap);
       uint32_t cnt = 0;
+      const int id_bytes = rec_id_bytes(p.nI);
       // TIGHTEN: room is checked on every second tile of this thread, so two tiles' worth of slots are kept free
       const uint32_t cap_lim = (uint32_t)(p.cap - (TIGHTEN ? 2 : 1) * GROUPS_PER_TILE);
       int t = pset;
@@ -454,8 +458,8 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmap_b, const FilterPara
             if (need64 + (need64 >> 3) + 16 <= (int64_t)cap_lim) {
               const long long tt0 = p.stats != nullptr ? clock64() : 0;
               const uint32_t g_src = (uint32_t)(((q * 32 + src) * 4 + h * 2 + pset) * p.cap);
-              n_new = tighten_list(Ls_blk + (size_t)g_src * GROUP, Li_blk + g_src, n_src, (int)need64, row_margin2(p, row_src),
-                                   (uint32_t)p.nI, thr_src);
+              n_new = tighten_list(Ls_blk + (size_t)g_src * REC_FLOATS, n_src, (int)need64, row_margin2(p, row_src),
+                                   (uint32_t)p.nI, id_bytes, thr_src);
               if (p.stats != nullptr && lane == 0) {  // measurement aid: tightening events and their cycles per CTA
                 atomicAdd(reinterpret_cast<unsigned long long*>(p.stats) + (size_t)blockIdx.x * 8 + 4, 1ull);
                 atomicAdd(reinterpret_cast<unsigned long long*>(p.stats) + (size_t)blockIdx.x * 8 + 5, (unsigned long long)(clock64() - tt0));
@@ -485,23 +489,25 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmap_b, const FilterPara
 
         if (p.debug_mode == 1) continue;   // measurement aid: MMA + TMA pipeline alone (no filtering)
         const float thr_st = p.debug_mode == 2 ? INFINITY : thr;  // measurement aid: filter arithmetic without the stores
-        const uint32_t item0 = (uint32_t)(t * BN + h * COLS_PER_THREAD);
+        const uint32_t gi0 = (uint32_t)(t * (BN / GROUP) + h * GROUPS_PER_TILE);  // index of this thread's first group of the tile
 #pragma unroll
         for (int g = 0; g < GROUPS_PER_TILE; ++g) {
           const uint32_t* v = g < 4 ? &v0[8 * g] : &v1[8 * (g - 4)];
           const float m = max8(v);
-          float* dst = Ls_blk + (size_t)(goff + cnt) * GROUP;
-          uint32_t* idst = Li_blk + (goff + cnt);
-          // branch-free append: predicated 128-bit stores of the whole group + its first item id
+          float* dst = Ls_blk + (size_t)(goff + cnt) * REC_FLOATS;
+          // the record carries its group index in the low mantissa bytes of its first scores (taken AFTER the maximum)
+          const uint32_t gi = gi0 + (uint32_t)g;
+          const uint32_t w0 = (v[0] & 0xffffff00u) | (gi & 0xffu), w1 = (v[1] & 0xffffff00u) | ((gi >> 8) & 0xffu);
+          const uint32_t w2 = id_bytes > 2 ? ((v[2] & 0xffffff00u) | ((gi >> 16) & 0xffu)) : v[2];
+          const uint32_t w3 = id_bytes > 2 ? ((v[3] & 0xffffff00u) | (gi >> 24)) : v[3];
+          // branch-free append: ONE predicated 256-bit store (STG.E.ENL2.256)
           asm volatile(
               "{\n"
               ".reg .pred p;\n"
               "setp.ge.f32 p, %0, %1;\n"
-              "@p st.global.v8.b32 [%2], {%4, %5, %6, %7, %8, %9, %10, %11};\n"  // one 256-bit store (STG.E.ENL2.256)
-              "@p st.global.b32 [%3], %12;\n"
+              "@p st.global.v8.b32 [%2], {%3, %4, %5, %6, %7, %8, %9, %10};\n"
               "}\n"
-              ::"f"(m), "f"(thr_st), "l"(dst), "l"(idst), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]),
-                "r"(v[6]), "r"(v[7]), "r"(item0 + 8 * g)
+              ::"f"(m), "f"(thr_st), "l"(dst), "r"(w0), "r"(w1), "r"(w2), "r"(w3), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
               : "memory");
           cnt += (m >= thr) ? 1u : 0u;
         }

@@ -54,7 +54,7 @@ struct Smem2 {
   uint64_t a_empty;
   uint32_t tmem_base;
   uint32_t pad;
-  float sorted[NB][HS][EPI_THREADS];
+  alignas(16) float sorted[NB][HS][EPI_THREADS];  // hint phase; afterwards rows 0..5 = ladder checkpoint exchange, rows 8..9 = ladder levels (float4 per row)
   int dropped[NB][EPI_THREADS];   // sample groups a thread left out of the hint because they contain seen items
 };
 
@@ -74,6 +74,43 @@ __device__ __forceinline__ float max32(const uint32_t* v) {
 }
 __device__ __forceinline__ int sched_tile(int s, int n_sample, int stride) {
   return s < n_sample ? s * stride : s - n_sample;
+}
+
+// Ladder checkpoint (rare path, out of line so that it does not weigh on the hot loop's registers): the highest
+// threshold -- a level, or a log-linear interpolation between two levels -- whose projected number of UNMASKED items
+// above it still covers k + margin.  cj = clean 64-column blocks (of nc seen so far, both column halves of the row)
+// whose maximum reached level j; P(block max >= t) = q  <=>  per-item tail p = -log(1 - q) / 64; the count is taken
+// at a 2.5 sigma lower confidence bound of q, plus one sigma of the part of the catalogue still to come.
+// Returns -inf when no level qualifies.  Both threads of a row evaluate this on the same numbers.
+__device__ __noinline__ float ladder_decide(const FilterParams& p, int64_t row, float4 l4, uint32_t s01, uint32_t s23, float nc,
+                                            float frac) {
+  int64_t seen_u = 0;
+  if (p.seen_rowptr != nullptr) seen_u = p.seen_rowptr[row + 1] - p.seen_rowptr[row];
+  const float n_un = fmaxf(1.0f, (float)((int64_t)p.nI - seen_u));
+  const float need = (float)p.k + (float)max(16, p.k >> 2);
+  const float req = need + sqrtf(need * (1.0f - frac));
+  const float cj[4] = {(float)(s01 & 0xffffu), (float)(s01 >> 16), (float)(s23 & 0xffffu), (float)(s23 >> 16)};
+  const float lj[4] = {l4.x, l4.y, l4.z, l4.w};
+  float nlo[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float qh = cj[j] / nc;
+    const float se = sqrtf(fmaxf(qh * (1.0f - qh), 1e-9f) / nc);
+    const float qlo = fminf(fmaxf(qh - 2.5f * se, 1e-6f), 0.999f);
+    nlo[j] = -log1pf(-qlo) * (1.0f / 64.0f) * n_un;  // items above level j, lower confidence bound
+  }
+  float cand = -INFINITY;
+#pragma unroll
+  for (int j = 3; j >= 0; --j) {
+    if (cand == -INFINITY && lj[j] < 3.0e38f && nlo[j] >= req) {
+      cand = lj[j];
+      if (j < 3 && lj[j + 1] < 3.0e38f && lj[j + 1] > lj[j] && nlo[j + 1] < req && nlo[j + 1] > 0.0f) {
+        const float wgt = (__logf(nlo[j]) - __logf(req)) / fmaxf(__logf(nlo[j]) - __logf(nlo[j + 1]), 1e-6f);
+        cand += (lj[j + 1] - lj[j]) * fminf(fmaxf(wgt, 0.0f), 1.0f);
+      }
+    }
+  }
+  return cand;
 }
 
 // Seen-item patterns of every row, one pass over the CSR (one warp per row, words assembled in shared memory):
@@ -368,13 +405,15 @@ score_filter2_kernel(const __grid_constant__ CUtensorMap tmap_b, const FilterPar
       float4* const lv_s = reinterpret_cast<float4*>(&sm->sorted[bset][8][0]);
       lv_s[row_local] = lv;
 
-      // ---- phase 2: fixed-threshold group filter over every tile of this set's block ----
-      float* const Ls_blk = p.list_scores + (size_t)ub * (BM * 4) * ((size_t)p.cap * GROUP);
-      uint32_t* const Li_blk = p.list_item0 + (size_t)ub * (BM * 4) * (size_t)p.cap;
-      const uint32_t goff = (uint32_t)((row_local * 4 + h * 2) * p.cap);  // slots (h,0)+(h,1): one list of 2 * cap groups
-      const uint32_t cap2 = 2u * (uint32_t)p.cap;
+      // ---- phase 2: group filter over every tile of this set's block ----
+      // The epilogue is instruction-bound (16 warps share the SM's issue slots with nothing to hide behind), so an append
+      // is one predicate, ONE 256-bit store (the group's scores carry its index in their low mantissa bytes) and a bump
+      // of the thread's running record pointer.  The group count is the pointer's distance.
+      const uint32_t cap2 = 2u * (uint32_t)p.cap;                 // slots (h,0)+(h,1): one list of 2 * cap records
       const uint32_t cap_lim = cap2 - GROUPS_PER_TILE;
-      uint32_t cnt = 0;
+      float* const rec0 = p.lists + ((size_t)ub * (BM * 4) * (size_t)p.cap + (size_t)((row_local * 4 + h * 2) * p.cap)) * REC_FLOATS;
+      float* rec = rec0;
+      bool overflow = false;
       // ladder state: per level, clean 64-column blocks of this thread whose maximum reached it (16-bit fields), and the
       // clean blocks seen; the dirty-block bitmap is read 32 tiles at a time
       uint32_t c01 = 0, c23 = 0, ncl = 0, dirty = 0;
@@ -400,38 +439,41 @@ score_filter2_kernel(const __grid_constant__ CUtensorMap tmap_b, const FilterPar
         if (lane == 0) mbar_arrive(smem_u32(&sm->acc_empty[acc]));
 
         if (p.debug_mode == 1) continue;
-        if (cnt > cap_lim) { thr = INFINITY; cnt = cap2 + 1; }  // overflow: the row goes to the rescue kernel
-        const float thr_st = p.debug_mode == 2 ? INFINITY : thr;
-        const uint32_t item0 = (uint32_t)(t * BN + h * COLS_PER_THREAD);
+        // records appended so far, from the low words of the pointers (a list is far smaller than 4 GB)
+        if ((((uint32_t)reinterpret_cast<uintptr_t>(rec) - (uint32_t)reinterpret_cast<uintptr_t>(rec0)) >> 5) > cap_lim) { thr = INFINITY; overflow = true; }  // the row goes to the rescue kernel
+        // index of this thread's first group of the tile (< 2^16: this kernel runs below TIGHTEN_MIN_ITEMS items); a record
+        // carries it in the low mantissa bytes of its first two scores: (v | 0xff) ^ x with x = 0xff ^ byte
+        const uint32_t gi0 = (uint32_t)(t * (BN / GROUP) + h * GROUPS_PER_TILE);
+        const uint32_t xlo = 0xffu ^ (gi0 & 0xffu), xhi = 0xffu ^ (gi0 >> 8);
         float mt0 = -INFINITY, mt1 = -INFINITY, mt2 = -INFINITY;  // maximum of the 64-column block
 #pragma unroll
         for (int g = 0; g < GROUPS_PER_TILE; ++g) {
-          const uint32_t* v = g < 4 ? &v0[8 * g] : &v1[8 * (g - 4)];
+          uint32_t* v = g < 4 ? &v0[8 * g] : &v1[8 * (g - 4)];
           const float m = max8(v);
-          float* dst = Ls_blk + (size_t)(goff + cnt) * GROUP;
-          uint32_t* idst = Li_blk + (goff + cnt);
+          v[0] = (v[0] | 0xffu) ^ (xlo ^ (uint32_t)g);  // gi0 is a multiple of 8: its low three bits take g
+          v[1] = (v[1] | 0xffu) ^ xhi;
           asm volatile(
               "{\n"
               ".reg .pred p;\n"
-              "setp.ge.f32 p, %0, %1;\n"
-              "@p st.global.v8.b32 [%2], {%4, %5, %6, %7, %8, %9, %10, %11};\n"  // one 256-bit store (STG.E.ENL2.256)
-              "@p st.global.b32 [%3], %12;\n"
+              "setp.ge.f32 p, %1, %2;\n"
+              "@p st.global.v8.b32 [%0], {%3, %4, %5, %6, %7, %8, %9, %10};\n"  // the whole append: one 256-bit store (STG.E.ENL2.256)
+              "@p add.u64 %0, %0, 32;\n"
               "}\n"
-              ::"f"(m), "f"(thr_st), "l"(dst), "l"(idst), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]),
-                "r"(v[6]), "r"(v[7]), "r"(item0 + 8 * g)
+              : "+l"(rec)
+              : "f"(m), "f"(thr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
               : "memory");
-          cnt += (m >= thr) ? 1u : 0u;
           if (g % 3 == 0) mt0 = fmaxf(mt0, m); else if (g % 3 == 1) mt1 = fmaxf(mt1, m); else mt2 = fmaxf(mt2, m);
         }
         if (ladder) {
-          const float mt = max3(mt0, mt1, mt2);
+          // a dirty block counts for nothing: its maximum is replaced by -inf, so the level compares need no second condition
           const bool clean = ((dirty >> (t & 31)) & 1u) == 0u;
+          const float mt = clean ? max3(mt0, mt1, mt2) : -INFINITY;
           const float4 l4 = lv_s[row_local];
           ncl += clean ? 1u : 0u;
-          c01 += (clean && mt >= l4.x) ? 1u : 0u;
-          c01 += (clean && mt >= l4.y) ? 0x10000u : 0u;
-          c23 += (clean && mt >= l4.z) ? 1u : 0u;
-          c23 += (clean && mt >= l4.w) ? 0x10000u : 0u;
+          c01 += (mt >= l4.x) ? 1u : 0u;
+          c01 += (mt >= l4.y) ? 0x10000u : 0u;
+          c23 += (mt >= l4.z) ? 1u : 0u;
+          c23 += (mt >= l4.w) ? 0x10000u : 0u;
           if (t + 1 == next_cp) {
             next_cp += p.ladder_stride;
             if (t + 1 < p.n_tiles) {
@@ -445,41 +487,12 @@ score_filter2_kernel(const __grid_constant__ CUtensorMap tmap_b, const FilterPar
               const int pe = et ^ 128;  // the row's other column half
               const uint32_t s01 = c01 + exch[(slot + 0) * EPI_THREADS + pe], s23 = c23 + exch[(slot + 1) * EPI_THREADS + pe];
               const float nc = (float)(ncl + exch[(slot + 2) * EPI_THREADS + pe]);
-              if (valid_row && nc >= 16.0f) {
-                int64_t seen_u = 0;
-                if (p.seen_rowptr != nullptr) seen_u = p.seen_rowptr[row + 1] - p.seen_rowptr[row];
-                const float n_un = fmaxf(1.0f, (float)((int64_t)p.nI - seen_u));
-                const float need = (float)p.k + (float)max(16, p.k >> 2);
-                const float frac = (float)(t + 1) / (float)p.n_tiles;
-                const float req = need + sqrtf(need * (1.0f - frac));  // + 1 sigma of the part of the catalogue still to come
-                const float cj[4] = {(float)(s01 & 0xffffu), (float)(s01 >> 16), (float)(s23 & 0xffffu), (float)(s23 >> 16)};
-                const float lj[4] = {l4.x, l4.y, l4.z, l4.w};
-                float nlo[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const float qh = cj[j] / nc;
-                  const float se = sqrtf(fmaxf(qh * (1.0f - qh), 1e-9f) / nc);
-                  const float qlo = fminf(fmaxf(qh - 2.5f * se, 1e-6f), 0.999f);
-                  nlo[j] = -log1pf(-qlo) * (1.0f / 64.0f) * n_un;  // items above level j, lower confidence bound
-                }
-                float cand = -INFINITY;
-#pragma unroll
-                for (int j = 3; j >= 0; --j) {
-                  if (cand == -INFINITY && lj[j] < 3.0e38f && nlo[j] >= req) {
-                    cand = lj[j];
-                    if (j < 3 && lj[j + 1] < 3.0e38f && lj[j + 1] > lj[j] && nlo[j + 1] < req && nlo[j + 1] > 0.0f) {
-                      // log-linear interpolation of the count between the two levels
-                      const float wgt = (__logf(nlo[j]) - __logf(req)) / fmaxf(__logf(nlo[j]) - __logf(nlo[j + 1]), 1e-6f);
-                      cand += (lj[j + 1] - lj[j]) * fminf(fmaxf(wgt, 0.0f), 1.0f);
-                    }
-                  }
-                }
-                thr = fmaxf(thr, cand);
-              }
+              if (valid_row && nc >= 16.0f) thr = fmaxf(thr, ladder_decide(p, row, l4, s01, s23, nc, (float)(t + 1) / (float)p.n_tiles));
             }
           }
         }
       }
+      const uint32_t cnt = overflow ? cap2 + 1u : (((uint32_t)reinterpret_cast<uintptr_t>(rec) - (uint32_t)reinterpret_cast<uintptr_t>(rec0)) >> 5);
       if (valid_row) {
         p.list_count[row * 4 + h * 2] = (int32_t)cnt;  // 2 * cap + 1 = overflowed
         p.list_count[row * 4 + h * 2 + 1] = 0;

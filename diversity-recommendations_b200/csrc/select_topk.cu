@@ -110,7 +110,7 @@ __device__ __forceinline__ float sum8(float v) {
 }
 
 // One pass over the row's captured groups: iteration `it` handles group it*32+lane of each of the row's four lists
-// (four independent 36-byte reads in flight per lane, trivial addressing).
+// (four independent record reads in flight per lane, trivial addressing).
 //   MODE 1: elements with score >= fmin are written to key[] / id[] (at most SEL_CAP), any order;
 //   MODE 2: their keys only are written to key[0 .. SEL_WORDS) (the warp's whole region);  MODE 0: count only.
 //   Returns how many there are in total.  Scores are compared as floats; -inf never qualifies.
@@ -132,6 +132,7 @@ __device__ __forceinline__ int scan_groups(const SelectParams& p, int64_t row, c
   const int nmax = max(max(cnt[0], cnt[1]), max(cnt[2], cnt[3]));
   const size_t row_base = (size_t)row * LISTS_PER_ROW * (size_t)p.cap;
   const uint32_t nI = (uint32_t)p.nI;
+  const bool wide_ids = p.id_bytes > 2;
   for (int g = lane; g < nmax + (int)lane; g += 32) {  // uniform trip count: every lane runs ceil(nmax / 32) iterations
     float4 a[LISTS_PER_ROW], b[LISTS_PER_ROW];
     uint32_t item0[LISTS_PER_ROW];
@@ -139,11 +140,13 @@ __device__ __forceinline__ int scan_groups(const SelectParams& p, int64_t row, c
     for (int l = 0; l < LISTS_PER_ROW; ++l) {
       item0[l] = 0xffffffffu;
       if (g < cnt[l]) {
-        const size_t base = row_base + (size_t)start[l] + g;
-        item0[l] = p.list_item0[base];
-        const float4* src = reinterpret_cast<const float4*>(p.list_scores + base * GROUP);
+        const float4* src = reinterpret_cast<const float4*>(p.lists + (row_base + (size_t)start[l] + g) * REC_FLOATS);
         a[l] = src[0];
         b[l] = src[1];
+        // the group index rides in the low mantissa bytes of the first scores
+        uint32_t gi = (__float_as_uint(a[l].x) & 0xffu) | ((__float_as_uint(a[l].y) & 0xffu) << 8);
+        if (wide_ids) gi |= ((__float_as_uint(a[l].z) & 0xffu) << 16) | ((__float_as_uint(a[l].w) & 0xffu) << 24);
+        item0[l] = gi * GROUP;
       }
     }
     uint32_t m[LISTS_PER_ROW];
@@ -256,7 +259,7 @@ select_topk_kernel(const SelectParams p) {
     const float au = __uint_as_float(p.amax_bits[0]), av = __uint_as_float(p.amax_bits[1]);
     delta += 3.64e-12f * sqrtf((float)p.d) * (nu * av + nvmax * au);
   }
-  const float margin2 = ldexpf(2.0f * delta, e2) * 1.0001f;
+  const float margin2 = ldexpf(2.0f * delta + REC_ID_SLACK * nu * nvmax, e2) * 1.0001f;  // + the index bytes carried by the record scores
 
   const float4 thr4 = *reinterpret_cast<const float4*>(p.thr + row * LISTS_PER_ROW);
   const float thr = fmaxf(fmaxf(thr4.x, thr4.y), fmaxf(thr4.z, thr4.w));  // everything >= the largest list threshold was captured by all lists
