@@ -13,15 +13,17 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OUT = os.path.join(HERE, "libdivrec_b200.so")
-OBJ_DIR = os.path.join(HERE, "build")
+# experiment builds (tools/ab.py): DIVREC_BUILD_TAG=<tag> DIVREC_BUILD_DEFS="-DX -DY" -> libdivrec_b200.<tag>.so, objects in build.<tag>/
+_TAG = os.environ.get("DIVREC_BUILD_TAG", "")
+OUT = os.path.join(HERE, f"libdivrec_b200.{_TAG}.so" if _TAG else "libdivrec_b200.so")
+OBJ_DIR = os.path.join(HERE, f"build.{_TAG}" if _TAG else "build")
 SOURCES = ["api.cu", "score_filter.cu", "select_topk.cu", "rescue.cu", "prep.cu", "metrics.cu", "bpr.cu", "mmr.cu", "score_filter2.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--use_fast_math=false",
 ]
-FLAGS = [f for f in FLAGS if f != "--use_fast_math=false"]
+FLAGS = [f for f in FLAGS if f != "--use_fast_math=false"] + os.environ.get("DIVREC_BUILD_DEFS", "").split()
 
 
 def _digest():

@@ -59,6 +59,8 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a pipeline bug must become a trap (an error the host sees), never a hung GPU.
+// (A suspend-time hint on try_wait and a cheaper loop body were measured: no change -- the ~20 % of executed instructions
+// that are wait loops run in issue slots nobody else wants.)
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();

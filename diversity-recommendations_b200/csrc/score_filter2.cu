@@ -32,6 +32,12 @@ namespace divrec {
 
 namespace {
 
+#ifndef DIVREC_Z_HINT
+#define DIVREC_Z_HINT 4.0f   // safety of the sampled hint on the masked rule, standard deviations
+#endif
+#ifndef DIVREC_Z_CP
+#define DIVREC_Z_CP 2.5f     // lower confidence bound of the ladder's checkpoint counts
+#endif
 constexpr int BM = 128, BN = 128, BK = 64;
 constexpr int SLAB_BYTES = BM * BK * 2;
 constexpr int TMEM_COLS = 512;
@@ -96,7 +102,7 @@ __device__ __noinline__ float ladder_decide(const FilterParams& p, int64_t row, 
   for (int j = 0; j < 4; ++j) {
     const float qh = cj[j] / nc;
     const float se = sqrtf(fmaxf(qh * (1.0f - qh), 1e-9f) / nc);
-    const float qlo = fminf(fmaxf(qh - 2.5f * se, 1e-6f), 0.999f);
+    const float qlo = fminf(fmaxf(qh - DIVREC_Z_CP * se, 1e-6f), 0.999f);
     nlo[j] = -log1pf(-qlo) * (1.0f / 64.0f) * n_un;  // items above level j, lower confidence bound
   }
   float cand = -INFINITY;
@@ -362,7 +368,7 @@ score_filter2_kernel(const __grid_constant__ CUtensorMap tmap_b, const FilterPar
             const float n = (float)n_groups;
             // 4 sigma on the masked rule: an uncertified row costs a rescue launch (~0.17 ms of latency per call even for a
             // handful of rows), which at 3 sigma (24 rows per 138k) hits every call of the chunked host pipeline
-            r = (int)ceilf(n * pg + (masked_rule ? 4.0f : 3.0f) * sqrtf(n * pg * (1.0f - pg))) + 1;
+            r = (int)ceilf(n * pg + (masked_rule ? DIVREC_Z_HINT : 3.0f) * sqrtf(n * pg * (1.0f - pg))) + 1;
           }
           // ladder levels: the same order statistic at 3, 2, 1, 0 sigma for k + margin UNMASKED items (ranks r_lv[j] <= r);
           // which of them is safe is decided later from live counts, so their own noise costs tightness, never exactness
@@ -426,11 +432,21 @@ score_filter2_kernel(const __grid_constant__ CUtensorMap tmap_b, const FilterPar
       for (int t = 0; t < p.n_tiles; ++t) {
         if (ladder && (t & 31) == 0)
           dirty = dirty_w != nullptr ? __ldg(dirty_w + (size_t)(t >> 6) * (size_t)p.hint_mask_stride * 2 + ((t >> 5) & 1)) : 0u;
+        // this set's accumulator sequence advances by NB per tile: running stage / phase instead of a division per tile
         const uint32_t seq = base_seq + (uint32_t)(NB * (n_sample + t) + bset), acc = seq % ACC_STAGES, acc_phase = (seq / ACC_STAGES) & 1;
         mbar_wait(smem_u32(&sm->acc_full[acc]), acc_phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + h * COLS_PER_THREAD;
         uint32_t v0[32], v1[32];
+        if (p.debug_mode == 3) {  // measurement aid: half of the tensor-memory read traffic, no filtering
+          tmem_ld_32x32b_x32(taddr, v0);
+          tmem_wait_ld();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&sm->acc_empty[acc]));
+          if ((v0[0] ^ v0[13] ^ v0[31]) == 0x7fc12345u) thr = 0.f;  // keep the load alive
+          continue;
+        }
         tmem_ld_32x32b_x32(taddr, v0);
         tmem_ld_32x32b_x32(taddr + 32, v1);
         tmem_wait_ld();
@@ -450,8 +466,21 @@ score_filter2_kernel(const __grid_constant__ CUtensorMap tmap_b, const FilterPar
         for (int g = 0; g < GROUPS_PER_TILE; ++g) {
           uint32_t* v = g < 4 ? &v0[8 * g] : &v1[8 * (g - 4)];
           const float m = max8(v);
+#ifndef DIVREC_DIAG_NOEMBED
           v[0] = (v[0] | 0xffu) ^ (xlo ^ (uint32_t)g);  // gi0 is a multiple of 8: its low three bits take g
           v[1] = (v[1] | 0xffu) ^ xhi;
+#endif
+#ifdef DIVREC_DIAG_NOSTORE
+          asm volatile(
+              "{\n"
+              ".reg .pred p;\n"
+              "setp.ge.f32 p, %1, %2;\n"
+              "@p add.u64 %0, %0, 32;\n"
+              "}\n"
+              : "+l"(rec)
+              : "f"(m), "f"(thr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+              : "memory");
+#else
           asm volatile(
               "{\n"
               ".reg .pred p;\n"
@@ -462,13 +491,18 @@ score_filter2_kernel(const __grid_constant__ CUtensorMap tmap_b, const FilterPar
               : "+l"(rec)
               : "f"(m), "f"(thr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
               : "memory");
+#endif
           if (g % 3 == 0) mt0 = fmaxf(mt0, m); else if (g % 3 == 1) mt1 = fmaxf(mt1, m); else mt2 = fmaxf(mt2, m);
         }
+#ifdef DIVREC_EXP_LADDER_EVEN
+        if (ladder && ((t & 1) == 0 || t + 1 == next_cp)) {
+#else
         if (ladder) {
+#endif
           // a dirty block counts for nothing: its maximum is replaced by -inf, so the level compares need no second condition
           const bool clean = ((dirty >> (t & 31)) & 1u) == 0u;
           const float mt = clean ? max3(mt0, mt1, mt2) : -INFINITY;
-          const float4 l4 = lv_s[row_local];
+          const float4 l4 = lv_s[row_local];  // (an explicit ld.shared + running stage counters measured 5 % slower)
           ncl += clean ? 1u : 0u;
           c01 += (mt >= l4.x) ? 1u : 0u;
           c01 += (mt >= l4.y) ? 0x10000u : 0u;
@@ -560,6 +594,9 @@ cudaError_t launch_score_filter2(const void* A16, const void* B16, FilterParams 
   p.mask_words = mask_words_for(p.nI);
   // ladder checkpoints every ~1/8 of the catalogue (off without a hint phase: catalogues under HINT_MIN_TILES tiles)
   p.ladder_stride = p.n_sample > 0 ? ((p.n_tiles + 7) / 8 > 8 ? (p.n_tiles + 7) / 8 : 8) : 0;
+#ifdef DIVREC_DIAG_NOLADDER
+  p.ladder_stride = 0;
+#endif
   const size_t smem = 1024 + (size_t)p.b_stages * SLAB_BYTES + sizeof(Smem2);
   const int n_dblocks = (p.n_ublocks + NB - 1) / NB;
   int grid = n_dblocks < sm_count ? n_dblocks : sm_count;

@@ -11,7 +11,7 @@ U, V = O.make_embeddings(nU, d, "gauss", g).to(dev), O.make_embeddings(nI, d, "g
 lib = N.load_library()
 N.set_profiling(True)
 out = {}
-for mode in (0, 1):
+for mode in (0, 1, 3):
     lib.divrec_debug_filter_mode(mode)
     ms = []
     for _ in range(6):
@@ -22,7 +22,7 @@ for mode in (0, 1):
     print(mode, out[f"mode{mode}"], flush=True)
 lib.divrec_debug_filter_mode(0)
 buf = torch.zeros((148, 8), dtype=torch.int64, device=dev)
-for mode in (0, 1):
+for mode in (0, 1, 3):
     lib.divrec_debug_filter_mode(mode)
     lib.divrec_debug_filter_stats(buf.data_ptr())
     N.score_topk(U, V, k); torch.cuda.synchronize()
