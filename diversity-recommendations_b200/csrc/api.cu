@@ -402,53 +402,118 @@ int divrec_entropy_from_counts(const int32_t* counts, int64_t nI, float* out2, v
   return DIVREC_OK;
 }
 
-static int check_rows(const float* U, const float* V, int d, const char* who) {
+static int check_rows(const float* U, const float* V, int64_t nU, int64_t nI, int d, const char* who) {
   if (!U || !V) return fail(DIVREC_ERR_ARG, "%s: null embedding table", who);
-  if (d <= 0 || (d & 3) || d > 1024) return fail(DIVREC_ERR_ARG, "%s: d must be a multiple of 4, <= 1024", who);
-  if ((reinterpret_cast<uintptr_t>(U) & 15) || (reinterpret_cast<uintptr_t>(V) & 15))
-    return fail(DIVREC_ERR_ARG, "%s: tables must be 16-byte aligned", who);
+  if (nU <= 0 || nI <= 0) return fail(DIVREC_ERR_ARG, "%s: nU and nI must be positive", who);
+  if (d <= 0 || d > 1024) return fail(DIVREC_ERR_ARG, "%s: d must be in [1, 1024]", who);
   return DIVREC_OK;
 }
+static bool vec_ok(int d, const void* a, const void* b = nullptr, const void* c = nullptr) {
+  return (d & 3) == 0 && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c)) & 15) == 0;
+}
 
-int divrec_bpr_fwd(const float* U, const float* V, const int64_t* u, const int64_t* p, const int64_t* n, int64_t B,
-                   int d, float* pos, float* neg, float* loss_sum, int32_t* auc_sum, void* stream) {
-  int rc = check_rows(U, V, d, "bpr_fwd");
+int divrec_bpr_fwd(const float* U, const float* V, int64_t nU, int64_t nI, const int64_t* u, const int64_t* p, const int64_t* n,
+                   int64_t B, int d, float* pos, float* neg, float* loss_sum, int32_t* auc_sum, void* stream) {
+  int rc = check_rows(U, V, nU, nI, d, "bpr_fwd");
   if (rc != DIVREC_OK) return rc;
   if (!u || !p || !n || !pos || !neg) return fail(DIVREC_ERR_ARG, "bpr_fwd: null pointer");
   if (B <= 0) return fail(DIVREC_ERR_ARG, "bpr_fwd: B must be positive");
-  cudaError_t e = launch_bpr_fwd(U, V, u, p, n, B, d, pos, neg, loss_sum, auc_sum, reinterpret_cast<cudaStream_t>(stream));
+  cudaError_t e = launch_bpr_fwd(U, V, nU, nI, u, p, n, B, d, pos, neg, loss_sum, auc_sum, reinterpret_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "bpr_fwd launch");
   return DIVREC_OK;
 }
 
-int divrec_bpr_bwd(const float* U, const float* V, const int64_t* u, const int64_t* p, const int64_t* n,
+int divrec_bpr_bwd(const float* U, const float* V, int64_t nU, int64_t nI, const int64_t* u, const int64_t* p, const int64_t* n,
                    const float* pos, const float* neg, const float* g, float grad_scale, int64_t B, int d, float* gU,
                    float* gV, void* stream) {
-  int rc = check_rows(U, V, d, "bpr_bwd");
+  int rc = check_rows(U, V, nU, nI, d, "bpr_bwd");
   if (rc != DIVREC_OK) return rc;
   if (!u || !p || !n) return fail(DIVREC_ERR_ARG, "bpr_bwd: null index pointer");
   if (!g && (!pos || !neg)) return fail(DIVREC_ERR_ARG, "bpr_bwd: need g or (pos,neg)");
   if (B <= 0) return fail(DIVREC_ERR_ARG, "bpr_bwd: B must be positive");
-  if ((gU && (reinterpret_cast<uintptr_t>(gU) & 15)) || (gV && (reinterpret_cast<uintptr_t>(gV) & 15)))
-    return fail(DIVREC_ERR_ARG, "bpr_bwd: gradient tables must be 16-byte aligned");
-  cudaError_t e = launch_bpr_bwd(U, V, u, p, n, pos, neg, g, grad_scale, B, d, gU, gV, reinterpret_cast<cudaStream_t>(stream));
+  cudaError_t e = launch_bpr_bwd(U, V, nU, nI, u, p, n, pos, neg, g, grad_scale, B, d, gU, gV, reinterpret_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "bpr_bwd launch");
   return DIVREC_OK;
 }
 
-int divrec_bpr_step(const float* U, const float* V, const int64_t* u, const int64_t* p, const int64_t* n, int64_t B, int d,
-                    float grad_scale, float* pos, float* neg, float* loss_sum, int32_t* auc_sum, float* gU, float* gV,
-                    float* item_rows, void* stream) {
-  int rc = check_rows(U, V, d, "bpr_step");
+static int bpr_step_impl(const float* U, const float* V, int64_t nU, int64_t nI, const int64_t* u, const int64_t* p,
+                         const int64_t* n, int64_t B, int d, float grad_scale, float* pos, float* neg, float* loss_sum,
+                         int32_t* auc_sum, float* gU, float* gV, float* item_rows, float* const* slices, int64_t slice_rows,
+                         void* stream) {
+  int rc = check_rows(U, V, nU, nI, d, "bpr_step");
   if (rc != DIVREC_OK) return rc;
   if (!u || !p || !n) return fail(DIVREC_ERR_ARG, "bpr_step: null index pointer");
   if (B <= 0) return fail(DIVREC_ERR_ARG, "bpr_step: B must be positive");
-  if ((gU && (reinterpret_cast<uintptr_t>(gU) & 15)) || (gV && (reinterpret_cast<uintptr_t>(gV) & 15)))
-    return fail(DIVREC_ERR_ARG, "bpr_step: gradient tables must be 16-byte aligned");
-  if (item_rows && (reinterpret_cast<uintptr_t>(item_rows) & 15)) return fail(DIVREC_ERR_ARG, "bpr_step: item_rows must be 16-byte aligned");
-  cudaError_t e = launch_bpr_step(U, V, u, p, n, B, d, grad_scale, pos, neg, loss_sum, auc_sum, gU, gV, item_rows,
-                                  reinterpret_cast<cudaStream_t>(stream));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (!vec_ok(d, U, V) || !vec_ok(d, gU, gV, item_rows)) {
+    // rows that cannot move as 128-bit vectors (d % 4 != 0 or unaligned tables): forward, then backward (two passes)
+    if (slices || item_rows) return fail(DIVREC_ERR_ARG, "bpr_step: the sparse / owner-sharded item gradient needs d % 4 == 0 and 16-byte aligned tables");
+    if (!pos || !neg) return fail(DIVREC_ERR_ARG, "bpr_step: pos and neg are required when d % 4 != 0 (two-pass form)");
+    cudaError_t e = launch_bpr_fwd(U, V, nU, nI, u, p, n, B, d, pos, neg, loss_sum, auc_sum, st);
+    if (e == cudaSuccess) e = launch_bpr_bwd(U, V, nU, nI, u, p, n, pos, neg, nullptr, grad_scale, B, d, gU, gV, st);
+    if (e != cudaSuccess) return cuda_fail(e, "bpr_step launch");
+    return DIVREC_OK;
+  }
+  cudaError_t e = launch_bpr_step(U, V, nU, nI, u, p, n, B, d, grad_scale, pos, neg, loss_sum, auc_sum, gU, gV, item_rows, slices,
+                                  slice_rows, st);
   if (e != cudaSuccess) return cuda_fail(e, "bpr_step launch");
+  return DIVREC_OK;
+}
+
+int divrec_bpr_step(const float* U, const float* V, int64_t nU, int64_t nI, const int64_t* u, const int64_t* p, const int64_t* n,
+                    int64_t B, int d, float grad_scale, float* pos, float* neg, float* loss_sum, int32_t* auc_sum, float* gU,
+                    float* gV, float* item_rows, void* stream) {
+  return bpr_step_impl(U, V, nU, nI, u, p, n, B, d, grad_scale, pos, neg, loss_sum, auc_sum, gU, gV, item_rows, nullptr, 1, stream);
+}
+
+int divrec_bpr_step_owner(const float* U, const float* V, int64_t nU, int64_t nI, const int64_t* u, const int64_t* p,
+                          const int64_t* n, int64_t B, int d, float grad_scale, float* pos, float* neg, float* loss_sum,
+                          int32_t* auc_sum, float* gU, float* const* gV_slices, int n_slices, int64_t slice_rows, void* stream) {
+  if (!gV_slices || n_slices <= 0 || slice_rows <= 0) return fail(DIVREC_ERR_ARG, "bpr_step_owner: need the slice table, n_slices > 0 and slice_rows > 0");
+  if ((int64_t)n_slices * slice_rows < nI) return fail(DIVREC_ERR_ARG, "bpr_step_owner: n_slices * slice_rows must cover nI");
+  return bpr_step_impl(U, V, nU, nI, u, p, n, B, d, grad_scale, pos, neg, loss_sum, auc_sum, gU, nullptr, nullptr, gV_slices, slice_rows,
+                       stream);
+}
+
+int divrec_bad_index_count(int64_t* host_out, int reset, void* stream) {
+  if (!host_out) return fail(DIVREC_ERR_ARG, "bad_index_count: null pointer");
+  unsigned long long v = 0;
+  cudaError_t e = read_bad_index_count(&v, reset, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "bad_index_count");
+  *host_out = (int64_t)v;
+  return DIVREC_OK;
+}
+
+// ---- peer buffers (CUDA IPC): device memory another process of the same node can map ----
+int divrec_peer_alloc(size_t bytes, void** ptr_out, unsigned char* handle_out) {
+  if (!ptr_out || !handle_out || bytes == 0) return fail(DIVREC_ERR_ARG, "peer_alloc: bad argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == DIVREC_PEER_HANDLE_BYTES, "handle size");
+  void* ptr = nullptr;
+  cudaError_t e = cudaMalloc(&ptr, bytes);
+  if (e != cudaSuccess) return cuda_fail(e, "peer_alloc: cudaMalloc");
+  cudaIpcMemHandle_t hd;
+  e = cudaIpcGetMemHandle(&hd, ptr);
+  if (e != cudaSuccess) { cudaFree(ptr); return cuda_fail(e, "peer_alloc: cudaIpcGetMemHandle"); }
+  memcpy(handle_out, &hd, sizeof(hd));
+  *ptr_out = ptr;
+  return DIVREC_OK;
+}
+int divrec_peer_open(const unsigned char* handle, void** ptr_out) {
+  if (!handle || !ptr_out) return fail(DIVREC_ERR_ARG, "peer_open: bad argument");
+  cudaIpcMemHandle_t hd;
+  memcpy(&hd, handle, sizeof(hd));
+  cudaError_t e = cudaIpcOpenMemHandle(ptr_out, hd, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) return cuda_fail(e, "peer_open: cudaIpcOpenMemHandle");
+  return DIVREC_OK;
+}
+int divrec_peer_close(void* ptr) {
+  cudaError_t e = cudaIpcCloseMemHandle(ptr);
+  if (e != cudaSuccess) return cuda_fail(e, "peer_close");
+  return DIVREC_OK;
+}
+int divrec_peer_free(void* ptr) {
+  cudaError_t e = cudaFree(ptr);
+  if (e != cudaSuccess) return cuda_fail(e, "peer_free");
   return DIVREC_OK;
 }
 
@@ -464,37 +529,35 @@ int divrec_bpr_sample_triples(const int64_t* pos_rowptr, const int32_t* pos_item
   return DIVREC_OK;
 }
 
-int divrec_bpr_apply_rows(const float* rows, const int64_t* p, const int64_t* n, int64_t N, int d, float* gV, void* stream) {
+int divrec_bpr_apply_rows(const float* rows, const int64_t* p, const int64_t* n, int64_t N, int64_t nI, int d, float* gV, void* stream) {
   if (!rows || !p || !n || !gV) return fail(DIVREC_ERR_ARG, "bpr_apply_rows: null pointer");
-  if (N <= 0) return fail(DIVREC_ERR_ARG, "bpr_apply_rows: N must be positive");
+  if (N <= 0 || nI <= 0) return fail(DIVREC_ERR_ARG, "bpr_apply_rows: N and nI must be positive");
   if (d <= 0 || (d & 3) || d > 1024) return fail(DIVREC_ERR_ARG, "bpr_apply_rows: d must be a multiple of 4, <= 1024");
   if ((reinterpret_cast<uintptr_t>(rows) & 15) || (reinterpret_cast<uintptr_t>(gV) & 15))
     return fail(DIVREC_ERR_ARG, "bpr_apply_rows: rows and gV must be 16-byte aligned");
-  cudaError_t e = launch_bpr_apply_rows(rows, p, n, N, d, gV, reinterpret_cast<cudaStream_t>(stream));
+  cudaError_t e = launch_bpr_apply_rows(rows, p, n, N, nI, d, gV, reinterpret_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "bpr_apply_rows launch");
   return DIVREC_OK;
 }
 
-int divrec_pair_scores(const float* U, const float* V, const int64_t* user_id, const int64_t* item_id, int64_t L,
-                       int d, float* out, void* stream) {
-  int rc = check_rows(U, V, d, "pair_scores");
+int divrec_pair_scores(const float* U, const float* V, int64_t nU, int64_t nI, const int64_t* user_id, const int64_t* item_id,
+                       int64_t L, int d, float* out, void* stream) {
+  int rc = check_rows(U, V, nU, nI, d, "pair_scores");
   if (rc != DIVREC_OK) return rc;
   if (!user_id || !item_id || !out) return fail(DIVREC_ERR_ARG, "pair_scores: null pointer");
   if (L <= 0) return fail(DIVREC_ERR_ARG, "pair_scores: L must be positive");
-  cudaError_t e = launch_pair_scores(U, V, user_id, item_id, L, d, out, reinterpret_cast<cudaStream_t>(stream));
+  cudaError_t e = launch_pair_scores(U, V, nU, nI, user_id, item_id, L, d, out, reinterpret_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "pair_scores launch");
   return DIVREC_OK;
 }
 
-int divrec_pair_scores_bwd(const float* U, const float* V, const int64_t* user_id, const int64_t* item_id,
+int divrec_pair_scores_bwd(const float* U, const float* V, int64_t nU, int64_t nI, const int64_t* user_id, const int64_t* item_id,
                            const float* g, int64_t L, int d, float* gU, float* gV, void* stream) {
-  int rc = check_rows(U, V, d, "pair_scores_bwd");
+  int rc = check_rows(U, V, nU, nI, d, "pair_scores_bwd");
   if (rc != DIVREC_OK) return rc;
   if (!user_id || !item_id || !g) return fail(DIVREC_ERR_ARG, "pair_scores_bwd: null pointer");
   if (L <= 0) return fail(DIVREC_ERR_ARG, "pair_scores_bwd: L must be positive");
-  if ((gU && (reinterpret_cast<uintptr_t>(gU) & 15)) || (gV && (reinterpret_cast<uintptr_t>(gV) & 15)))
-    return fail(DIVREC_ERR_ARG, "pair_scores_bwd: gradient tables must be 16-byte aligned");
-  cudaError_t e = launch_pair_scores_bwd(U, V, user_id, item_id, g, L, d, gU, gV, reinterpret_cast<cudaStream_t>(stream));
+  cudaError_t e = launch_pair_scores_bwd(U, V, nU, nI, user_id, item_id, g, L, d, gU, gV, reinterpret_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "pair_scores_bwd launch");
   return DIVREC_OK;
 }

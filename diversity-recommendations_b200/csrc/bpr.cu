@@ -20,12 +20,38 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
                : "memory");
 }
+__device__ __forceinline__ void red_add_f32(float* addr, float a) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(a) : "memory");
+}
+
+// Rows move as 128-bit vectors when d % 4 == 0 (V4); any other d takes the same kernels one float at a time
+// (the reference's nn.Embedding takes any embedding_dim).  `c` counts vectors (V4) or floats.
+template <bool V4>
+__device__ __forceinline__ float4 ld_row(const float* row, int c) {
+  if (V4) return __ldg(reinterpret_cast<const float4*>(row) + c);
+  return make_float4(__ldg(row + c), 0.f, 0.f, 0.f);
+}
+template <bool V4>
+__device__ __forceinline__ void red_row(float* row, int c, float x, float y, float z, float w) {
+  if (V4) red_add_v4(row + c * 4, x, y, z, w);
+  else red_add_f32(row + c, x);
+}
+
+// ids out of [0, n): torch.nn.Embedding (the reference) raises IndexError / a device assert.  Here the triple is
+// skipped (no out-of-range access) and counted; divrec_bad_index_count reports the count at the caller's next sync.
+__device__ unsigned long long g_bad_ids = 0ull;
+__device__ __forceinline__ bool ids_ok(int64_t iu, int64_t nU, int64_t ia, int64_t ib, int64_t nI, uint32_t lane) {
+  const bool ok = (uint64_t)iu < (uint64_t)nU && (uint64_t)ia < (uint64_t)nI && (uint64_t)ib < (uint64_t)nI;
+  if (!ok && lane == 0) atomicAdd(&g_bad_ids, 1ull);
+  return ok;
+}
 
 // torch.nn.LogSigmoid: min(x,0) - log1p(exp(-|x|))
 __device__ __forceinline__ float neg_logsigmoid(float x) { return log1pf(expf(-fabsf(x))) - fminf(x, 0.f); }
 
+template <bool V4>
 __global__ void __launch_bounds__(256)
-bpr_fwd_kernel(const float* __restrict__ U, const float* __restrict__ V, const int64_t* __restrict__ u,
+bpr_fwd_kernel(const float* __restrict__ U, const float* __restrict__ V, int64_t nU, int64_t nI, const int64_t* __restrict__ u,
                const int64_t* __restrict__ p, const int64_t* __restrict__ n, int64_t B, int d,
                float* __restrict__ pos, float* __restrict__ neg, float* __restrict__ loss_sum,
                int32_t* __restrict__ auc_sum) {
@@ -33,16 +59,18 @@ bpr_fwd_kernel(const float* __restrict__ U, const float* __restrict__ V, const i
   __shared__ int red_auc[8];
   const uint32_t lane = lane_id();
   const int warp = threadIdx.x >> 5;
-  const int nvec = d >> 2;
+  const int nvec = V4 ? d >> 2 : d;
   float wl = 0.f;
   int wa = 0;
   for (int64_t b = (int64_t)blockIdx.x * 8 + warp; b < B; b += (int64_t)gridDim.x * 8) {
-    const float4* ur = reinterpret_cast<const float4*>(U + u[b] * d);
-    const float4* pr = reinterpret_cast<const float4*>(V + p[b] * d);
-    const float4* nr = reinterpret_cast<const float4*>(V + n[b] * d);
+    const int64_t iu = u[b], ip = p[b], in = n[b];
+    if (!ids_ok(iu, nU, ip, in, nI, lane)) { if (lane == 0) { pos[b] = 0.f; neg[b] = 0.f; } continue; }
+    const float* ur = U + iu * d;
+    const float* pr = V + ip * d;
+    const float* nr = V + in * d;
     float sp = 0.f, sn = 0.f;
     for (int c = lane; c < nvec; c += 32) {
-      const float4 a = __ldg(ur + c), x = __ldg(pr + c), y = __ldg(nr + c);
+      const float4 a = ld_row<V4>(ur, c), x = ld_row<V4>(pr, c), y = ld_row<V4>(nr, c);
       sp = fmaf(a.x, x.x, sp); sp = fmaf(a.y, x.y, sp); sp = fmaf(a.z, x.z, sp); sp = fmaf(a.w, x.w, sp);
       sn = fmaf(a.x, y.x, sn); sn = fmaf(a.y, y.y, sn); sn = fmaf(a.z, y.z, sn); sn = fmaf(a.w, y.w, sn);
     }
@@ -67,16 +95,18 @@ bpr_fwd_kernel(const float* __restrict__ U, const float* __restrict__ V, const i
   }
 }
 
+template <bool V4>
 __global__ void __launch_bounds__(256)
-bpr_bwd_kernel(const float* __restrict__ U, const float* __restrict__ V, const int64_t* __restrict__ u,
+bpr_bwd_kernel(const float* __restrict__ U, const float* __restrict__ V, int64_t nU, int64_t nI, const int64_t* __restrict__ u,
                const int64_t* __restrict__ p, const int64_t* __restrict__ n, const float* __restrict__ pos,
                const float* __restrict__ neg, const float* __restrict__ g, float grad_scale, int64_t B, int d,
                float* __restrict__ gU, float* __restrict__ gV) {
   const uint32_t lane = lane_id();
   const int warp = threadIdx.x >> 5;
-  const int nvec = d >> 2;
+  const int nvec = V4 ? d >> 2 : d;
   for (int64_t b = (int64_t)blockIdx.x * 8 + warp; b < B; b += (int64_t)gridDim.x * 8) {
     const int64_t iu = u[b], ip = p[b], in = n[b];
+    if (!ids_ok(iu, nU, ip, in, nI, lane)) continue;
     float c;
     if (g != nullptr) {
       c = g[b];
@@ -84,15 +114,15 @@ bpr_bwd_kernel(const float* __restrict__ U, const float* __restrict__ V, const i
       const float x = pos[b] - neg[b];
       c = -grad_scale / (1.0f + expf(x));  // d/dx [-logsigmoid(x)] = -sigmoid(-x)
     }
-    const float4* ur = reinterpret_cast<const float4*>(U + iu * d);
-    const float4* pr = reinterpret_cast<const float4*>(V + ip * d);
-    const float4* nr = reinterpret_cast<const float4*>(V + in * d);
+    const float* ur = U + iu * d;
+    const float* pr = V + ip * d;
+    const float* nr = V + in * d;
     for (int v = lane; v < nvec; v += 32) {
-      const float4 a = __ldg(ur + v), x = __ldg(pr + v), y = __ldg(nr + v);
-      if (gU) red_add_v4(gU + iu * d + v * 4, c * (x.x - y.x), c * (x.y - y.y), c * (x.z - y.z), c * (x.w - y.w));
+      const float4 a = ld_row<V4>(ur, v), x = ld_row<V4>(pr, v), y = ld_row<V4>(nr, v);
+      if (gU) red_row<V4>(gU + iu * d, v, c * (x.x - y.x), c * (x.y - y.y), c * (x.z - y.z), c * (x.w - y.w));
       if (gV) {
-        red_add_v4(gV + ip * d + v * 4, c * a.x, c * a.y, c * a.z, c * a.w);
-        red_add_v4(gV + in * d + v * 4, -c * a.x, -c * a.y, -c * a.z, -c * a.w);
+        red_row<V4>(gV + ip * d, v, c * a.x, c * a.y, c * a.z, c * a.w);
+        red_row<V4>(gV + in * d, v, -c * a.x, -c * a.y, -c * a.z, -c * a.w);
       }
     }
   }
@@ -103,13 +133,20 @@ bpr_bwd_kernel(const float* __restrict__ U, const float* __restrict__ V, const i
 // rows of a triple are read once into registers, used for the scores, then for the three scatter-adds.  DRAM
 // traffic per triple = 3 row reads + 3 row read-modify-writes = the algorithmic figure (the two-kernel form reads
 // the rows twice).  NV = float4 chunks of a row per lane (d <= 128 * NV).
-template <int NV>
+//
+// OWNER (multi-GPU, item gradient sharded by owner): the item table's gradient is not one local dense table but
+// `n_slices` slices of `slice_rows` items, slice r living on rank r; `slices` holds their device addresses -- this rank's
+// own slice and the PEER-MAPPED slices of the other ranks (CUDA IPC over NVLink / NVSwitch).  The scatter-add of an item
+// row goes straight to its owner with the same vector red: the exchange of the item gradient happens inside this
+// kernel, row by row, overlapped with the gathers of the next triples -- no pack, no all-to-all, no second apply pass,
+// and every rank ends up holding the globally summed gradient of the items it owns (reduce-scatter semantics).
+template <int NV, bool OWNER>
 __global__ void __launch_bounds__(256)
-bpr_step_kernel(const float* __restrict__ U, const float* __restrict__ V, const int64_t* __restrict__ u,
+bpr_step_kernel(const float* __restrict__ U, const float* __restrict__ V, int64_t nU, int64_t nI, const int64_t* __restrict__ u,
                 const int64_t* __restrict__ p, const int64_t* __restrict__ n, int64_t B, int d, float grad_scale,
                 float* __restrict__ pos, float* __restrict__ neg, float* __restrict__ loss_sum,
                 int32_t* __restrict__ auc_sum, float* __restrict__ gU, float* __restrict__ gV,
-                float* __restrict__ item_rows) {
+                float* __restrict__ item_rows, float* const* __restrict__ slices, int64_t slice_rows) {
   __shared__ float red_loss[8];
   __shared__ int red_auc[8];
   const uint32_t lane = lane_id();
@@ -119,6 +156,7 @@ bpr_step_kernel(const float* __restrict__ U, const float* __restrict__ V, const 
   int wa = 0;
   for (int64_t b = (int64_t)blockIdx.x * 8 + warp; b < B; b += (int64_t)gridDim.x * 8) {
     const int64_t iu = u[b], ip = p[b], in = n[b];
+    if (!ids_ok(iu, nU, ip, in, nI, lane)) { if (lane == 0) { if (pos) pos[b] = 0.f; if (neg) neg[b] = 0.f; } continue; }
     const float4* ur = reinterpret_cast<const float4*>(U + iu * d);
     const float4* pr = reinterpret_cast<const float4*>(V + ip * d);
     const float4* nr = reinterpret_cast<const float4*>(V + in * d);
@@ -144,14 +182,24 @@ bpr_step_kernel(const float* __restrict__ U, const float* __restrict__ V, const 
       wl += neg_logsigmoid(sp - sn);
       wa += (sp >= sn) ? 1 : 0;
     }
+    float* gp = nullptr;
+    float* gn = nullptr;
+    if (OWNER) {
+      const int64_t op = ip / slice_rows, on = in / slice_rows;
+      gp = slices[op] + (ip - op * slice_rows) * d;
+      gn = slices[on] + (in - on * slice_rows) * d;
+    } else if (gV) {
+      gp = gV + ip * d;
+      gn = gV + in * d;
+    }
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
       const int v = (int)lane + 32 * j;
       if (v < nvec) {
         if (gU) red_add_v4(gU + iu * d + v * 4, c * (x[j].x - y[j].x), c * (x[j].y - y[j].y), c * (x[j].z - y[j].z), c * (x[j].w - y[j].w));
-        if (gV) {
-          red_add_v4(gV + ip * d + v * 4, c * a[j].x, c * a[j].y, c * a[j].z, c * a[j].w);
-          red_add_v4(gV + in * d + v * 4, -c * a[j].x, -c * a[j].y, -c * a[j].z, -c * a[j].w);
+        if (gp) {
+          red_add_v4(gp + v * 4, c * a[j].x, c * a[j].y, c * a[j].z, c * a[j].w);
+          red_add_v4(gn + v * 4, -c * a[j].x, -c * a[j].y, -c * a[j].z, -c * a[j].w);
         }
         // sparse form of the item gradient: row b = c U[u_b], to be added to gV[p_b] and subtracted from gV[n_b]
         if (item_rows) reinterpret_cast<float4*>(item_rows + b * d)[v] = make_float4(c * a[j].x, c * a[j].y, c * a[j].z, c * a[j].w);
@@ -173,12 +221,13 @@ bpr_step_kernel(const float* __restrict__ U, const float* __restrict__ V, const 
 // gV[p_j] += rows_j;  gV[n_j] -= rows_j  -- applies item-gradient rows gathered from all ranks (bpr_step's item_rows)
 __global__ void __launch_bounds__(256)
 bpr_apply_rows_kernel(const float* __restrict__ rows, const int64_t* __restrict__ p, const int64_t* __restrict__ n,
-                      int64_t N, int d, float* __restrict__ gV) {
+                      int64_t N, int64_t nI, int d, float* __restrict__ gV) {
   const uint32_t lane = lane_id();
   const int warp = threadIdx.x >> 5;
   const int nvec = d >> 2;
   for (int64_t b = (int64_t)blockIdx.x * 8 + warp; b < N; b += (int64_t)gridDim.x * 8) {
     const int64_t ip = p[b], in = n[b];
+    if (!ids_ok(0, 1, ip, in, nI, lane)) continue;
     for (int v = lane; v < nvec; v += 32) {
       const float4 r = __ldg(reinterpret_cast<const float4*>(rows + b * d) + v);
       red_add_v4(gV + ip * d + v * 4, r.x, r.y, r.z, r.w);
@@ -187,18 +236,21 @@ bpr_apply_rows_kernel(const float* __restrict__ rows, const int64_t* __restrict_
   }
 }
 
+template <bool V4>
 __global__ void __launch_bounds__(256)
-pair_scores_kernel(const float* __restrict__ U, const float* __restrict__ V, const int64_t* __restrict__ uid,
+pair_scores_kernel(const float* __restrict__ U, const float* __restrict__ V, int64_t nU, int64_t nI, const int64_t* __restrict__ uid,
                    const int64_t* __restrict__ iid, int64_t L, int d, float* __restrict__ out) {
   const uint32_t lane = lane_id();
   const int warp = threadIdx.x >> 5;
-  const int nvec = d >> 2;
+  const int nvec = V4 ? d >> 2 : d;
   for (int64_t l = (int64_t)blockIdx.x * 8 + warp; l < L; l += (int64_t)gridDim.x * 8) {
-    const float4* ur = reinterpret_cast<const float4*>(U + uid[l] * d);
-    const float4* vr = reinterpret_cast<const float4*>(V + iid[l] * d);
+    const int64_t iu = uid[l], ii = iid[l];
+    if (!ids_ok(iu, nU, ii, ii, nI, lane)) { if (lane == 0) out[l] = 0.f; continue; }
+    const float* ur = U + iu * d;
+    const float* vr = V + ii * d;
     float s = 0.f;
     for (int c = lane; c < nvec; c += 32) {
-      const float4 a = __ldg(ur + c), x = __ldg(vr + c);
+      const float4 a = ld_row<V4>(ur, c), x = ld_row<V4>(vr, c);
       s = fmaf(a.x, x.x, s); s = fmaf(a.y, x.y, s); s = fmaf(a.z, x.z, s); s = fmaf(a.w, x.w, s);
     }
     s = warp_sum(s);
@@ -207,22 +259,24 @@ pair_scores_kernel(const float* __restrict__ U, const float* __restrict__ V, con
 }
 
 // backward of pair_scores: gU[uid[l]] += g[l] V[iid[l]];  gV[iid[l]] += g[l] U[uid[l]]
+template <bool V4>
 __global__ void __launch_bounds__(256)
-pair_scores_bwd_kernel(const float* __restrict__ U, const float* __restrict__ V, const int64_t* __restrict__ uid,
+pair_scores_bwd_kernel(const float* __restrict__ U, const float* __restrict__ V, int64_t nU, int64_t nI, const int64_t* __restrict__ uid,
                        const int64_t* __restrict__ iid, const float* __restrict__ g, int64_t L, int d,
                        float* __restrict__ gU, float* __restrict__ gV) {
   const uint32_t lane = lane_id();
   const int warp = threadIdx.x >> 5;
-  const int nvec = d >> 2;
+  const int nvec = V4 ? d >> 2 : d;
   for (int64_t l = (int64_t)blockIdx.x * 8 + warp; l < L; l += (int64_t)gridDim.x * 8) {
     const int64_t iu = uid[l], ii = iid[l];
+    if (!ids_ok(iu, nU, ii, ii, nI, lane)) continue;
     const float c = g[l];
-    const float4* ur = reinterpret_cast<const float4*>(U + iu * d);
-    const float4* vr = reinterpret_cast<const float4*>(V + ii * d);
+    const float* ur = U + iu * d;
+    const float* vr = V + ii * d;
     for (int v = lane; v < nvec; v += 32) {
-      const float4 a = __ldg(ur + v), x = __ldg(vr + v);
-      if (gU) red_add_v4(gU + iu * d + v * 4, c * x.x, c * x.y, c * x.z, c * x.w);
-      if (gV) red_add_v4(gV + ii * d + v * 4, c * a.x, c * a.y, c * a.z, c * a.w);
+      const float4 a = ld_row<V4>(ur, v), x = ld_row<V4>(vr, v);
+      if (gU) red_row<V4>(gU + iu * d, v, c * x.x, c * x.y, c * x.z, c * x.w);
+      if (gV) red_row<V4>(gV + ii * d, v, c * a.x, c * a.y, c * a.z, c * a.w);
     }
   }
 }
@@ -321,32 +375,48 @@ inline unsigned warp_grid(int64_t items) {
 
 }  // namespace
 
-cudaError_t launch_bpr_fwd(const float* U, const float* V, const int64_t* u, const int64_t* p, const int64_t* n,
-                           int64_t B, int d, float* pos, float* neg, float* loss_sum, int32_t* auc_sum,
+static inline bool rows_v4(int d, const void* a, const void* b) {
+  return (d & 3) == 0 && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) == 0;
+}
+
+cudaError_t launch_bpr_fwd(const float* U, const float* V, int64_t nU, int64_t nI, const int64_t* u, const int64_t* p,
+                           const int64_t* n, int64_t B, int d, float* pos, float* neg, float* loss_sum, int32_t* auc_sum,
                            cudaStream_t stream) {
-  bpr_fwd_kernel<<<warp_grid(B), 256, 0, stream>>>(U, V, u, p, n, B, d, pos, neg, loss_sum, auc_sum);
+  if (rows_v4(d, U, V)) bpr_fwd_kernel<true><<<warp_grid(B), 256, 0, stream>>>(U, V, nU, nI, u, p, n, B, d, pos, neg, loss_sum, auc_sum);
+  else bpr_fwd_kernel<false><<<warp_grid(B), 256, 0, stream>>>(U, V, nU, nI, u, p, n, B, d, pos, neg, loss_sum, auc_sum);
   count_launch();
   return cudaGetLastError();
 }
 
-cudaError_t launch_bpr_bwd(const float* U, const float* V, const int64_t* u, const int64_t* p, const int64_t* n,
-                           const float* pos, const float* neg, const float* g, float grad_scale, int64_t B, int d,
-                           float* gU, float* gV, cudaStream_t stream) {
-  bpr_bwd_kernel<<<warp_grid(B), 256, 0, stream>>>(U, V, u, p, n, pos, neg, g, grad_scale, B, d, gU, gV);
+cudaError_t launch_bpr_bwd(const float* U, const float* V, int64_t nU, int64_t nI, const int64_t* u, const int64_t* p,
+                           const int64_t* n, const float* pos, const float* neg, const float* g, float grad_scale, int64_t B,
+                           int d, float* gU, float* gV, cudaStream_t stream) {
+  const bool v4 = rows_v4(d, U, V) && rows_v4(d, gU, gV);
+  if (v4) bpr_bwd_kernel<true><<<warp_grid(B), 256, 0, stream>>>(U, V, nU, nI, u, p, n, pos, neg, g, grad_scale, B, d, gU, gV);
+  else bpr_bwd_kernel<false><<<warp_grid(B), 256, 0, stream>>>(U, V, nU, nI, u, p, n, pos, neg, g, grad_scale, B, d, gU, gV);
   count_launch();
   return cudaGetLastError();
 }
 
-cudaError_t launch_bpr_step(const float* U, const float* V, const int64_t* u, const int64_t* p, const int64_t* n, int64_t B,
-                            int d, float grad_scale, float* pos, float* neg, float* loss_sum, int32_t* auc_sum, float* gU,
-                            float* gV, float* item_rows, cudaStream_t stream) {
+cudaError_t launch_bpr_step(const float* U, const float* V, int64_t nU, int64_t nI, const int64_t* u, const int64_t* p,
+                            const int64_t* n, int64_t B, int d, float grad_scale, float* pos, float* neg, float* loss_sum,
+                            int32_t* auc_sum, float* gU, float* gV, float* item_rows, float* const* slices, int64_t slice_rows,
+                            cudaStream_t stream) {
   // every resident warp loops over several triples, so loads of the next triple overlap the scatter-adds of this one
   int64_t g = (B + 7) / 8;
   if (g > 148 * 8) g = 148 * 8;
-  if (d <= 128) bpr_step_kernel<1><<<(unsigned)g, 256, 0, stream>>>(U, V, u, p, n, B, d, grad_scale, pos, neg, loss_sum, auc_sum, gU, gV, item_rows);
-  else if (d <= 256) bpr_step_kernel<2><<<(unsigned)g, 256, 0, stream>>>(U, V, u, p, n, B, d, grad_scale, pos, neg, loss_sum, auc_sum, gU, gV, item_rows);
-  else if (d <= 512) bpr_step_kernel<4><<<(unsigned)g, 256, 0, stream>>>(U, V, u, p, n, B, d, grad_scale, pos, neg, loss_sum, auc_sum, gU, gV, item_rows);
-  else bpr_step_kernel<8><<<(unsigned)g, 256, 0, stream>>>(U, V, u, p, n, B, d, grad_scale, pos, neg, loss_sum, auc_sum, gU, gV, item_rows);
+#define DIVREC_BPR_STEP(NV)                                                                                                        \
+  do {                                                                                                                             \
+    if (slices) bpr_step_kernel<NV, true><<<(unsigned)g, 256, 0, stream>>>(U, V, nU, nI, u, p, n, B, d, grad_scale, pos, neg,      \
+                                                                            loss_sum, auc_sum, gU, nullptr, item_rows, slices, slice_rows); \
+    else bpr_step_kernel<NV, false><<<(unsigned)g, 256, 0, stream>>>(U, V, nU, nI, u, p, n, B, d, grad_scale, pos, neg, loss_sum,  \
+                                                                     auc_sum, gU, gV, item_rows, nullptr, 1);                     \
+  } while (0)
+  if (d <= 128) DIVREC_BPR_STEP(1);
+  else if (d <= 256) DIVREC_BPR_STEP(2);
+  else if (d <= 512) DIVREC_BPR_STEP(4);
+  else DIVREC_BPR_STEP(8);
+#undef DIVREC_BPR_STEP
   count_launch();
   return cudaGetLastError();
 }
@@ -363,27 +433,41 @@ cudaError_t launch_bpr_sample(const int64_t* pos_rowptr, const int32_t* pos_item
   return cudaGetLastError();
 }
 
-cudaError_t launch_bpr_apply_rows(const float* rows, const int64_t* p, const int64_t* n, int64_t N, int d, float* gV,
+cudaError_t launch_bpr_apply_rows(const float* rows, const int64_t* p, const int64_t* n, int64_t N, int64_t nI, int d, float* gV,
                                   cudaStream_t stream) {
   int64_t g = (N + 7) / 8;
   if (g > 148 * 8) g = 148 * 8;
-  bpr_apply_rows_kernel<<<(unsigned)g, 256, 0, stream>>>(rows, p, n, N, d, gV);
+  bpr_apply_rows_kernel<<<(unsigned)g, 256, 0, stream>>>(rows, p, n, N, nI, d, gV);
   count_launch();
   return cudaGetLastError();
 }
 
-cudaError_t launch_pair_scores(const float* U, const float* V, const int64_t* uid, const int64_t* iid, int64_t L,
-                               int d, float* out, cudaStream_t stream) {
-  pair_scores_kernel<<<warp_grid(L), 256, 0, stream>>>(U, V, uid, iid, L, d, out);
+cudaError_t launch_pair_scores(const float* U, const float* V, int64_t nU, int64_t nI, const int64_t* uid, const int64_t* iid,
+                               int64_t L, int d, float* out, cudaStream_t stream) {
+  if (rows_v4(d, U, V)) pair_scores_kernel<true><<<warp_grid(L), 256, 0, stream>>>(U, V, nU, nI, uid, iid, L, d, out);
+  else pair_scores_kernel<false><<<warp_grid(L), 256, 0, stream>>>(U, V, nU, nI, uid, iid, L, d, out);
   count_launch();
   return cudaGetLastError();
 }
 
-cudaError_t launch_pair_scores_bwd(const float* U, const float* V, const int64_t* uid, const int64_t* iid,
+cudaError_t launch_pair_scores_bwd(const float* U, const float* V, int64_t nU, int64_t nI, const int64_t* uid, const int64_t* iid,
                                    const float* g, int64_t L, int d, float* gU, float* gV, cudaStream_t stream) {
-  pair_scores_bwd_kernel<<<warp_grid(L), 256, 0, stream>>>(U, V, uid, iid, g, L, d, gU, gV);
+  const bool v4 = rows_v4(d, U, V) && rows_v4(d, gU, gV);
+  if (v4) pair_scores_bwd_kernel<true><<<warp_grid(L), 256, 0, stream>>>(U, V, nU, nI, uid, iid, g, L, d, gU, gV);
+  else pair_scores_bwd_kernel<false><<<warp_grid(L), 256, 0, stream>>>(U, V, nU, nI, uid, iid, g, L, d, gU, gV);
   count_launch();
   return cudaGetLastError();
+}
+
+cudaError_t read_bad_index_count(unsigned long long* host_out, int reset, cudaStream_t stream) {
+  cudaError_t e = cudaMemcpyFromSymbolAsync(host_out, g_bad_ids, sizeof(unsigned long long), 0, cudaMemcpyDeviceToHost, stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+  if (e == cudaSuccess && reset) {
+    const unsigned long long zero = 0ull;
+    e = cudaMemcpyToSymbolAsync(g_bad_ids, &zero, sizeof(zero), 0, cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+  }
+  return e;
 }
 
 cudaError_t launch_bpr_loss_fwd(const float* pos, const float* neg, int64_t B, float* lv, int32_t* hit, cudaStream_t stream) {

@@ -165,25 +165,27 @@ cudaError_t launch_ild_matrix(const void* D, int d_is_int32, int64_t nI, const i
 cudaError_t launch_coverage_hist(const int64_t* recs, int64_t n, int64_t nI, int32_t* counts, cudaStream_t stream);
 cudaError_t launch_entropy(const int32_t* counts, int64_t nI, float* out2, cudaStream_t stream);
 
-cudaError_t launch_bpr_fwd(const float* U, const float* V, const int64_t* u, const int64_t* p, const int64_t* n,
-                           int64_t B, int d, float* pos, float* neg, float* loss_sum, int32_t* auc_sum,
+cudaError_t launch_bpr_fwd(const float* U, const float* V, int64_t nU, int64_t nI, const int64_t* u, const int64_t* p,
+                           const int64_t* n, int64_t B, int d, float* pos, float* neg, float* loss_sum, int32_t* auc_sum,
                            cudaStream_t stream);
-cudaError_t launch_bpr_bwd(const float* U, const float* V, const int64_t* u, const int64_t* p, const int64_t* n,
-                           const float* pos, const float* neg, const float* g, float grad_scale, int64_t B, int d,
-                           float* gU, float* gV, cudaStream_t stream);
-cudaError_t launch_bpr_step(const float* U, const float* V, const int64_t* u, const int64_t* p, const int64_t* n, int64_t B,
-                            int d, float grad_scale, float* pos, float* neg, float* loss_sum, int32_t* auc_sum, float* gU,
-                            float* gV, float* item_rows, cudaStream_t stream);
+cudaError_t launch_bpr_bwd(const float* U, const float* V, int64_t nU, int64_t nI, const int64_t* u, const int64_t* p,
+                           const int64_t* n, const float* pos, const float* neg, const float* g, float grad_scale, int64_t B,
+                           int d, float* gU, float* gV, cudaStream_t stream);
+// slices != null: the item gradient goes to per-owner slices of slice_rows items (peer-mapped addresses), gV unused
+cudaError_t launch_bpr_step(const float* U, const float* V, int64_t nU, int64_t nI, const int64_t* u, const int64_t* p,
+                            const int64_t* n, int64_t B, int d, float grad_scale, float* pos, float* neg, float* loss_sum,
+                            int32_t* auc_sum, float* gU, float* gV, float* item_rows, float* const* slices, int64_t slice_rows,
+                            cudaStream_t stream);
 cudaError_t launch_bpr_sample(const int64_t* pos_rowptr, const int32_t* pos_items, const int64_t* excl_rowptr,
                               const int32_t* excl_items, int64_t nU, int64_t nI, int m, uint64_t seed, int64_t* out_u,
                               int64_t* out_p, int64_t* out_n, cudaStream_t stream);
-cudaError_t launch_bpr_apply_rows(const float* rows, const int64_t* p, const int64_t* n, int64_t N, int d, float* gV,
+cudaError_t launch_bpr_apply_rows(const float* rows, const int64_t* p, const int64_t* n, int64_t N, int64_t nI, int d, float* gV,
                                   cudaStream_t stream);
-cudaError_t launch_pair_scores(const float* U, const float* V, const int64_t* uid, const int64_t* iid, int64_t L,
-                               int d, float* out, cudaStream_t stream);
-
-cudaError_t launch_pair_scores_bwd(const float* U, const float* V, const int64_t* uid, const int64_t* iid,
+cudaError_t launch_pair_scores(const float* U, const float* V, int64_t nU, int64_t nI, const int64_t* uid, const int64_t* iid,
+                               int64_t L, int d, float* out, cudaStream_t stream);
+cudaError_t launch_pair_scores_bwd(const float* U, const float* V, int64_t nU, int64_t nI, const int64_t* uid, const int64_t* iid,
                                    const float* g, int64_t L, int d, float* gU, float* gV, cudaStream_t stream);
+cudaError_t read_bad_index_count(unsigned long long* host_out, int reset, cudaStream_t stream);
 
 cudaError_t launch_ild_labels(const int64_t* labels, int64_t nI, const int64_t* recs, int64_t nU, int k, float* out,
                               cudaStream_t stream);

@@ -44,13 +44,19 @@ SIGNATURES = {
     "divrec_ild_matrix": (_i32, [_vp, _i32, _i64, _vp, _i64, _i32, _vp, _vp]),
     "divrec_coverage_hist": (_i32, [_vp, _i64, _i64, _vp, _vp]),
     "divrec_entropy_from_counts": (_i32, [_vp, _i64, _vp, _vp]),
-    "divrec_bpr_fwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp]),
-    "divrec_bpr_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _i64, _i32, _vp, _vp, _vp]),
-    "divrec_bpr_step": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "divrec_bpr_apply_rows": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _vp]),
+    "divrec_bpr_fwd": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "divrec_bpr_bwd": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _i64, _i32, _vp, _vp, _vp]),
+    "divrec_bpr_step": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _i64, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "divrec_bpr_step_owner": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _i64, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _vp]),
+    "divrec_bad_index_count": (_i32, [_c.POINTER(_c.c_int64), _i32, _vp]),
+    "divrec_peer_alloc": (_i32, [_sz, _c.POINTER(_vp), _c.POINTER(_c.c_ubyte)]),
+    "divrec_peer_open": (_i32, [_c.POINTER(_c.c_ubyte), _c.POINTER(_vp)]),
+    "divrec_peer_close": (_i32, [_vp]),
+    "divrec_peer_free": (_i32, [_vp]),
+    "divrec_bpr_apply_rows": (_i32, [_vp, _vp, _vp, _i64, _i64, _i32, _vp, _vp]),
     "divrec_bpr_sample_triples": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _c.c_uint64, _vp, _vp, _vp, _vp]),
-    "divrec_pair_scores": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp]),
-    "divrec_pair_scores_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp]),
+    "divrec_pair_scores": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp, _i64, _i32, _vp, _vp]),
+    "divrec_pair_scores_bwd": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp]),
     "divrec_ild_labels": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _vp]),
     "divrec_coverage_hist_ranks": (_i32, [_vp, _i64, _i32, _i64, _vp, _vp, _vp]),
     "divrec_relevance_metrics": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp]),
@@ -363,7 +369,7 @@ def bpr_fwd(U, V, u, p, n):
     loss_sum = torch.zeros(1, dtype=torch.float32, device=U.device)
     auc_sum = torch.zeros(1, dtype=torch.int32, device=U.device)
     with torch.cuda.device(U.device):
-        rc = lib.divrec_bpr_fwd(_ptr(U), _ptr(V), _ptr(u), _ptr(p), _ptr(n), B, d, _ptr(pos), _ptr(neg),
+        rc = lib.divrec_bpr_fwd(_ptr(U), _ptr(V), U.shape[0], V.shape[0], _ptr(u), _ptr(p), _ptr(n), B, d, _ptr(pos), _ptr(neg),
                                 _ptr(loss_sum), _ptr(auc_sum), _stream(U.device))
     _check(rc, "divrec_bpr_fwd")
     return pos, neg, loss_sum, auc_sum
@@ -389,6 +395,7 @@ def bpr_step(U, V, u, p, n, grad_scale: float, gU: Optional[torch.Tensor], gV: O
     d = U.shape[1]
     if item_rows is not None and tuple(item_rows.shape) != (B, d):
         raise ValueError("item_rows must be [B, d]")
+    want_scores = want_scores or d % 4 != 0  # the two-pass form of odd row widths needs the score buffers
     pos = torch.empty(B, dtype=torch.float32, device=U.device) if want_scores else None
     neg = torch.empty(B, dtype=torch.float32, device=U.device) if want_scores else None
     if loss_sum is None:
@@ -396,10 +403,106 @@ def bpr_step(U, V, u, p, n, grad_scale: float, gU: Optional[torch.Tensor], gV: O
     if auc_sum is None:
         auc_sum = torch.zeros(1, dtype=torch.int32, device=U.device)
     with torch.cuda.device(U.device):
-        rc = lib.divrec_bpr_step(_ptr(U), _ptr(V), _ptr(u), _ptr(p), _ptr(n), B, d, float(grad_scale), _ptr(pos), _ptr(neg),
+        rc = lib.divrec_bpr_step(_ptr(U), _ptr(V), U.shape[0], V.shape[0], _ptr(u), _ptr(p), _ptr(n), B, d, float(grad_scale), _ptr(pos), _ptr(neg),
                                  _ptr(loss_sum), _ptr(auc_sum), _ptr(gU), _ptr(gV), _ptr(item_rows), _stream(U.device))
     _check(rc, "divrec_bpr_step")
     return pos, neg, loss_sum, auc_sum
+
+
+def bad_index_count(device=None, reset: bool = True) -> int:
+    """Triples / pairs the row-gather kernels skipped since the last reset because an id was outside its table
+    (synchronises the current stream).  The reference's nn.Embedding raises IndexError for such ids."""
+    lib = load_library()
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    out = _c.c_int64(0)
+    with torch.cuda.device(dev):
+        _check(lib.divrec_bad_index_count(_c.byref(out), 1 if reset else 0, _stream(dev)), "divrec_bad_index_count")
+    return int(out.value)
+
+
+def raise_on_bad_indices(device=None) -> None:
+    n_bad = bad_index_count(device)
+    if n_bad:
+        raise IndexError(f"{n_bad} (user, item) ids were outside the embedding tables (index out of range in self)")
+
+
+class PeerBuffer:
+    """A float32 [rows, cols] device buffer allocated by the library (cudaMalloc) and exported over CUDA IPC, plus the
+    peers' buffers mapped into this process: `ptrs` is an int64 device tensor of world addresses (this rank's own buffer at
+    index `rank`), `local` a torch view of the own buffer.  Used by the owner-sharded BPR step (divrec_bpr_step_owner)."""
+
+    def __init__(self, rows: int, cols: int, device, group=None):
+        import torch.distributed as dist
+        lib = load_library()
+        self.dev = torch.device(device)
+        self.rows, self.cols = int(rows), int(cols)
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self._own = _vp()
+        handle = (_c.c_ubyte * 64)()
+        with torch.cuda.device(self.dev):
+            _check(lib.divrec_peer_alloc(self.rows * self.cols * 4, _c.byref(self._own), handle), "divrec_peer_alloc")
+        self._opened = []
+        addrs = [0] * self.world
+        addrs[self.rank] = int(self._own.value)
+        if self.world > 1:
+            mine = torch.tensor(list(handle), dtype=torch.uint8, device=self.dev)
+            allh = torch.empty((self.world, 64), dtype=torch.uint8, device=self.dev)
+            dist.all_gather_into_tensor(allh, mine, group=group)
+            allh = allh.cpu()
+            with torch.cuda.device(self.dev):
+                for r in range(self.world):
+                    if r == self.rank:
+                        continue
+                    hb = (_c.c_ubyte * 64)(*allh[r].tolist())
+                    ptr = _vp()
+                    _check(lib.divrec_peer_open(hb, _c.byref(ptr)), "divrec_peer_open")
+                    self._opened.append(ptr)
+                    addrs[r] = int(ptr.value)
+        self.ptrs = torch.tensor(addrs, dtype=torch.int64, device=self.dev)
+
+        class _Raw:  # __cuda_array_interface__ view of the own buffer
+            pass
+        raw = _Raw()
+        raw.__cuda_array_interface__ = {"shape": (self.rows, self.cols), "typestr": "<f4", "data": (int(self._own.value), False),
+                                        "version": 3, "strides": None}
+        self._raw = raw
+        self.local = torch.as_tensor(raw, device=self.dev)
+
+    def close(self):
+        lib = load_library()
+        if self._own is None:
+            return
+        torch.cuda.synchronize(self.dev)
+        with torch.cuda.device(self.dev):
+            for ptr in self._opened:
+                lib.divrec_peer_close(ptr)
+            self.local = None
+            lib.divrec_peer_free(self._own)
+        self._opened, self._own = [], None
+
+
+def bpr_step_owner(U, V, u, p, n, grad_scale: float, gU: Optional[torch.Tensor], slices: torch.Tensor, slice_rows: int,
+                   loss_sum: Optional[torch.Tensor] = None, auc_sum: Optional[torch.Tensor] = None):
+    """One-pass BPR step whose item-gradient updates go straight to the owning rank's slice (`slices`: int64 device tensor
+    of per-rank slice addresses, PeerBuffer.ptrs).  Returns (loss_sum [1], auc_sum [1])."""
+    lib = load_library()
+    U = _cuda(U, "U", torch.float32)
+    V = _cuda(V, "V", torch.float32)
+    u = _cuda(u, "user_id", torch.int64)
+    p = _cuda(p, "positive_item_id", torch.int64)
+    n = _cuda(n, "negative_item_id", torch.int64)
+    slices = _cuda(slices, "slices", torch.int64)
+    if loss_sum is None:
+        loss_sum = torch.zeros(1, dtype=torch.float32, device=U.device)
+    if auc_sum is None:
+        auc_sum = torch.zeros(1, dtype=torch.int32, device=U.device)
+    with torch.cuda.device(U.device):
+        rc = lib.divrec_bpr_step_owner(_ptr(U), _ptr(V), U.shape[0], V.shape[0], _ptr(u), _ptr(p), _ptr(n), u.numel(), U.shape[1],
+                                       float(grad_scale), None, None, _ptr(loss_sum), _ptr(auc_sum), _ptr(gU), _ptr(slices),
+                                       slices.numel(), int(slice_rows), _stream(U.device))
+    _check(rc, "divrec_bpr_step_owner")
+    return loss_sum, auc_sum
 
 
 def bpr_apply_rows(rows: torch.Tensor, p: torch.Tensor, n: torch.Tensor, gV: torch.Tensor) -> None:
@@ -414,7 +517,7 @@ def bpr_apply_rows(rows: torch.Tensor, p: torch.Tensor, n: torch.Tensor, gV: tor
     if p.numel() != N or n.numel() != N or gV.shape[1] != d:
         raise ValueError("rows [N,d], p [N], n [N], gV [nI,d] expected")
     with torch.cuda.device(rows.device):
-        rc = lib.divrec_bpr_apply_rows(_ptr(rows), _ptr(p), _ptr(n), N, d, _ptr(gV), _stream(rows.device))
+        rc = lib.divrec_bpr_apply_rows(_ptr(rows), _ptr(p), _ptr(n), N, gV.shape[0], d, _ptr(gV), _stream(rows.device))
     _check(rc, "divrec_bpr_apply_rows")
 
 
@@ -451,7 +554,7 @@ def bpr_bwd(U, V, u, p, n, pos, neg, grad_scale: float, gU: torch.Tensor, gV: to
     B = u.numel()
     d = U.shape[1]
     with torch.cuda.device(U.device):
-        rc = lib.divrec_bpr_bwd(_ptr(U), _ptr(V), _ptr(u), _ptr(p), _ptr(n), _ptr(pos), _ptr(neg), _ptr(g),
+        rc = lib.divrec_bpr_bwd(_ptr(U), _ptr(V), U.shape[0], V.shape[0], _ptr(u), _ptr(p), _ptr(n), _ptr(pos), _ptr(neg), _ptr(g),
                                 float(grad_scale), B, d, _ptr(gU), _ptr(gV), _stream(U.device))
     _check(rc, "divrec_bpr_bwd")
 
@@ -469,7 +572,7 @@ def pair_scores(U, V, user_id, item_id) -> torch.Tensor:
     if L == 0:
         return out
     with torch.cuda.device(U.device):
-        rc = lib.divrec_pair_scores(_ptr(U), _ptr(V), _ptr(user_id), _ptr(item_id), L, U.shape[1], _ptr(out), _stream(U.device))
+        rc = lib.divrec_pair_scores(_ptr(U), _ptr(V), U.shape[0], V.shape[0], _ptr(user_id), _ptr(item_id), L, U.shape[1], _ptr(out), _stream(U.device))
     _check(rc, "divrec_pair_scores")
     return out
 
@@ -481,7 +584,7 @@ def pair_scores_bwd(U, V, user_id, item_id, g, gU: Optional[torch.Tensor], gV: O
     if L == 0:
         return
     with torch.cuda.device(U.device):
-        rc = lib.divrec_pair_scores_bwd(_ptr(U), _ptr(V), _ptr(user_id), _ptr(item_id), _ptr(g), L, U.shape[1],
+        rc = lib.divrec_pair_scores_bwd(_ptr(U), _ptr(V), U.shape[0], V.shape[0], _ptr(user_id), _ptr(item_id), _ptr(g), L, U.shape[1],
                                         _ptr(gU), _ptr(gV), _stream(U.device))
     _check(rc, "divrec_pair_scores_bwd")
 

@@ -16,15 +16,25 @@ from ..datasets.base_datasets import interactions_to_csr
 from ..losses.base_losses import RecommendationsAwareLoss
 
 
+_last = {"key": None, "value": None}
+
+
 def _per_user(interactions: torch.LongTensor, recommendations: torch.LongTensor) -> torch.Tensor:
-    """[4, U] fp32: precision, recall, average precision, ndcg"""
+    """[4, U] fp32: precision, recall, average precision, ndcg.  The four metric functions of one evaluation are called on
+    the same two tensors: the CSR build and the kernel run once and are shared (keyed on the tensors' storage and version)."""
+    key = (interactions.data_ptr(), interactions._version, tuple(interactions.shape), recommendations.data_ptr(),
+           recommendations._version, tuple(recommendations.shape), str(recommendations.device))
+    if _last["key"] == key:
+        return _last["value"]
     dev = recommendations.device
     n_users = recommendations.size(0)
     inter = interactions.to(dev)
     inter = inter[inter[:, 0] < n_users]
     rowptr, items = interactions_to_csr(inter, n_users)
     raw_counts = torch.bincount(inter[:, 0], minlength=n_users).to(torch.int32)
-    return _native.relevance_metrics(recommendations, rowptr, items, raw_counts)
+    out = _native.relevance_metrics(recommendations, rowptr, items, raw_counts)
+    _last["key"], _last["value"] = key, out
+    return out
 
 
 def precision_at_k(interactions: torch.LongTensor, recommendations: torch.LongTensor):

@@ -5,22 +5,23 @@ The path shards two ways:
     of the [I] coverage histogram and one of the (ILD sum, user count) pair;
   * item table sharded (large catalogues) -- every rank scores all query users against its slice, one
     all_gather of the per-shard [U,k] (score, id) lists, then the n-way merge kernel;
-  * BPR -- triples partitioned by user shard (user gradients stay local), item gradient all_reduce.
+  * BPR -- triples partitioned by user shard (user gradients stay local); the item gradient is either sharded by
+    OWNER and exchanged inside the step kernel over NVLink peer memory (divrec_bpr_step_owner, the default on GPUs), or
+    all-reduced dense, or all-gathered as per-triple rows (BprShardedState.route).
 
-`kernels` is the compute backend (default: the ctypes binding of libdivrec_b200.so).  It is a parameter only
-so that the sharding / collective logic can be exercised on CPU with the gloo backend in tests; the product
-path never substitutes it.
+The compute backend is the ctypes binding of libdivrec_b200.so, always: there is no backend parameter.  (The 2-rank gloo
+tests on CPU replace this module's `_native` attribute with an oracle-backed stand-in -- a monkeypatch in the test, not
+a seam in the product.)
 """
 from typing import Optional, Tuple
 
 import torch
 import torch.distributed as dist
 
+from . import _native
 
-def _kernels(kernels):
-    if kernels is not None:
-        return kernels
-    from . import _native
+
+def _kernels():
     return _native
 
 
@@ -38,10 +39,10 @@ def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
 
 
 def recommend_user_sharded(U: torch.Tensor, V: torch.Tensor, seen_rowptr: Optional[torch.Tensor],
-                           seen_items: Optional[torch.Tensor], k: int, group=None, kernels=None):
+                           seen_items: Optional[torch.Tensor], k: int, group=None):
     """Score this rank's contiguous range of users against the replicated item table.
     Returns (items [n_local,k], scores [n_local,k], ild_local [n_local], ild_mean_global, coverage_counts_global, (a,b))."""
-    K = _kernels(kernels)
+    K = _kernels()
     rank, world = _world(group)
     nU = U.shape[0]
     a, b = shard_range(nU, rank, world)
@@ -68,11 +69,11 @@ def _all_gather_stacked(t: torch.Tensor, world: int, group) -> torch.Tensor:
 
 def recommend_item_sharded(U: torch.Tensor, V_shard: torch.Tensor, shard_offset: int, k: int,
                            seen_rowptr: Optional[torch.Tensor] = None, seen_items: Optional[torch.Tensor] = None,
-                           group=None, kernels=None) -> Tuple[torch.Tensor, torch.Tensor]:
+                           group=None) -> Tuple[torch.Tensor, torch.Tensor]:
     """Every rank holds items [shard_offset, shard_offset + len(V_shard)) and all query users.
     Local top-k with global ids -> all_gather -> merge (ties -> lowest id; deterministic because the merge
     uses the total order (score desc, id asc)).  Returns the global (scores [U,k], items [U,k]) on every rank."""
-    K = _kernels(kernels)
+    K = _kernels()
     rank, world = _world(group)
     s, i = K.score_topk(U, V_shard, k, seen_rowptr, seen_items, item_id_offset=shard_offset)
     if world == 1:
@@ -93,50 +94,118 @@ def recommend_item_sharded(U: torch.Tensor, V_shard: torch.Tensor, shard_offset:
     return K.topk_merge(_all_gather_stacked(s, world, group), _all_gather_stacked(i, world, group))
 
 
-def bpr_step_sharded(U: torch.Tensor, V: torch.Tensor, u: torch.Tensor, p: torch.Tensor, n: torch.Tensor,
-                     global_batch: int, group=None, kernels=None, item_grad: str = "dense"):
-    """One BPR forward/backward on this rank's triples (its users only).  Gradients are those of the GLOBAL
-    mean loss: every rank scales by 1 / global_batch, the item-table gradient is summed over ranks, the user
-    gradient needs no communication because a user's triples live on one rank.
+class BprShardedState:
+    """Buffers and exchange route of the user-sharded BPR step (BASELINE.json config 3), built once and reused every step.
 
-    item_grad: "dense" (default) all-reduces the [nI, d] item gradient (BASELINE.json config 3 as stated).
-    "sparse" all-gathers the per-triple rows g_b U[u_b] with their (positive, negative) ids and every rank
-    scatter-adds all of them -- the same dense result on every rank for world * B * (d + 4) * 4 gathered bytes instead
-    of the ring all-reduce's 2 nI d 4; the caller guarantees EQUAL batch sizes on all ranks (no check, no host sync).
-    "auto" agrees on the batch sizes first (one tiny all-reduce and a host sync per call) and takes the sparse route
-    when they are equal and the gathered rows are at most half the all-reduce volume.
-    Returns (loss_global, auc_global, gU_local_rows_dense, gV_global)."""
-    K = _kernels(kernels)
+    route:
+      "local"   one GPU: dense gU / gV, no exchange;
+      "owner"   (default for world > 1) the item gradient is SHARDED BY OWNER: rank r owns items [r S, (r+1) S),
+                S = ceil(nI / world), in a peer-mapped buffer (PeerBuffer, CUDA IPC); divrec_bpr_step_owner scatters every
+                item-row update straight to its owner over NVLink inside the step kernel.  After the step's one collective
+                (the loss / AUC all-reduce, which is also the barrier behind the remote reductions) `gV_slice` holds the
+                globally summed gradient of the rank's own items -- reduce-scatter semantics, 1/world of the table per rank;
+      "dense"   the [nI, d] item gradient is all-reduced (BASELINE.json config 3 as literally stated);
+      "sparse"  the per-triple rows g_b U[u_b] and their ids are all-gathered and every rank scatter-adds all of them
+                (same dense result on every rank; needs equal batch sizes on all ranks).
+    Gradient buffers accumulate across steps (zero_grad belongs to the optimiser)."""
+
+    def __init__(self, U: torch.Tensor, V: torch.Tensor, world: int, rank: int, batch: int, route: str = "owner", group=None):
+        K = _kernels()
+        if world == 1:
+            route = "local"
+        if route not in ("local", "owner", "dense", "sparse"):
+            raise ValueError(f"unknown route {route!r}")
+        self.U, self.V, self.world, self.rank, self.batch, self.route, self.group = U, V, world, rank, batch, route, group
+        dev, (nI, d) = U.device, V.shape
+        self.gU = torch.zeros_like(U)
+        self.loss_sum = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.auc_sum = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.stat = torch.zeros(2, dtype=torch.float64, device=dev)
+        self.gV = self.peer = self.gV_slice = None
+        self.slice_rows = -(-nI // world)
+        if route == "owner":
+            self.peer = K.PeerBuffer(self.slice_rows, d, dev, group=group)
+            self.gV_slice = self.peer.local
+            self.gV_slice.zero_()
+            torch.cuda.synchronize(dev)
+            dist.barrier(group=group)  # every slice is zeroed before any rank's kernel adds into it
+        else:
+            self.gV = torch.zeros_like(V)
+        if route == "sparse":
+            self.rows = torch.empty((batch, d), dtype=torch.float32, device=dev)
+            self.all_rows = torch.empty((world * batch, d), dtype=torch.float32, device=dev)
+            self.ids = torch.empty((2, batch), dtype=torch.int64, device=dev)
+            self.all_ids = torch.empty((world * 2, batch), dtype=torch.int64, device=dev)
+
+    def describe(self) -> str:
+        return {"local": "single GPU (dense gradient tables)",
+                "owner": "sharded by owner: row updates scattered to the owning rank's peer-mapped slice inside the step kernel "
+                         "(red.global.add.v4.f32 over NVLink), one all-reduce of the loss / AUC scalars",
+                "dense": "dense all-reduce of the [nI, d] item gradient",
+                "sparse": "all-gather of per-triple rows + ids, every rank scatter-adds all of them"}[self.route]
+
+    def owned_range(self) -> Tuple[int, int]:
+        a = self.rank * self.slice_rows
+        return a, min(self.V.shape[0], a + self.slice_rows)
+
+    def close(self):
+        if self.peer is not None:
+            dist.barrier(group=self.group)  # no rank may still be adding into a slice that is about to be unmapped
+            self.gV_slice = None
+            self.peer.close()
+            self.peer = None
+
+
+def bpr_step_sharded(state: BprShardedState, u: torch.Tensor, p: torch.Tensor, n: torch.Tensor, grad_scale: float) -> torch.Tensor:
+    """One BPR forward/backward on this rank's triples (its users only), gradients accumulated into the state's buffers.
+    grad_scale = 1 / global_batch for the GLOBAL mean loss.  Returns a device tensor [2] float64: (loss sum, AUC hit count)
+    over ALL ranks' triples of this step (divide by the global batch for the means); no host synchronisation."""
+    K = _kernels()
+    st = state
+    st.loss_sum.zero_()
+    st.auc_sum.zero_()
+    if st.route == "owner":
+        K.bpr_step_owner(st.U, st.V, u, p, n, grad_scale, st.gU, st.peer.ptrs, st.slice_rows, loss_sum=st.loss_sum, auc_sum=st.auc_sum)
+    elif st.route == "sparse":
+        K.bpr_step(st.U, st.V, u, p, n, grad_scale, st.gU, None, want_scores=False, loss_sum=st.loss_sum, auc_sum=st.auc_sum, item_rows=st.rows)
+        st.ids[0].copy_(p); st.ids[1].copy_(n)
+        dist.all_gather_into_tensor(st.all_rows, st.rows, group=st.group)
+        dist.all_gather_into_tensor(st.all_ids, st.ids, group=st.group)
+        g3 = st.all_ids.view(st.world, 2, st.batch)
+        K.bpr_apply_rows(st.all_rows, g3[:, 0].reshape(-1), g3[:, 1].reshape(-1), st.gV)
+    else:
+        K.bpr_step(st.U, st.V, u, p, n, grad_scale, st.gU, st.gV, want_scores=False, loss_sum=st.loss_sum, auc_sum=st.auc_sum)
+        if st.route == "dense":
+            dist.all_reduce(st.gV, group=st.group)
+    st.stat[0] = st.loss_sum[0]
+    st.stat[1] = st.auc_sum[0]
+    if st.world > 1:
+        # also the barrier of the owner route: when it completes, every rank's step kernel -- and with it every remote
+        # reduction into this rank's slice -- has finished
+        dist.all_reduce(st.stat, group=st.group)
+    return st.stat
+
+
+def bpr_step_once(U: torch.Tensor, V: torch.Tensor, u: torch.Tensor, p: torch.Tensor, n: torch.Tensor,
+                  global_batch: int, group=None, item_grad: str = "dense"):
+    """One step on fresh buffers (tests, one-off calls): returns (loss_global, auc_global, gU_local_rows_dense, gV) where gV
+    is the dense global item gradient, or -- item_grad="owner" -- this rank's slice of it.
+    item_grad="auto": the ranks agree on their batch sizes first (one tiny all-reduce and a host sync) and take the sparse
+    route when they are equal and the gathered rows are at most half the all-reduce volume, else the dense one."""
     rank, world = _world(group)
     B, d = u.numel(), U.shape[1]
-    sparse = False
-    if world > 1 and item_grad != "dense" and hasattr(K, "bpr_apply_rows"):
-        if item_grad == "sparse":
-            sparse = True
-        else:
-            mm = torch.tensor([B, -B], dtype=torch.int64, device=U.device)
-            dist.all_reduce(mm, op=dist.ReduceOp.MAX, group=group)
-            bmax, bmin = int(mm[0]), -int(mm[1])
-            sparse = bmax == bmin and world * B * (d + 4) * 4 <= V.shape[0] * d * 4
-    gU, gV = torch.zeros_like(U), torch.zeros_like(V)
-    if sparse:
-        rows = torch.empty((B, d), dtype=torch.float32, device=U.device)
-        _pos, _neg, loss_sum, auc_sum = K.bpr_step(U, V, u, p, n, 1.0 / global_batch, gU, None, want_scores=False, item_rows=rows)
-        ids = torch.stack([p.to(torch.int64), n.to(torch.int64)])                       # [2, B]
-        all_rows = torch.empty((world * B, d), dtype=torch.float32, device=U.device)
-        all_ids = torch.empty((world * 2, B), dtype=torch.int64, device=U.device)
-        dist.all_gather_into_tensor(all_rows, rows, group=group)
-        dist.all_gather_into_tensor(all_ids, ids.contiguous(), group=group)
-        all_ids = all_ids.view(world, 2, B)
-        K.bpr_apply_rows(all_rows, all_ids[:, 0].reshape(-1), all_ids[:, 1].reshape(-1), gV)
-    elif hasattr(K, "bpr_step"):  # forward + backward in one pass over the rows
-        _pos, _neg, loss_sum, auc_sum = K.bpr_step(U, V, u, p, n, 1.0 / global_batch, gU, gV, want_scores=False)
-    else:
-        pos, neg, loss_sum, auc_sum = K.bpr_fwd(U, V, u, p, n)
-        K.bpr_bwd(U, V, u, p, n, pos, neg, 1.0 / global_batch, gU, gV)
-    stat = torch.stack([loss_sum.reshape(()).to(torch.float64), auc_sum.reshape(()).to(torch.float64)])
-    if world > 1:
-        if not sparse:
-            dist.all_reduce(gV, group=group)
-        dist.all_reduce(stat, group=group)
-    return (stat[0] / global_batch).to(torch.float32), (stat[1] / global_batch).to(torch.float32), gU, gV
+    route = item_grad
+    if world == 1:
+        route = "local"
+    elif item_grad == "auto":
+        mm = torch.tensor([B, -B], dtype=torch.int64, device=U.device)
+        dist.all_reduce(mm, op=dist.ReduceOp.MAX, group=group)
+        bmax, bmin = int(mm[0]), -int(mm[1])
+        route = "sparse" if (bmax == bmin and world * B * (d + 4) * 4 <= V.shape[0] * d * 4) else "dense"
+    state = BprShardedState(U, V, world, rank, B, route=route, group=group)
+    stat = bpr_step_sharded(state, u, p, n, 1.0 / global_batch)
+    loss, auc = (stat[0] / global_batch).to(torch.float32), (stat[1] / global_batch).to(torch.float32)
+    gV = state.gV_slice.clone() if route == "owner" else state.gV
+    gU = state.gU
+    state.close()
+    return loss, auc, gU, gV

@@ -227,6 +227,8 @@ def pair_wise_train_loop(dataset: PairWiseDataset, model: RankingModel, loss: Pa
         optimizer.zero_grad()
         n += 1
         loss_total += value.item()
+        if dev.type == "cuda":  # the loop's synchronisation point: ids outside the tables raise here (nn.Embedding's IndexError)
+            _native.raise_on_bad_indices(dev)
         for i, score in enumerate(scores):
             if fused and type(score) is AUCScore and score.reduction == "mean":
                 score_totals[i] += auc_sum.item() / positives.numel()  # free epilogue of the fused forward

@@ -68,7 +68,7 @@ int64_t divrec_launch_count(void);
  * 1 score+filter kernel, 2 select kernel, 3 ILD, 4 coverage histogram, 5 rescue kernel.  Host-only calls. */
 void divrec_set_profiling(int on);
 /* Measurement aid: 0 = normal; 1 = score+filter kernel runs its TMA/MMA pipeline but skips the filter;
- * 2 = filter arithmetic without the candidate stores.  Results are meaningless unless mode == 0. */
+ * 3 = as 1 with half of the tensor-memory read traffic.  Results are meaningless unless mode == 0. */
 void divrec_debug_filter_mode(int mode);
 /* Measurement aid: device buffer int64 [148][8] (caller-zeroed) receiving, per CTA of the score+filter kernel, the
  * MMA-issuing thread's cycles: [0] total, [1] blocked on the A operand, [2] on a free accumulator stage, [3] on B operand
@@ -88,7 +88,7 @@ int divrec_profile_read(float* ms_out /*host*/, int n);
  *   reported (global) item ids and subtracted from seen_items (item-sharded catalogue).
  *   Output row u = the k best unmasked items by (score desc, item id asc); rows with fewer
  *   than k unmasked items are padded with score -inf / item -1.
- *   Limits of this version: k <= 128; d <= 512 in DIVREC_MODE_TENSOR; nI < 2^31; tables 16-byte aligned;
+ *   Limits of this version: k <= 512; d <= 512 in DIVREC_MODE_TENSOR; nI < 2^31; tables 16-byte aligned;
  *   finite inputs.  Users are processed in internal passes of <= 151 552 rows, which bounds the workspace.
  *   divrec_score_topk_rescued: (host call, synchronises `stream`) host_out[0] = how many rows of the last call on
  *   this workspace were re-done by the exact SIMT kernel; host_out[1..4] = why (candidate-list overflow or forced,
@@ -175,28 +175,60 @@ int divrec_entropy_from_counts(const int32_t* counts, int64_t nI, float* out2, v
  *   bwd: with g_b = dL/dx_b supplied per triple (x = pos-neg):
  *        gU[u] += g (V[p]-V[n]);  gV[p] += g U[u];  gV[n] -= g U[u]   (duplicates accumulate)
  *        If g == NULL it is recomputed as -sigmoid(-(pos-neg)) * grad_scale.
- *   d must be a multiple of 4 and <= 1024; fp32 tables.
+ *   fp32 tables; any d <= 1024 (rows move as 128-bit vectors when d % 4 == 0 and the tables are 16-byte aligned,
+ *   one float at a time otherwise -- nn.Embedding takes any embedding_dim).
+ *   nU / nI are the table heights: a triple with an id outside [0, nU) x [0, nI)^2 is SKIPPED (no out-of-range
+ *   access; its pos / neg read 0) and counted -- the reference's nn.Embedding raises IndexError there, and the
+ *   shim turns a non-zero divrec_bad_index_count into that IndexError at its next synchronisation point.
  * ------------------------------------------------------------------------------------- */
-int divrec_bpr_fwd(const float* U, const float* V, const int64_t* u, const int64_t* p,
+int divrec_bpr_fwd(const float* U, const float* V, int64_t nU, int64_t nI, const int64_t* u, const int64_t* p,
                    const int64_t* n, int64_t B, int d, float* pos /*[B]*/, float* neg /*[B]*/,
                    float* loss_sum, int32_t* auc_sum, void* stream);
 
-int divrec_bpr_bwd(const float* U, const float* V, const int64_t* u, const int64_t* p,
+int divrec_bpr_bwd(const float* U, const float* V, int64_t nU, int64_t nI, const int64_t* u, const int64_t* p,
                    const int64_t* n, const float* pos, const float* neg, const float* g,
                    float grad_scale, int64_t B, int d, float* gU, float* gV, void* stream);
 
 /* Forward and backward of one batch in ONE pass (the loop's `loss_value.backward()` at
  *   divrec/train/utils.py:149 has upstream gradient 1, so g_b = -sigmoid(-(pos_b-neg_b)) * grad_scale
  *   is known as soon as the scores are; grad_scale = 1/B for the mean loss): rows are read once, DRAM
- *   traffic = 3 row reads + 3 row read-modify-writes per triple.  pos / neg may be NULL; loss_sum and
- *   auc_sum as in divrec_bpr_fwd; gU / gV accumulate (dense tables, caller-owned, either may be NULL).
+ *   traffic = 3 row reads + 3 row read-modify-writes per triple.  pos / neg may be NULL (required when d % 4 != 0:
+ *   that shape runs forward then backward); loss_sum and auc_sum as in divrec_bpr_fwd; gU / gV accumulate (dense
+ *   tables, caller-owned, either may be NULL).
  *   item_rows (nullable, [B,d]): the SPARSE form of the item gradient -- row b = g_b U[u_b], to be added to
  *   gV[p_b] and subtracted from gV[n_b].  Multi-GPU steps whose batch touches few rows all-gather these rows (+ ids)
  *   instead of all-reducing the dense [nI,d] table and apply them with divrec_bpr_apply_rows. */
-int divrec_bpr_step(const float* U, const float* V, const int64_t* u, const int64_t* p,
+int divrec_bpr_step(const float* U, const float* V, int64_t nU, int64_t nI, const int64_t* u, const int64_t* p,
                     const int64_t* n, int64_t B, int d, float grad_scale, float* pos, float* neg,
                     float* loss_sum, int32_t* auc_sum, float* gU, float* gV, float* item_rows,
                     void* stream);
+
+/* The same one-pass step with the item gradient SHARDED BY OWNER across the GPUs of a node (BASELINE.json config 3's
+ *   gradient exchange fused into the kernel): gV_slices [n_slices] (device array of device pointers) holds, for every
+ *   rank r, the address of the [slice_rows, d] gradient slice of items [r slice_rows, (r + 1) slice_rows) -- this rank's
+ *   own slice and the peer-mapped slices of the others (divrec_peer_alloc / divrec_peer_open).  Every item-row update
+ *   is scattered straight to its owner with red.global.add.v4.f32 over NVLink, overlapped with the gathers of the
+ *   following triples: no packing, no all-to-all, no second apply pass; after the ranks' kernels and ONE barrier
+ *   every rank holds the globally summed gradient of the items it owns (reduce-scatter semantics; the dense
+ *   replicated table of autograd is the concatenation of the slices).  d % 4 == 0, 16-byte aligned tables. */
+int divrec_bpr_step_owner(const float* U, const float* V, int64_t nU, int64_t nI, const int64_t* u, const int64_t* p,
+                          const int64_t* n, int64_t B, int d, float grad_scale, float* pos, float* neg,
+                          float* loss_sum, int32_t* auc_sum, float* gU, float* const* gV_slices, int n_slices,
+                          int64_t slice_rows, void* stream);
+
+/* (host call, synchronises `stream`) triples / pairs skipped since the last reset because an id was out of range */
+int divrec_bad_index_count(int64_t* host_out /*host*/, int reset, void* stream);
+
+/* Peer buffers: device memory that the other processes of the node can map (CUDA IPC, NVLink / NVSwitch peer access).
+ *   divrec_peer_alloc: cudaMalloc + export; handle_out is DIVREC_PEER_HANDLE_BYTES opaque bytes to hand to the peers
+ *   (e.g. one all_gather); divrec_peer_open maps a peer's buffer into this process; close / free undo them.
+ *   These four are the library's only allocating entry points. */
+#define DIVREC_PEER_HANDLE_BYTES 64
+int divrec_peer_alloc(size_t bytes, void** ptr_out, unsigned char* handle_out /*host [64]*/);
+int divrec_peer_open(const unsigned char* handle /*host [64]*/, void** ptr_out);
+int divrec_peer_close(void* ptr);
+int divrec_peer_free(void* ptr);
+
 /* BPR triple sampler on the device
  *   replaces: PairWiseDataset.__iter__, divrec/datasets/base_datasets.py:70-107 -- per user max_sampled positives drawn
  *             with replacement from the user's items, max_sampled negatives with replacement from
@@ -210,18 +242,18 @@ int divrec_bpr_sample_triples(const int64_t* pos_rowptr, const int32_t* pos_item
                               int64_t* out_u, int64_t* out_p, int64_t* out_n, void* stream);
 
 /* gV[p_j] += rows_j;  gV[n_j] -= rows_j   for j < N (duplicates accumulate) */
-int divrec_bpr_apply_rows(const float* rows, const int64_t* p, const int64_t* n, int64_t N, int d,
+int divrec_bpr_apply_rows(const float* rows, const int64_t* p, const int64_t* n, int64_t N, int64_t nI, int d,
                           float* gV, void* stream);
 
 /* paired scoring  out[l] = <U[user_id[l]], V[item_id[l]]>
  *   replaces: divrec/models/matrix_factorization.py:19-28 (MatrixFactorization.forward) */
-int divrec_pair_scores(const float* U, const float* V, const int64_t* user_id,
+int divrec_pair_scores(const float* U, const float* V, int64_t nU, int64_t nI, const int64_t* user_id,
                        const int64_t* item_id, int64_t L, int d, float* out, void* stream);
 
 /* backward of divrec_pair_scores: gU[user_id[l]] += g[l] V[item_id[l]]; gV[item_id[l]] += g[l] U[user_id[l]]
  *   replaces: autograd's embedding_dense_backward behind loss_value.backward() at
  *             divrec/train/utils.py:149 for a single model(...) call; gU / gV may be NULL. */
-int divrec_pair_scores_bwd(const float* U, const float* V, const int64_t* user_id,
+int divrec_pair_scores_bwd(const float* U, const float* V, int64_t nU, int64_t nI, const int64_t* user_id,
                            const int64_t* item_id, const float* g, int64_t L, int d, float* gU,
                            float* gV, void* stream);
 

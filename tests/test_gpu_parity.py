@@ -741,3 +741,259 @@ def test_cfg2_full_size_properties(native, dev):
     torch.testing.assert_close(a[:4096], b, rtol=REL, atol=1e-7)
     assert bool((a > 0).all()) and bool((a < 1).all())
     torch.testing.assert_close(a[sample.to(dev)].cpu(), O.ild_cosine(i[sample.to(dev)].cpu(), V), rtol=REL, atol=1e-7)
+
+
+# ------------------------------------------------------------------------------------------------
+# list metrics against goldens produced by the real reference (tests/golden/make_golden_metrics.py)
+# ------------------------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("name", ["metrics_small", "metrics_k50"])
+def test_relevance_pri_unfairness_vs_reference_golden(native, dev, name):
+    from divrec.datasets import UserItemInteractionsDataset
+    from divrec.datasets.storages import Features
+    from divrec.losses.intra_list_diversity_score import IntraListBinaryUnfairnessScore
+    from divrec.metrics import (PRI, MeanAveragePrecisionAtKScore, NDCGScore, PrecisionAtKScore, RecallAtKScore,
+                                average_precision_at_k, avg_rank, normalized_discounted_cumulative_gain, precision_at_k, recall_at_k)
+    g = load_golden(name)
+    inter, recs, nI = g["interactions"], g["recs"].to(dev), int(g["nI"])
+    for fn, key in ((precision_at_k, "precision"), (recall_at_k, "recall"), (average_precision_at_k, "ap"),
+                    (normalized_discounted_cumulative_gain, "ndcg")):
+        torch.testing.assert_close(fn(inter, recs).cpu(), g[key], rtol=1e-5, atol=1e-7)
+    for cls, key in ((PrecisionAtKScore, "precision_mean"), (RecallAtKScore, "recall_mean"), (MeanAveragePrecisionAtKScore, "map_mean"),
+                     (NDCGScore, "ndcg_mean")):
+        assert cls().name  # snake-cased class name, as in the reference
+        torch.testing.assert_close(cls()(inter, recs).cpu(), g[key], rtol=1e-5, atol=1e-7)
+    # avg_rank / coverage_hist_ranks: items bit-exact, mean positions within 1e-6
+    items, ranks = avg_rank(recs, nI)
+    assert torch.equal(items.cpu(), g["avg_rank_items"])
+    torch.testing.assert_close(ranks.cpu(), g["avg_rank_values"], rtol=1e-6, atol=1e-6)
+    counts, sums = native.coverage_hist_ranks(recs, nI)
+    assert torch.equal(counts.cpu().long(), torch.bincount(g["recs"].flatten(), minlength=nI))
+    pos = torch.arange(recs.shape[1]).expand_as(g["recs"]).flatten()
+    assert torch.equal(sums.cpu(), torch.zeros(nI, dtype=torch.int64).index_add_(0, g["recs"].flatten(), pos))
+    # PRI and the binary-unfairness class through the shim's own classes
+    feats = Features(feature_names=["partition"], features=g["labels"].reshape(-1, 1))
+    data = UserItemInteractionsDataset(interactions=inter, item_features=feats, number_of_users=recs.shape[0], number_of_items=nI)
+    pri = PRI(dataset=data)
+    assert pri.name == "pri"
+    torch.testing.assert_close(pri(inter, recs).cpu(), g["pri"], rtol=1e-4, atol=1e-6)
+    unfair = IntraListBinaryUnfairnessScore(dataset=data, reduction="none")
+    assert unfair.name == "intra_list_binary_unfairness_score"
+    torch.testing.assert_close(unfair(inter, recs).cpu(), g["unfairness"], rtol=1e-6, atol=1e-7)
+    assert torch.equal(unfair.get_distance_matrix(), (g["labels"][None] == g["labels"][:, None]).int())
+
+
+# ------------------------------------------------------------------------------------------------
+# row-gather kernels: any embedding_dim, ids out of range
+# ------------------------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("d", [10, 30, 50])
+def test_bpr_and_pair_scores_with_odd_embedding_dims(native, dev, d):
+    """nn.Embedding takes any embedding_dim (the reference's configs use 10 / 30 / 50): rows that cannot move as 128-bit
+    vectors take the scalar form of the same kernels."""
+    gen = torch.Generator().manual_seed(d)
+    nU, nI, B = 120, 150, 700
+    U, V = O.make_embeddings(nU, d, "gauss", gen), O.make_embeddings(nI, d, "gauss", gen)
+    u, p, n = (torch.randint(0, m, (B,), generator=gen) for m in (nU, nI, nI))
+    Ud, Vd, ud, pd, nd = U.to(dev), V.to(dev), u.to(dev), p.to(dev), n.to(dev)
+    o_pos, o_neg, o_loss, o_auc = O.bpr_forward(U, V, u, p, n)
+    o_gU, o_gV = O.bpr_backward(U, V, u, p, n)
+    tol = 1e-5 * float(U.norm(dim=1).max() * V.norm(dim=1).max())
+    s = native.pair_scores(Ud, Vd, ud, pd).cpu()
+    assert (s - o_pos).abs().max().item() <= tol
+    gU, gV = torch.zeros_like(Ud), torch.zeros_like(Vd)
+    pos, neg, loss_sum, auc_sum = native.bpr_step(Ud, Vd, ud, pd, nd, 1.0 / B, gU, gV)
+    assert (pos.cpu() - o_pos).abs().max().item() <= tol and (neg.cpu() - o_neg).abs().max().item() <= tol
+    assert abs(float(loss_sum) / B - float(o_loss)) <= 1e-5 * abs(float(o_loss))
+    assert (gU.cpu() - o_gU).abs().max().item() <= 1e-5 * float(o_gU.abs().max())
+    assert (gV.cpu() - o_gV).abs().max().item() <= 1e-5 * float(o_gV.abs().max())
+    # the model shim end to end (forward + autograd backward)
+    from divrec.models import MatrixFactorization
+    m = MatrixFactorization(nU, nI, d).to(dev)
+    with torch.no_grad():
+        m.user_embeddings.weight.copy_(Ud); m.item_embeddings.weight.copy_(Vd)
+    out = m(ud, pd)
+    out.sum().backward()
+    ref_gU = torch.zeros(nU, d).index_add_(0, u, V[p])
+    torch.testing.assert_close(m.user_embeddings.weight.grad.cpu(), ref_gU, rtol=1e-5, atol=1e-5)
+
+
+def test_out_of_range_ids_are_skipped_and_reported(native, dev):
+    """The reference's nn.Embedding raises IndexError for an id outside the table; here the triple is skipped (no
+    out-of-range access) and the shim raises IndexError at its next synchronisation point."""
+    gen = torch.Generator().manual_seed(3)
+    nU, nI, d, B = 50, 60, 32, 64
+    U, V = O.make_embeddings(nU, d, "gauss", gen).to(dev), O.make_embeddings(nI, d, "gauss", gen).to(dev)
+    u, p, n = (torch.randint(0, m, (B,), generator=gen).to(dev) for m in (nU, nI, nI))
+    native.bad_index_count(dev)  # reset
+    u_bad, p_bad = u.clone(), p.clone()
+    u_bad[5] = nU + 7
+    p_bad[9] = -1
+    gU, gV = torch.zeros_like(U), torch.zeros_like(V)
+    pos, neg, _, _ = native.bpr_step(U, V, u_bad, p_bad, n, 1.0 / B, gU, gV)
+    good = torch.ones(B, dtype=torch.bool); good[5] = False; good[9] = False
+    o_gU, o_gV = O.bpr_backward(U.cpu(), V.cpu(), u.cpu()[good], p.cpu()[good], n.cpu()[good], upstream=(B - 2) / B)
+    assert (gU.cpu() - o_gU).abs().max().item() <= 1e-5 * float(o_gU.abs().max())
+    assert (gV.cpu() - o_gV).abs().max().item() <= 1e-5 * float(o_gV.abs().max())
+    assert float(pos[5]) == 0.0 and float(pos[9]) == 0.0
+    assert native.bad_index_count(dev, reset=False) == 2
+    with pytest.raises(IndexError):
+        native.raise_on_bad_indices(dev)
+    assert native.bad_index_count(dev) == 0
+    native.pair_scores(U, V, u_bad, p)
+    with pytest.raises(IndexError):
+        native.raise_on_bad_indices(dev)
+
+
+# ------------------------------------------------------------------------------------------------
+# owner-sharded BPR step over peer memory (2 GPUs of one node; skipped on a 1-GPU box)
+# ------------------------------------------------------------------------------------------------
+
+
+def _owner_worker(rank, world, port, out):
+    import os
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from divrec import parallel
+    gen = torch.Generator().manual_seed(0)
+    nU, nI, d, B = 4000, 5003, 128, 6000
+    U, V = O.make_embeddings(nU, d, "gauss", gen), O.make_embeddings(nI, d, "gauss", gen)
+    a, b = parallel.shard_range(nU, rank, world)
+    us, ps, ns = [], [], []
+    for r in range(world):  # every rank's triples, generated identically everywhere
+        ra, rb = parallel.shard_range(nU, r, world)
+        us.append(torch.randint(ra, rb, (B,), generator=gen)); ps.append(torch.randint(0, nI, (B,), generator=gen)); ns.append(torch.randint(0, nI, (B,), generator=gen))
+    Ud, Vd = U.to(dev), V.to(dev)
+    state = parallel.BprShardedState(Ud, Vd, world, rank, B, route="owner")
+    for _ in range(2):  # gradients accumulate across steps
+        stat = parallel.bpr_step_sharded(state, us[rank].to(dev), ps[rank].to(dev), ns[rank].to(dev), 1.0 / (world * B))
+    torch.cuda.synchronize()
+    ua, pa, na = torch.cat(us), torch.cat(ps), torch.cat(ns)
+    _, _, o_loss, o_auc = O.bpr_forward(U, V, ua, pa, na)
+    o_gU, o_gV = O.bpr_backward(U, V, ua, pa, na)
+    lo, hi = state.owned_range()
+    ok = abs(float(stat[0]) / (world * B) - float(o_loss)) <= 1e-5 * abs(float(o_loss))
+    ok = ok and (state.gV_slice[:hi - lo].cpu() - 2 * o_gV[lo:hi]).abs().max().item() <= 1e-5 * 2 * float(o_gV.abs().max())
+    ok = ok and (state.gU[a:b].cpu() - 2 * o_gU[a:b]).abs().max().item() <= 1e-5 * 2 * float(o_gU.abs().max())
+    # and the dense all-reduce route gives the same item gradient
+    l2, a2, gU2, gV2 = parallel.bpr_step_once(Ud, Vd, us[rank].to(dev), ps[rank].to(dev), ns[rank].to(dev), world * B, item_grad="dense")
+    ok = ok and (gV2.cpu() - o_gV).abs().max().item() <= 1e-5 * float(o_gV.abs().max())
+    state.close()
+    dist.barrier()
+    dist.destroy_process_group()
+    out.put((rank, bool(ok)))
+
+
+def test_bpr_owner_sharded_step_over_peer_memory():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs of one node (gpurun --gpus 2)")
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    procs = [ctx.Process(target=_owner_worker, args=(r, 2, port, out)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    for pr in procs:
+        pr.join(300)
+    assert all(pr.exitcode == 0 for pr in procs), [pr.exitcode for pr in procs]
+    res = sorted(out.get(timeout=5) for _ in range(2))
+    assert res == [(0, True), (1, True)], res
+
+
+# ------------------------------------------------------------------------------------------------
+# parity at the BENCHED shapes (BASELINE.json configs[1], [2], [3]): sampled oracle rows + size-independent properties
+# ------------------------------------------------------------------------------------------------
+
+
+def _oracle_rows(U, V, rowptr, items, sample, k):
+    sub_rowptr = torch.zeros(sample.numel() + 1, dtype=torch.int64)
+    segs = []
+    for j, u in enumerate(sample.tolist()):
+        seg = items[rowptr[u]:rowptr[u + 1]]
+        segs.append(seg)
+        sub_rowptr[j + 1] = sub_rowptr[j] + seg.numel()
+    return O.recommendations_dense(U[sample], V, sub_rowptr, torch.cat(segs) if segs else torch.zeros(0, dtype=torch.int32), k)
+
+
+def test_cfg2_bench_inputs_2000_oracle_rows(native, dev):
+    """The bench's own cfg2 inputs (138 493 x 26 744, d = 128, k = 100, ~20M seen pairs): 2 000+ sampled rows against the
+    oracle, the fused metrics against the separate kernels, no masked item in any list."""
+    nU, nI, d, k, nnz = 138493, 26744, 128, 100, 20000263
+    gen = torch.Generator().manual_seed(0)
+    U, V = O.make_embeddings(nU, d, "gauss", gen), O.make_embeddings(nI, d, "gauss", gen)
+    seen = O.make_seen(nU, nI, nnz, gen)
+    rowptr, items = O.seen_csr(seen, nU)
+    Ud, Vd, rp, it = U.to(dev), V.to(dev), rowptr.to(dev), items.to(dev)
+    s, i, ild, counts = native.score_topk_metrics(Ud, Vd, k, rp, it)
+    _s, _i, stats = native.score_topk(Ud, Vd, k, rp, it, return_stats=True)
+    assert torch.equal(_i, i) and torch.equal(_s, s)
+    assert stats["rescued_rows"] < 64, stats   # the whole-chip rescue path covers the usual handful
+    sample = torch.arange(0, nU, 67)   # 2 068 rows
+    o_i, o_s = _oracle_rows(U, V, rowptr, items, sample, k)
+    n_diff = check_topk_against_oracle(i[sample.to(dev)], s[sample.to(dev)], o_i, o_s, U, V, False)
+    assert n_diff <= sample.numel() // 100
+    keys = (torch.arange(nU, device=dev)[:, None] * nI + i).flatten()
+    seen_keys = (seen[:, 0] * nI + seen[:, 1]).to(dev)
+    assert not bool(torch.isin(keys, seen_keys).any())
+    assert torch.equal(counts.long(), torch.bincount(i.flatten(), minlength=nI))
+    torch.testing.assert_close(ild, native.ild_cosine(Vd, i), rtol=REL, atol=1e-7)
+    torch.testing.assert_close(ild[sample.to(dev)].cpu(), O.ild_cosine(i[sample.to(dev)].cpu(), V), rtol=REL, atol=1e-7)
+
+
+def test_cfg4_shard_shape_bf16(native, dev):
+    """One shard of BASELINE.json configs[3]: 1.25M items x d = 256 bf16, 65 536 queries, k = 100 -- the benched shape.
+    512+ sampled rows against the oracle (exact fp32 dot products of the bf16 tables) and two-way shard merge == unsharded."""
+    nI, d, k, nQ = 1_250_000, 256, 100, 65536
+    gen = torch.Generator().manual_seed(4)
+    V = torch.randn((nI, d), generator=gen).to(torch.bfloat16)
+    U = torch.randn((nQ, d), generator=gen).to(torch.bfloat16)
+    Ud, Vd = U.to(dev), V.to(dev)
+    s, i, stats = native.score_topk(Ud, Vd, k, return_stats=True)
+    assert stats["rescued_rows"] <= 8, stats
+    ok = (s[:, :-1] > s[:, 1:]) | ((s[:, :-1] == s[:, 1:]) & (i[:, :-1] < i[:, 1:]))
+    assert bool(ok.all()) and bool((i >= 0).all()) and bool((i < nI).all())
+    sample = torch.arange(0, nQ, 127)   # 517 rows
+    o_i, o_s = O.recommendations_dense(U[sample].float(), V.float(), None, None, k)
+    check_topk_against_oracle(i[sample.to(dev)], s[sample.to(dev)], o_i, o_s, U.float(), V.float(), False)
+    # item-sharded in two halves + packed merge == unsharded, bit for bit
+    h = nI // 2
+    parts = [native.score_topk(Ud, Vd[a:b], k, item_id_offset=a) for a, b in ((0, h), (h, nI))]
+    ms, mi = native.topk_merge_packed(torch.stack([native.topk_pack(ps, pi) for ps, pi in parts]))
+    assert torch.equal(mi, i) and torch.equal(ms, s)
+
+
+def test_cfg3_shape_sampled_gradient_rows(native, dev):
+    """BASELINE.json configs[2] at its shape: 1M users x 1M items, d = 128, 65 536 triples: the dense gradients of the
+    one-kernel step on every touched row against the oracle's formula (fp64), untouched rows exactly zero."""
+    nU = nI = 1_000_000
+    d, B = 128, 65536
+    g = torch.Generator(device=dev).manual_seed(5)
+    U = torch.randn((nU, d), generator=g, device=dev)
+    V = torch.randn((nI, d), generator=g, device=dev)
+    gh = torch.Generator().manual_seed(100)
+    u, p, n = (torch.randint(0, m, (B,), generator=gh).to(dev) for m in (nU, nI, nI))
+    u[:64] = u[0]; p[:32] = p[0]      # duplicates accumulate
+    gU, gV = torch.zeros_like(U), torch.zeros_like(V)
+    pos, neg, loss_sum, auc_sum = native.bpr_step(U, V, u, p, n, 1.0 / B, gU, gV)
+    Uu, Vp, Vn = U[u].double(), V[p].double(), V[n].double()
+    x = ((Uu * Vp).sum(1) - (Uu * Vn).sum(1))
+    c = (-torch.sigmoid(-x) / B)[:, None]
+    ref_loss = torch.nn.functional.softplus(-x).mean()
+    assert abs(float(loss_sum) / B - float(ref_loss)) <= 1e-5 * float(ref_loss)
+    assert int(auc_sum) == int(((Uu * Vp).sum(1).float() >= (Uu * Vn).sum(1).float()).sum()) or abs(int(auc_sum) - int((x >= 0).sum())) <= 2
+    ref_gU = torch.zeros((nU, d), dtype=torch.float64, device=dev).index_add_(0, u, c * (Vp - Vn))
+    ref_gV = torch.zeros((nI, d), dtype=torch.float64, device=dev).index_add_(0, p, c * Uu).index_add_(0, n, -c * Uu)
+    assert (gU.double() - ref_gU).abs().max().item() <= 1e-5 * float(ref_gU.abs().max())
+    assert (gV.double() - ref_gV).abs().max().item() <= 1e-5 * float(ref_gV.abs().max())
+    touched = torch.zeros(nI, dtype=torch.bool, device=dev); touched[p] = True; touched[n] = True
+    assert float(gV[~touched].abs().sum()) == 0.0

@@ -1,6 +1,8 @@
-"""The N > 1 host logic (sharding, collectives, merge order) with 2 ranks over gloo on CPU.  The compute
-backend is substituted by the oracle HERE ONLY (tests may use the oracle); the collectives, shard ranges and
-result layout are the product code in divrec/parallel.py."""
+"""The N > 1 host logic (sharding, collectives, merge order) with 2 ranks over gloo on CPU.  The product has no
+backend parameter: the workers below REPLACE the module attribute divrec.parallel._native with an oracle-backed
+stand-in (tests may use the oracle); the collectives, shard ranges and result layout are the product code in
+divrec/parallel.py.  The owner-sharded BPR route lives in a CUDA kernel over peer memory and is covered by the
+2-GPU test in test_gpu_parity.py."""
 import os
 import socket
 
@@ -70,7 +72,12 @@ class OracleKernels:
             gV += b
         if item_rows is not None:   # row b = g_b U[u_b], g_b = -sigmoid(-(pos - neg)) * scale
             item_rows.copy_((-torch.sigmoid(-(pos - neg).double()) * scale)[:, None].float() * U[u])
-        return pos, neg, (loss * B).reshape(1), (auc * B).round().int().reshape(1)
+        ls, au = (loss * B).reshape(1), (auc * B).round().int().reshape(1)
+        if loss_sum is not None:    # caller-owned accumulators, as in the C ABI
+            loss_sum += ls; ls = loss_sum
+        if auc_sum is not None:
+            auc_sum += au; au = auc_sum
+        return pos, neg, ls, au
 
     @staticmethod
     def bpr_apply_rows(rows, p, n, gV):
@@ -101,28 +108,30 @@ def _worker(rank, world, port, out):
     seen = O.make_seen(nU, nI, 3000, gen)
     rowptr, items = O.seen_csr(seen, nU)
     full_i, full_s = O.recommendations_dense(U, V, rowptr, items, k)
-    K = OracleKernels()
+    parallel._native = OracleKernels   # test-only substitution of the compute backend (no CUDA here)
     # users sharded
-    it, sc, ild, ild_mean, counts, (a, b) = parallel.recommend_user_sharded(U, V, rowptr, items, k, kernels=K)
+    it, sc, ild, ild_mean, counts, (a, b) = parallel.recommend_user_sharded(U, V, rowptr, items, k)
     assert (a, b) == parallel.shard_range(nU, rank, world)
     assert torch.equal(it, full_i[a:b]) and torch.equal(sc, full_s[a:b])
     assert torch.equal(counts.long(), O.coverage_counts(full_i, nI))          # all-reduced histogram = global
     assert abs(float(ild_mean) - float(O.ild_cosine(full_i, V).double().mean())) < 1e-6
     # items sharded
     ia, ib = parallel.shard_range(nI, rank, world)
-    ms, mi = parallel.recommend_item_sharded(U, V[ia:ib].contiguous(), ia, k, rowptr, items, kernels=K)
+    ms, mi = parallel.recommend_item_sharded(U, V[ia:ib].contiguous(), ia, k, rowptr, items)
     assert torch.equal(mi, full_i) and torch.equal(ms, full_s)
 
     class TwoTensorKernels(OracleKernels):   # a backend without the packed exchange: two all-gathers + topk_merge
         MERGE_PACKED_MAX = 0
-    ms2, mi2 = parallel.recommend_item_sharded(U, V[ia:ib].contiguous(), ia, k, rowptr, items, kernels=TwoTensorKernels())
+    parallel._native = TwoTensorKernels
+    ms2, mi2 = parallel.recommend_item_sharded(U, V[ia:ib].contiguous(), ia, k, rowptr, items)
     assert torch.equal(mi2, full_i) and torch.equal(ms2, full_s)
+    parallel._native = OracleKernels
     # BPR: triples partitioned by user shard
     B = 400
     u = torch.randint(0, nU, (B,), generator=gen); p = torch.randint(0, nI, (B,), generator=gen); n = torch.randint(0, nI, (B,), generator=gen)
     mine = (u >= a) & (u < b)
     Ug = O.make_embeddings(nU, d, "gauss", gen); Vg = O.make_embeddings(nI, d, "gauss", gen)
-    loss, auc, gU, gV = parallel.bpr_step_sharded(Ug, Vg, u[mine], p[mine], n[mine], B, kernels=K)
+    loss, auc, gU, gV = parallel.bpr_step_once(Ug, Vg, u[mine], p[mine], n[mine], B)
     _, _, o_loss, o_auc = O.bpr_forward(Ug, Vg, u, p, n)
     o_gU, o_gV = O.bpr_backward(Ug, Vg, u, p, n)
     assert abs(float(loss) - float(o_loss)) < 1e-5 * abs(float(o_loss)) and abs(float(auc) - float(o_auc)) < 1e-6
@@ -137,18 +146,18 @@ def _worker(rank, world, port, out):
     m = min(t.numel() for t in per_rank)
     sel = torch.cat([t[:m] for t in per_rank])
     me = per_rank[rank][:m]
-    loss_s, auc_s, gU_s, gV_s = parallel.bpr_step_sharded(Ug, Vg, u[me], p[me], n[me], world * m, kernels=K, item_grad="sparse")
+    loss_s, auc_s, gU_s, gV_s = parallel.bpr_step_once(Ug, Vg, u[me], p[me], n[me], world * m, item_grad="sparse")
     _, _, o_loss, o_auc = O.bpr_forward(Ug, Vg, u[sel], p[sel], n[sel])
     o_gU, o_gV = O.bpr_backward(Ug, Vg, u[sel], p[sel], n[sel])
     assert abs(float(loss_s) - float(o_loss)) < 1e-5 * abs(float(o_loss)) and abs(float(auc_s) - float(o_auc)) < 1e-6
     torch.testing.assert_close(gV_s, o_gV, rtol=0, atol=1e-6 * float(o_gV.abs().max()))
     torch.testing.assert_close(gU_s[a:b], o_gU[a:b], rtol=0, atol=1e-6 * float(o_gU.abs().max()))
-    loss_d, _, _, gV_d = parallel.bpr_step_sharded(Ug, Vg, u[me], p[me], n[me], world * m, kernels=K, item_grad="dense")
+    loss_d, _, _, gV_d = parallel.bpr_step_once(Ug, Vg, u[me], p[me], n[me], world * m, item_grad="dense")
     torch.testing.assert_close(gV_d, gV_s, rtol=0, atol=1e-6 * float(o_gV.abs().max()))
     # "auto": equal batches and a small volume -> sparse; unequal batches (the first call's split) -> dense, no mismatch
-    _, _, _, gV_a = parallel.bpr_step_sharded(Ug, Vg, u[me], p[me], n[me], world * m, kernels=K, item_grad="auto")
+    _, _, _, gV_a = parallel.bpr_step_once(Ug, Vg, u[me], p[me], n[me], world * m, item_grad="auto")
     torch.testing.assert_close(gV_a, gV_s, rtol=0, atol=1e-6 * float(o_gV.abs().max()))
-    _, _, _, gV_u = parallel.bpr_step_sharded(Ug, Vg, u[mine], p[mine], n[mine], B, kernels=K, item_grad="auto")
+    _, _, _, gV_u = parallel.bpr_step_once(Ug, Vg, u[mine], p[mine], n[mine], B, item_grad="auto")
     torch.testing.assert_close(gV_u, gV, rtol=0, atol=1e-6 * float(gV.abs().max()))
     dist.barrier()
     dist.destroy_process_group()
