@@ -763,7 +763,7 @@ def test_relevance_pri_unfairness_vs_reference_golden(native, dev, name):
     for cls, key in ((PrecisionAtKScore, "precision_mean"), (RecallAtKScore, "recall_mean"), (MeanAveragePrecisionAtKScore, "map_mean"),
                      (NDCGScore, "ndcg_mean")):
         assert cls().name  # snake-cased class name, as in the reference
-        torch.testing.assert_close(cls()(inter, recs).cpu(), g[key], rtol=1e-5, atol=1e-7)
+        assert float(cls()(inter, recs)) == pytest.approx(float(g[key]), rel=1e-5, abs=1e-7)
     # avg_rank / coverage_hist_ranks: items bit-exact, mean positions within 1e-6
     items, ranks = avg_rank(recs, nI)
     assert torch.equal(items.cpu(), g["avg_rank_items"])
@@ -777,7 +777,7 @@ def test_relevance_pri_unfairness_vs_reference_golden(native, dev, name):
     data = UserItemInteractionsDataset(interactions=inter, item_features=feats, number_of_users=recs.shape[0], number_of_items=nI)
     pri = PRI(dataset=data)
     assert pri.name == "pri"
-    torch.testing.assert_close(pri(inter, recs).cpu(), g["pri"], rtol=1e-4, atol=1e-6)
+    assert float(pri(inter, recs)) == pytest.approx(float(g["pri"]), rel=1e-4, abs=1e-6)
     unfair = IntraListBinaryUnfairnessScore(dataset=data, reduction="none")
     assert unfair.name == "intra_list_binary_unfairness_score"
     torch.testing.assert_close(unfair(inter, recs).cpu(), g["unfairness"], rtol=1e-6, atol=1e-7)
