@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 _TAG = os.environ.get("DIVREC_BUILD_TAG", "")
 OUT = os.path.join(HERE, f"libdivrec_b200.{_TAG}.so" if _TAG else "libdivrec_b200.so")
 OBJ_DIR = os.path.join(HERE, f"build.{_TAG}" if _TAG else "build")
-SOURCES = ["api.cu", "score_filter.cu", "select_topk.cu", "rescue.cu", "prep.cu", "metrics.cu", "bpr.cu", "mmr.cu", "score_filter2.cu"]
+SOURCES = ["api.cu", "score_filter.cu", "select_topk.cu", "rescue.cu", "prep.cu", "metrics.cu", "bpr.cu", "mmr.cu", "score_filter2.cu", "csr.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -73,7 +73,7 @@ struct WsLayout {
   bool convA, convB;  // operands have to be rewritten into the workspace (fp32 -> fp16, or bf16 padding)
   int64_t chunk;
   int rescue_grid;
-  size_t offA, offB, offNormU, offInvV, offListS, offCounts, offThr, offFail, offScalars, offRescue, offHintMask, total;
+  size_t offA, offB, offNormU, offRowExp, offInvV, offListS, offCounts, offThr, offFail, offScalars, offRescue, offHintMask, total;
   bool two_blocks;
 };
 static WsLayout ws_layout(int64_t nU, int64_t nI, int d, int dtype, int k) {
@@ -90,6 +90,7 @@ static WsLayout ws_layout(int64_t nU, int64_t nI, int d, int dtype, int k) {
   w.offA = off; if (w.convA) off += align_up(cpad * w.K * 2, 1024);
   w.offB = off; if (w.convB) off += align_up((size_t)nI * w.K * 2, 1024);
   w.offNormU = off; off += align_up(cpad * sizeof(float), 1024);
+  w.offRowExp = off; off += align_up(cpad * sizeof(int32_t), 1024);
   w.offInvV = off; off += align_up((size_t)nI * sizeof(float), 1024);
   w.offListS = off; off += align_up(cpad * LISTS_PER_ROW * w.cap * REC_FLOATS * sizeof(float), 1024);
   w.offCounts = off; off += align_up(cpad * LISTS_PER_ROW * sizeof(int32_t), 1024);
@@ -231,17 +232,16 @@ static int score_topk_impl(const void* U, const void* V, int64_t nU, int64_t nI,
       const void* A16 = Uc;
       if (u0 > 0) prof_mark(PROF_PREP, 0, st);
       if (dtype == DIVREC_F32) {
-        e = cudaMemsetAsync(amax, 0, sizeof(uint32_t), st);
-        if (e != cudaSuccess) return cuda_fail(e, "memset amax");
-        e = launch_prep_f32(reinterpret_cast<const float*>(Uc), cu, d, w.d_pad, reinterpret_cast<__half*>(ws + w.offA), amax,
-                            sexp, norms_u, nullptr, nullptr, st);
+        int32_t* row_exps = reinterpret_cast<int32_t*>(ws + w.offRowExp);
+        e = launch_prep_f32_rows(reinterpret_cast<const float*>(Uc), cu, d, w.d_pad, reinterpret_cast<__half*>(ws + w.offA), row_exps,
+                                 norms_u, st);
         A16 = ws + w.offA;
-        sp.scale_exps = sexp; sp.amax_bits = amax;
+        sp.scale_exps = sexp; sp.amax_bits = amax; sp.row_exps = row_exps;
         sp.c_margin = 1.1f / 1024.0f;
       } else {
         e = launch_prep_bf16(Uc, cu, d, w.d_pad, w.convA ? ws + w.offA : nullptr, norms_u, nullptr, nullptr, st);
         if (w.convA) A16 = ws + w.offA;
-        sp.scale_exps = nullptr; sp.amax_bits = nullptr;
+        sp.scale_exps = nullptr; sp.amax_bits = nullptr; sp.row_exps = nullptr;
         sp.c_margin = 1.0f / 4096.0f;
       }
       if (e != cudaSuccess) return cuda_fail(e, "prepare user table");
@@ -253,7 +253,7 @@ static int score_topk_impl(const void* U, const void* V, int64_t nU, int64_t nI,
       fp.lists = reinterpret_cast<float*>(ws + w.offListS);
       fp.list_count = reinterpret_cast<int32_t*>(ws + w.offCounts);
       fp.thr_out = reinterpret_cast<float*>(ws + w.offThr);
-      fp.norms_u = norms_u; fp.nvmax_bits = nvmax; fp.amax_bits = sp.amax_bits; fp.scale_exps = sp.scale_exps;
+      fp.norms_u = norms_u; fp.nvmax_bits = nvmax; fp.amax_bits = sp.amax_bits; fp.scale_exps = sp.scale_exps; fp.row_exps = sp.row_exps;
       fp.c_margin = sp.c_margin; fp.d = d;
       const char* err = "";
       prof_mark(PROF_FILTER, 0, st);
@@ -605,6 +605,23 @@ int divrec_bpr_loss_bwd(const float* pos, const float* neg, const float* g, int6
   if (B <= 0) return fail(DIVREC_ERR_ARG, "bpr_loss_bwd: B must be positive");
   cudaError_t e = launch_bpr_loss_bwd(pos, neg, g, B, gpos, gneg, reinterpret_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "bpr_loss_bwd launch");
+  return DIVREC_OK;
+}
+
+size_t divrec_build_csr_workspace(int64_t nnz, int64_t nU) {
+  if (nnz < 0 || nU <= 0) return 0;
+  return build_csr_workspace_bytes(nnz, nU);
+}
+
+int divrec_build_csr(const int64_t* pairs, int64_t nnz, int64_t nU, int64_t nI, int64_t* rowptr, int32_t* items, void* workspace,
+                     size_t ws_bytes, void* stream) {
+  if (!rowptr || (nnz > 0 && (!pairs || !items))) return fail(DIVREC_ERR_ARG, "build_csr: null pointer");
+  if (nnz < 0 || nU <= 0 || nI <= 0 || nI >= ((int64_t)1 << 31)) return fail(DIVREC_ERR_ARG, "build_csr: need nnz >= 0, nU > 0, 0 < nI < 2^31");
+  if (reinterpret_cast<uintptr_t>(pairs) & 15) return fail(DIVREC_ERR_ARG, "build_csr: pairs must be 16-byte aligned");
+  if (!workspace || ws_bytes < build_csr_workspace_bytes(nnz, nU)) return fail(DIVREC_ERR_WORKSPACE, "build_csr: workspace too small");
+  if (reinterpret_cast<uintptr_t>(workspace) & 255) return fail(DIVREC_ERR_ARG, "build_csr: workspace must be 256-byte aligned");
+  cudaError_t e = launch_build_csr(pairs, nnz, nU, nI, rowptr, items, workspace, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "build_csr launch");
   return DIVREC_OK;
 }
 

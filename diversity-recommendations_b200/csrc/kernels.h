@@ -61,6 +61,7 @@ struct FilterParams {
   const uint32_t* nvmax_bits;
   const uint32_t* amax_bits;
   const int32_t* scale_exps;
+  const int32_t* row_exps;
   float c_margin;
   int d;
   // two-block kernel only: seen-item pattern of the rows over the sample tiles (hint_mask_kernel), or null
@@ -88,6 +89,9 @@ cudaError_t launch_hint_mask(const int64_t* seen_rowptr, const int32_t* seen_ite
 // amax_bits must be zeroed by the caller; scale_exp is written.
 cudaError_t launch_prep_f32(const float* X, int64_t rows, int d, int d_pad, __half* out, uint32_t* amax_bits,
                             int32_t* scale_exp, float* norms, float* inv_norms, uint32_t* normmax_bits, cudaStream_t stream);
+// fp32 user rows -> fp16 plane with a per-ROW power-of-two scale (row_exp[r]) + row norms, in one pass
+cudaError_t launch_prep_f32_rows(const float* X, int64_t rows, int d, int d_pad, __half* out, int32_t* row_exp, float* norms,
+                                 cudaStream_t stream);
 // bf16 [rows,d]: row norms (+ max); zero-padded copy [rows,d_pad] when out != null
 cudaError_t launch_prep_bf16(const void* X, int64_t rows, int d, int d_pad, void* out, float* norms, float* inv_norms,
                              uint32_t* normmax_bits, cudaStream_t stream);
@@ -104,11 +108,12 @@ struct SelectParams {
   const int64_t* seen_rowptr;
   const int32_t* seen_items;
   int64_t item_id_offset;
-  const int32_t* scale_exps;   // device [2] or null: tensor-core scores carry a factor 2^(e0+e1)
+  const int32_t* scale_exps;   // device [2] or null: [1] = exponent of the item plane (tensor-core scores carry 2^(row_exps[row] + scale_exps[1]))
+  const int32_t* row_exps;     // device [nU] or null: per-row exponent of the user plane
   const float* norms_u;        // [nU]
   const uint32_t* nvmax_bits;  // device: max item row norm (float bits)
   const float* inv_norm_v;     // [nI] 1 / |V_i| (fused ILD)
-  const uint32_t* amax_bits;   // device [2]: max |element| of the user / item table (float bits), null for bf16
+  const uint32_t* amax_bits;   // device [2]: [1] = max |element| of the item table (float bits), null for bf16
   float c_margin;              // delta_u = c_margin * |u| * max|v|
   float* out_scores;           // [nU,k]
   int64_t* out_items;          // [nU,k]
@@ -196,6 +201,10 @@ cudaError_t launch_relevance(const int64_t* recs, int64_t nU, int k, const int64
 cudaError_t launch_bpr_loss_fwd(const float* pos, const float* neg, int64_t B, float* lv, int32_t* hit, cudaStream_t stream);
 cudaError_t launch_bpr_loss_bwd(const float* pos, const float* neg, const float* g, int64_t B, float* gpos, float* gneg,
                                 cudaStream_t stream);
+
+size_t build_csr_workspace_bytes(int64_t nnz, int64_t nU);
+cudaError_t launch_build_csr(const int64_t* pairs, int64_t nnz, int64_t nU, int64_t nI, int64_t* rowptr, int32_t* items,
+                             void* workspace, cudaStream_t stream);
 
 struct MmrParams {
   const void* V;

@@ -78,6 +78,107 @@ convert_f32_kernel(const float* __restrict__ X, int64_t rows, int d, int d_pad, 
   if (normmax_bits && lane == 0 && wmax > 0.f && wmax < INFINITY) atomicMax(normmax_bits, __float_as_uint(wmax));
 }
 
+// User rows: ONE pass, each row scaled by its OWN power of two (max |x| of the row into [2^13, 2^14)): no global absmax pass
+// over the table, and small-norm rows keep their full fp16 precision.  row_exp[r] is the exponent used (the select kernel
+// and the list-tightening margin read it back), norms[r] the fp32 row norm (rounded up: it feeds an error bound).
+__global__ void __launch_bounds__(256)
+convert_f32_rows_kernel(const float* __restrict__ X, int64_t rows, int d, int d_pad, __half* __restrict__ out,
+                        int32_t* __restrict__ row_exp, float* __restrict__ norms) {
+  const uint32_t lane = lane_id();
+  const bool vec = ((d & 3) == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
+  for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < rows; r += ((int64_t)gridDim.x * blockDim.x) >> 5) {
+    const float* x = X + r * d;
+    __half* o = out + r * d_pad;
+    float ss = 0.f, am = 0.f;
+    if (d_pad <= 512) {
+      // the whole row in registers (up to 4 float4 per lane): one read of the table
+      float4 v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = (int)lane * 4 + j * 128;
+        v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < d_pad) {
+          if (vec && c + 3 < d) v[j] = __ldg(reinterpret_cast<const float4*>(x + c));
+          else { v[j].x = c < d ? x[c] : 0.f; v[j].y = c + 1 < d ? x[c + 1] : 0.f; v[j].z = c + 2 < d ? x[c + 2] : 0.f; v[j].w = c + 3 < d ? x[c + 3] : 0.f; }
+        }
+        ss = fmaf(v[j].x, v[j].x, ss); ss = fmaf(v[j].y, v[j].y, ss); ss = fmaf(v[j].z, v[j].z, ss); ss = fmaf(v[j].w, v[j].w, ss);
+        am = fmaxf(am, fmaxf(fmaxf(fabsf(v[j].x), fabsf(v[j].y)), fmaxf(fabsf(v[j].z), fabsf(v[j].w))));
+      }
+#pragma unroll
+      for (int o2 = 16; o2 > 0; o2 >>= 1) am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, o2));
+      int e = 0;
+      if (am > 0.f && am < INFINITY) e = max(-100, min(100, 13 - ilogbf(am)));
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = (int)lane * 4 + j * 128;
+        if (c < d_pad) {
+          __half hv[4] = {__float2half_rn(ldexpf(v[j].x, e)), __float2half_rn(ldexpf(v[j].y, e)), __float2half_rn(ldexpf(v[j].z, e)),
+                          __float2half_rn(ldexpf(v[j].w, e))};
+          *reinterpret_cast<uint2*>(o + c) = *reinterpret_cast<const uint2*>(hv);
+        }
+      }
+      ss = warp_sum(ss);
+      if (lane == 0) { row_exp[r] = e; norms[r] = sqrtf(ss) * 1.000001f; }
+    } else {
+      for (int c = lane; c < d; c += 32) { const float t = x[c]; ss = fmaf(t, t, ss); am = fmaxf(am, fabsf(t)); }
+#pragma unroll
+      for (int o2 = 16; o2 > 0; o2 >>= 1) am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, o2));
+      int e = 0;
+      if (am > 0.f && am < INFINITY) e = max(-100, min(100, 13 - ilogbf(am)));
+      for (int c = lane; c < d_pad; c += 32) o[c] = __float2half_rn(ldexpf(c < d ? x[c] : 0.f, e));
+      ss = warp_sum(ss);
+      if (lane == 0) { row_exp[r] = e; norms[r] = sqrtf(ss) * 1.000001f; }
+    }
+  }
+}
+
+// The same for the common shape (d_pad == 128, 16-byte aligned rows, d % 4 == 0): FOUR rows per warp, eight lanes per row,
+// four independent 128-bit loads in flight per lane (the one-row-per-warp form is latency-bound: one load per lane and a
+// dependent reduce / scale / store chain per row).
+__global__ void __launch_bounds__(256)
+convert_f32_rows128_kernel(const float* __restrict__ X, int64_t rows, int d, __half* __restrict__ out,
+                           int32_t* __restrict__ row_exp, float* __restrict__ norms) {
+  const uint32_t lane = lane_id();
+  const int sub = lane & 7, grp = lane >> 3;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r0 = warp0 * 4; r0 < rows; r0 += nwarps * 4) {
+    const int64_t r = r0 + grp;
+    const bool on = r < rows;
+    const float* x = X + r * d;
+    float4 v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = (sub + 8 * j) * 4;
+      v[j] = (on && c < d) ? __ldg(reinterpret_cast<const float4*>(x + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float ss = 0.f, am = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      ss = fmaf(v[j].x, v[j].x, ss); ss = fmaf(v[j].y, v[j].y, ss); ss = fmaf(v[j].z, v[j].z, ss); ss = fmaf(v[j].w, v[j].w, ss);
+      am = fmaxf(am, fmaxf(fmaxf(fabsf(v[j].x), fabsf(v[j].y)), fmaxf(fabsf(v[j].z), fabsf(v[j].w))));
+    }
+#pragma unroll
+    for (int o2 = 1; o2 < 8; o2 <<= 1) {
+      am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, o2));
+      ss += __shfl_xor_sync(0xffffffffu, ss, o2);
+    }
+    int e = 0;
+    if (am > 0.f && am < INFINITY) e = max(-100, min(100, 13 - ilogbf(am)));
+    if (on) {
+      __half* o = out + r * 128;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = (sub + 8 * j) * 4;
+        __half hv[4] = {__float2half_rn(ldexpf(v[j].x, e)), __float2half_rn(ldexpf(v[j].y, e)), __float2half_rn(ldexpf(v[j].z, e)),
+                        __float2half_rn(ldexpf(v[j].w, e))};
+        *reinterpret_cast<uint2*>(o + c) = *reinterpret_cast<const uint2*>(hv);
+      }
+      if (sub == 0) { row_exp[r] = e; norms[r] = sqrtf(ss) * 1.000001f; }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256)
 prep_bf16_kernel(const __nv_bfloat16* __restrict__ X, int64_t rows, int d, int d_pad, __nv_bfloat16* __restrict__ out,
                  float* __restrict__ norms, float* __restrict__ inv_norms, uint32_t* __restrict__ normmax_bits) {
@@ -120,6 +221,16 @@ cudaError_t launch_prep_f32(const float* X, int64_t rows, int d, int d_pad, __ha
   scale_exp_kernel<<<1, 1, 0, stream>>>(amax_bits, scale_exp);
   count_launch();
   convert_f32_kernel<<<grid_for(rows * 32, 256), 256, 0, stream>>>(X, rows, d, d_pad, out, scale_exp, norms, inv_norms, normmax_bits);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_prep_f32_rows(const float* X, int64_t rows, int d, int d_pad, __half* out, int32_t* row_exp, float* norms,
+                                 cudaStream_t stream) {
+  if (d_pad == 128 && (d & 3) == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0)
+    convert_f32_rows128_kernel<<<grid_for(rows * 8, 256), 256, 0, stream>>>(X, rows, d, out, row_exp, norms);
+  else
+    convert_f32_rows_kernel<<<grid_for(rows * 32, 256), 256, 0, stream>>>(X, rows, d, d_pad, out, row_exp, norms);
   count_launch();
   return cudaGetLastError();
 }

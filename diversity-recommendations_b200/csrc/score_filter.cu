@@ -87,12 +87,13 @@ __device__ __forceinline__ float max32(const uint32_t* v) {
 // 2 delta of a user row in the (scaled) units of the tensor-core scores; same formula as select_topk.cu
 __device__ __forceinline__ float row_margin2(const FilterParams& p, int64_t row) {
   int e2 = 0;
-  if (p.scale_exps != nullptr) e2 = p.scale_exps[0] + p.scale_exps[1];
+  if (p.scale_exps != nullptr) e2 = p.scale_exps[1];
+  if (p.row_exps != nullptr) e2 += p.row_exps[row];
   const float nu = p.norms_u[row], nvmax = __uint_as_float(*p.nvmax_bits);
   float delta = p.c_margin * nu * nvmax;
   if (p.amax_bits != nullptr) {
-    const float au = __uint_as_float(p.amax_bits[0]), av = __uint_as_float(p.amax_bits[1]);
-    delta += 3.64e-12f * sqrtf((float)p.d) * (nu * av + nvmax * au);
+    const float av = __uint_as_float(p.amax_bits[1]);
+    delta += 3.64e-12f * sqrtf((float)p.d) * (nu * av + nvmax * nu);
   }
   return ldexpf(2.0f * delta + REC_ID_SLACK * nu * nvmax, e2) * 1.0001f;
 }

@@ -258,14 +258,16 @@ select_topk_kernel(const SelectParams p) {
 
   // 2 delta in the (scaled) units of the tensor-core scores
   int e2 = 0;
-  if (p.scale_exps != nullptr) e2 = p.scale_exps[0] + p.scale_exps[1];
+  if (p.scale_exps != nullptr) e2 = p.scale_exps[1];
+  if (p.row_exps != nullptr) e2 += p.row_exps[row];
   const float nu = p.norms_u[row], nvmax = __uint_as_float(*p.nvmax_bits);
   float delta = p.c_margin * nu * nvmax;
   if (p.amax_bits != nullptr) {
     // fp16 subnormals: |fp16(x) - x| <= 2^-11 |x| + 2^-25 in scaled units, the absolute part adds
-    // 2^-25 sqrt(d) (|u| 2^-e1 + |v| 2^-e0) <= 2^-38 sqrt(d) (|u| amax_v + |v| amax_u) to delta
-    const float au = __uint_as_float(p.amax_bits[0]), av = __uint_as_float(p.amax_bits[1]);
-    delta += 3.64e-12f * sqrtf((float)p.d) * (nu * av + nvmax * au);
+    // 2^-25 sqrt(d) (|u| 2^-e_v + |v| 2^-e_u) <= 2^-38 sqrt(d) (|u| amax_v + |v| amax_u), amax_u = the ROW's largest
+    // element (its own scale), itself <= |u|
+    const float av = __uint_as_float(p.amax_bits[1]);
+    delta += 3.64e-12f * sqrtf((float)p.d) * (nu * av + nvmax * nu);
   }
   const float margin2 = ldexpf(2.0f * delta + REC_ID_SLACK * nu * nvmax, e2) * 1.0001f;  // + the index bytes carried by the record scores
 

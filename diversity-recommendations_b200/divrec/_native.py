@@ -62,6 +62,8 @@ SIGNATURES = {
     "divrec_relevance_metrics": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp]),
     "divrec_bpr_loss_fwd": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp]),
     "divrec_bpr_loss_bwd": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "divrec_build_csr_workspace": (_sz, [_i64, _i64]),
+    "divrec_build_csr": (_i32, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _sz, _vp]),
     "divrec_mmr_workspace": (_sz, [_i32, _i32]),
     "divrec_mmr_rerank": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp, _i64, _i32, _i32, _f32, _vp, _vp, _vp, _sz, _vp]),
 }
@@ -352,6 +354,27 @@ def entropy_from_counts(counts: torch.Tensor) -> torch.Tensor:
         rc = lib.divrec_entropy_from_counts(_ptr(counts), counts.numel(), _ptr(out), _stream(counts.device))
     _check(rc, "divrec_entropy_from_counts")
     return out
+
+
+def build_csr(pairs: torch.Tensor, n_users: int, n_items: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """[nnz,2] int64 (user,item) pairs on the device -> (rowptr int64 [U+1], items int32 ascending and unique per row).
+    Pairs outside [0,U) x [0,I) are dropped.  One host synchronisation at the end (the number of distinct pairs sizes the
+    returned item array)."""
+    lib = load_library()
+    pairs = _cuda(pairs, "interactions", torch.int64)
+    if pairs.dim() != 2 or pairs.shape[1] != 2:
+        raise ValueError("interactions must be [nnz, 2]")
+    nnz, dev = pairs.shape[0], pairs.device
+    rowptr = torch.empty(n_users + 1, dtype=torch.int64, device=dev)
+    items = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        nbytes = lib.divrec_build_csr_workspace(nnz, n_users)
+        ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
+        off = (-ws.data_ptr()) % 256
+        rc = lib.divrec_build_csr(_ptr(pairs) if nnz else None, nnz, int(n_users), int(n_items), _ptr(rowptr), _ptr(items),
+                                  ws.data_ptr() + off, nbytes, _stream(dev))
+    _check(rc, "divrec_build_csr")
+    return rowptr, items[:int(rowptr[-1])]
 
 
 def bpr_fwd(U, V, u, p, n):

@@ -20,15 +20,21 @@ PairWiseRow = Tuple[int, int, int, Optional[torch.Tensor], Optional[torch.Tensor
 RankingRow = Tuple[torch.LongTensor, torch.LongTensor, torch.LongTensor, Optional[torch.Tensor], Optional[torch.Tensor]]
 
 
-def interactions_to_csr(interactions: Optional[torch.Tensor], n_users: int) -> Tuple[torch.Tensor, torch.Tensor]:
+def interactions_to_csr(interactions: Optional[torch.Tensor], n_users: int, n_items: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """[nnz,2] (user,item) pairs -> (rowptr int64 [U+1], items int32 ascending and unique per row).
-    Works on whatever device `interactions` lives on (sort-based, no per-user scan)."""
+    Interactions on a CUDA device go through the library's sort-free builder (divrec_build_csr: count, scan, bucket,
+    per-row sort + de-duplication, compaction); host tensors (the reference-compatible `__iter__` path) are built with a
+    sort on the host.  Users outside [0, n_users) have no row (a frozen / train set may hold users the scored set never
+    mentions: the reference filters `frozen` per user, base_datasets.py:145-147)."""
     if interactions is None or interactions.numel() == 0:
         dev = interactions.device if interactions is not None else "cpu"
         return torch.zeros(n_users + 1, dtype=torch.int64, device=dev), torch.zeros(0, dtype=torch.int32, device=dev)
+    if interactions.is_cuda:
+        from .. import _native
+        if n_items is None:
+            n_items = int(interactions[:, 1].max()) + 1
+        return _native.build_csr(interactions.to(torch.int64), int(n_users), int(n_items))
     pairs = interactions.to(torch.int64)
-    # users outside [0, n_users) have no row here (a frozen / train set may hold users the scored set never mentions:
-    # the reference filters `frozen` per user, base_datasets.py:145-147)
     pairs = pairs[(pairs[:, 0] >= 0) & (pairs[:, 0] < n_users)]
     pairs = torch.unique(pairs, dim=0)
     counts = torch.bincount(pairs[:, 0], minlength=n_users)
@@ -127,7 +133,7 @@ class RankingDataset(IterableDataset):
             inter = None if self.frozen is None else self.frozen.interactions
             if inter is not None:
                 inter = inter.to(device)
-            rowptr, items = interactions_to_csr(inter, int(self.data.number_of_users))
+            rowptr, items = interactions_to_csr(inter, int(self.data.number_of_users), int(self.data.number_of_items))
             self._csr[key] = (rowptr.to(device), items.to(device))
         return self._csr[key]
 

@@ -229,6 +229,21 @@ int divrec_peer_open(const unsigned char* handle /*host [64]*/, void** ptr_out);
 int divrec_peer_close(void* ptr);
 int divrec_peer_free(void* ptr);
 
+/* ---------------------------------------------------------------------------------------
+ * seen-item mask builder: interaction pairs -> CSR (rows ascending and unique)
+ *   replaces: the per-user scan `interactions[:, 0] == user_id` + set construction of
+ *             divrec/datasets/base_datasets.py:139-149 (RankingDataset.__iter__; 78 % of the reference's evaluation
+ *             time at the MovieLens-20M shape) and the same scan in divrec/metrics/precision_at_k.py:18 etc.
+ *   pairs [nnz, 2] int64 (user, item), any order, duplicates allowed; pairs with a user outside [0, nU) or an item
+ *   outside [0, nI) are dropped.  rowptr [nU + 1] int64 and items [>= nnz] int32 are outputs: row u holds the distinct
+ *   items of user u in ascending order, rowptr[nU] of the entries of `items` are valid.
+ *   Sort-free: count per user, scan, scatter into buckets, per-bucket sort (bitonic or id-window bitmap) + de-duplication,
+ *   second scan, compaction -- all on the device, no synchronisation.
+ * ------------------------------------------------------------------------------------- */
+size_t divrec_build_csr_workspace(int64_t nnz, int64_t nU);
+int divrec_build_csr(const int64_t* pairs, int64_t nnz, int64_t nU, int64_t nI, int64_t* rowptr /*[nU+1]*/,
+                     int32_t* items /*[nnz]*/, void* workspace, size_t ws_bytes, void* stream);
+
 /* BPR triple sampler on the device
  *   replaces: PairWiseDataset.__iter__, divrec/datasets/base_datasets.py:70-107 -- per user max_sampled positives drawn
  *             with replacement from the user's items, max_sampled negatives with replacement from

@@ -997,3 +997,38 @@ def test_cfg3_shape_sampled_gradient_rows(native, dev):
     assert (gV.double() - ref_gV).abs().max().item() <= 1e-5 * float(ref_gV.abs().max())
     touched = torch.zeros(nI, dtype=torch.bool, device=dev); touched[p] = True; touched[n] = True
     assert float(gV[~touched].abs().sum()) == 0.0
+
+
+# ------------------------------------------------------------------------------------------------
+# seen-mask CSR builder (divrec_build_csr) against the oracle's sort-based restatement
+# ------------------------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("nU,nI,nnz,shape", [
+    (943, 1682, 90570, "uniform"),          # cfg1's mask
+    (300, 26744, 60000, "duplicates"),      # repeated pairs, users / items out of range, empty rows
+    (50, 400000, 30000, "uniform"),         # catalogue wider than one id window of the bitmap path
+    (40, 20000, 200000, "long_rows"),       # rows of ~10 000 items: beyond the shared-memory sort
+    (1, 100, 0, "uniform"),                 # no interactions at all
+])
+def test_csr_builder_vs_oracle(native, dev, nU, nI, nnz, shape):
+    gen = torch.Generator().manual_seed(nU + nnz)
+    if nnz == 0:
+        pairs = torch.zeros((0, 2), dtype=torch.int64)
+    elif shape == "long_rows":
+        pairs = torch.stack([torch.randint(0, nU // 2, (nnz,), generator=gen) * 2, torch.randint(0, nI, (nnz,), generator=gen)], 1)
+    else:
+        pairs = torch.stack([torch.randint(0, nU, (nnz,), generator=gen), torch.randint(0, nI, (nnz,), generator=gen)], 1)
+    if shape == "duplicates":
+        pairs[: nnz // 3] = pairs[nnz // 3: 2 * (nnz // 3)]                 # exact repeats
+        pairs[-50:, 0] = nU + 5                                             # users beyond the scored set
+        pairs[-100:-50, 0] = -1
+        pairs[pairs[:, 0] % 7 == 3, 0] = 0                                  # some users end up with no row at all
+    keep = (pairs[:, 0] >= 0) & (pairs[:, 0] < nU)
+    o_rp, o_it = O.seen_csr(pairs[keep], nU)
+    rp, it = native.build_csr(pairs.to(dev), nU, nI)
+    assert torch.equal(rp.cpu(), o_rp) and torch.equal(it.cpu(), o_it)
+    # and through the dataset shim (the path get_model_recommendations takes)
+    from divrec.datasets.base_datasets import interactions_to_csr
+    rp2, it2 = interactions_to_csr(pairs.to(dev), nU, nI)
+    assert torch.equal(rp2.cpu(), o_rp) and torch.equal(it2.cpu(), o_it)
