@@ -20,6 +20,9 @@ namespace {
 
 constexpr int RT = 1024;       // threads per CTA of the selection kernel (one CTA per row: its passes are latency, so go wide)
 constexpr int RT_SCORE = 256;  // threads per CTA of the chip-wide scoring kernel
+#ifndef DIVREC_RESCUE_CHUNKS
+#define DIVREC_RESCUE_CHUNKS 148  // item ranges per row in the chip-wide scoring kernel: one wave of CTAs
+#endif
 constexpr int RSORT = 512;     // >= MAX_K
 static_assert(RSORT >= MAX_K, "sort buffer covers the largest k");
 
@@ -317,10 +320,13 @@ cudaError_t launch_rescue(const RescueParams& p_in, cudaStream_t stream) {
   const size_t smem_sel = (size_t)((p.d + 3) & ~3) * sizeof(float) + keys_bytes;
   p.keys_in_smem = smem_sel <= 200 * 1024 ? 1 : 0;
   // the first `slots` uncertified rows are scored by the whole chip (CTAs beyond the device-side count exit at once)
-  const int slots = p.grid < 64 ? p.grid : 64;
-  // item ranges of >= 128 items, up to two waves of CTAs per row: one uncertified row (the usual count) is scored by the whole chip
+#ifndef DIVREC_RESCUE_SLOTS
+#define DIVREC_RESCUE_SLOTS 32   // uncertified rows scored by the whole chip (a step has ~6; the rest fall back to one CTA per row)
+#endif
+  const int slots = p.grid < DIVREC_RESCUE_SLOTS ? p.grid : DIVREC_RESCUE_SLOTS;
+  // item ranges of >= 128 items, about one wave of CTAs per row: one uncertified row (the usual count) is scored by the whole chip
   int64_t chunks = ((int64_t)p.nI + 127) / 128;
-  if (chunks > 296) chunks = 296;
+  if (chunks > DIVREC_RESCUE_CHUNKS) chunks = DIVREC_RESCUE_CHUNKS;
   const int64_t items_per_cta = ((int64_t)p.nI + chunks - 1) / chunks;
   p.prescored = slots;
   rescue_score_kernel<<<dim3((unsigned)chunks, (unsigned)slots), RT_SCORE, smem, stream>>>(p, items_per_cta);
