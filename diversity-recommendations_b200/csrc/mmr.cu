@@ -360,6 +360,220 @@ mmr_lazy_kernel(const MmrParams p) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// lazy greedy, ONE WARP PER USER (round 2)
+// ---------------------------------------------------------------------------------------------------------
+// The block-per-user kernel above spends its time at block barriers (ncu: 55 % of the stall samples, ~10k cycles per
+// pick for a handful of dot products).  Lazy greedy needs very little arithmetic per pick -- a nomination (arg-max of
+// the bounds) and the refresh of one or two stale nominees -- so here a user is handled by a single warp and nothing
+// ever waits for another warp: candidate c = 32 s + lane lives in slot s of its lane (score, max-cosine so far, picks
+// seen, item id: registers); the picks made so far are a list of (item id, 1 / |V|) in shared memory, and a refresh
+// re-gathers the unseen pick rows from the L2-resident item table (coalesced 512-byte rows, four in flight) instead of
+// keeping a 50 KB copy per user in shared memory -- which is what capped the old kernel at four users per SM.  Twenty-odd
+// users per SM are in flight and hide each other's latencies.
+constexpr int WPB = 4;  // warps (users) per CTA
+
+// Four warp sums for the price of six shuffles: two butterfly steps fold the four partials onto lane groups, three more
+// finish.  Afterwards every lane with ((lane >> 4) & 1) | (((lane >> 3) & 1) << 1) == q holds the total of part[q].
+__device__ __forceinline__ float warp_sum4(const float (&part)[4], uint32_t lane) {
+  float v01 = (lane & 16) ? part[1] : part[0], o01 = (lane & 16) ? part[0] : part[1];
+  float v23 = (lane & 16) ? part[3] : part[2], o23 = (lane & 16) ? part[2] : part[3];
+  v01 += __shfl_xor_sync(0xffffffffu, o01, 16);
+  v23 += __shfl_xor_sync(0xffffffffu, o23, 16);
+  float v = (lane & 8) ? v23 : v01, o = (lane & 8) ? v01 : v23;
+  v += __shfl_xor_sync(0xffffffffu, o, 8);
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v;
+}
+__device__ __forceinline__ int sum4_group(uint32_t lane) { return (int)(((lane >> 4) & 1u) | (((lane >> 3) & 1u) << 1)); }
+__device__ __forceinline__ int sum4_lane_of(int q) { return ((q & 1) << 4) | ((q >> 1) << 3); }
+
+// per-warp shared memory: candidate state [Cp] x (score, max cosine so far, item id, picks seen as u16) + the pick list
+// (14 bytes per candidate: the state is what bounds the users in flight per SM, and the kernel is latency-bound)
+__host__ __device__ inline size_t mmr_warp_smem_bytes(int Cp, int k) { return (size_t)Cp * 14 + (size_t)k * 8; }
+
+template <int NV, int DT>
+__global__ void __launch_bounds__(WPB * 32)
+mmr_warp_kernel(const MmrParams p, int Cp) {
+  extern __shared__ __align__(16) uint8_t wsm[];
+  const int w = threadIdx.x >> 5;
+  const uint32_t lane = lane_id();
+  const int C = p.C, d = p.d, k = p.k, nvec = d >> 2;
+  uint8_t* base = wsm + (size_t)w * mmr_warp_smem_bytes(Cp, k);
+  float* sc = reinterpret_cast<float*>(base);      // [Cp] relevance score (-inf: not a candidate)
+  float* ms = sc + Cp;                             // [Cp] max cosine with the picks seen so far (-1.0001 before any)
+  int* id = reinterpret_cast<int*>(ms + Cp);       // [Cp] item id
+  int* pick_id = id + Cp;                          // [k]
+  float* pick_inv = reinterpret_cast<float*>(pick_id + k);
+  unsigned short* seen = reinterpret_cast<unsigned short*>(pick_inv + k);  // [Cp] picks the candidate has been evaluated against
+  const float lam = p.lambda, om = 1.0f - p.lambda;
+  const int64_t warp0 = (int64_t)blockIdx.x * WPB + w, nwarps = (int64_t)gridDim.x * WPB;
+
+  for (int64_t u = warp0; u < p.nU; u += nwarps) {
+    __syncwarp();
+    int nv = 0;
+    for (int c = lane; c < Cp; c += 32) {
+      float s_ = -INFINITY;
+      int i_ = -1;
+      if (c < C) {
+        const int64_t it = p.cand_items[u * C + c];
+        if (it >= 0 && it < p.nI) { i_ = (int)it; s_ = p.cand_scores[u * C + c]; ++nv; }
+      }
+      sc[c] = s_; id[c] = i_; ms[c] = -1.0001f; seen[c] = 0;   // score -inf: padding (or, later, picked)
+    }
+    nv = __reduce_add_sync(0xffffffffu, nv);
+    __syncwarp();
+    const int n_pick = min(k, nv);
+
+    for (int r = 0; r < k; ++r) {
+      if (r >= n_pick) {  // fewer real candidates than k: pad
+        if (lane == 0) { p.out_items[u * k + r] = -1; if (p.out_scores) p.out_scores[u * k + r] = -INFINITY; }
+        continue;
+      }
+      int j = 0;  // the first pick is the best-scored candidate
+      while (r > 0) {
+        // ---- nominate: the candidate with the largest bound, ties -> lowest rank ----
+        float best = -INFINITY;
+        int bidx = 0x7fffffff;
+        for (int c = lane; c < Cp; c += 32) {
+          const float ub = lam * sc[c] - om * ms[c];  // -inf for padding and picked candidates
+          if (ub > best) { best = ub; bidx = c; }     // ascending c per lane: the first maximum is the lowest rank
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+          if (ov > best || (ov == best && oi < bidx)) { best = ov; bidx = oi; }
+        }
+        j = bidx;
+        const int cs = seen[j];
+        if (cs >= r) break;   // the nominee's bound is exact: it is the eager arg-max
+        // ---- refresh: cosines with the picks the nominee has not seen; its row and the pick rows are re-gathered from
+        // the L2-resident item table, all loads of a batch in flight together ----
+        const int item = id[j];
+        float4 e[NV];
+#pragma unroll
+        for (int jj = 0; jj < NV; ++jj) {
+          const int c4 = (int)lane + 32 * jj;
+          e[jj] = c4 < nvec ? ld_row4<DT>(p.V, item, d, c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        float nn = 0.f;   // |V_c|^2 from the row that is in flight anyway
+#pragma unroll
+        for (int jj = 0; jj < NV; ++jj) { nn = fmaf(e[jj].x, e[jj].x, nn); nn = fmaf(e[jj].y, e[jj].y, nn); nn = fmaf(e[jj].z, e[jj].z, nn); nn = fmaf(e[jj].w, e[jj].w, nn); }
+        float mx = -INFINITY;
+        for (int t0 = cs; t0 < r; t0 += 4) {
+          float part[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int t = min(t0 + q, r - 1);
+            const int pit = pick_id[t];
+            float a = 0.f;
+#pragma unroll
+            for (int jj = 0; jj < NV; ++jj) {
+              const int c4 = (int)lane + 32 * jj;
+              if (c4 < nvec) {
+                const float4 x = ld_row4<DT>(p.V, pit, d, c4);
+                a = fmaf(e[jj].x, x.x, a); a = fmaf(e[jj].y, x.y, a); a = fmaf(e[jj].z, x.z, a); a = fmaf(e[jj].w, x.w, a);
+              }
+            }
+            part[q] = a;
+          }
+          const float v = warp_sum4(part, lane);
+          const int t = t0 + sum4_group(lane);
+          if (t < r) mx = fmaxf(mx, v * pick_inv[t]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o)); nn += __shfl_xor_sync(0xffffffffu, nn, o); }
+        if (lane == 0) { ms[j] = fmaxf(ms[j], mx / sqrtf(nn)); seen[j] = (unsigned short)r; }
+        __syncwarp();
+      }
+      // ---- commit pick j ----
+      if (lane == 0) {
+        const int item = id[j];
+        pick_id[r] = item;
+        p.out_items[u * k + r] = (int64_t)item;
+        if (p.out_scores) p.out_scores[u * k + r] = sc[j];
+        sc[j] = -INFINITY;  // picked: no longer a candidate
+      }
+      __syncwarp();
+      if (r > 0) {  // 1 / |V| of the new pick (its row is L2- or L1-hot: it was the last refreshed nominee more often than not)
+        const int pit = pick_id[r];
+        float n1 = 0.f;
+#pragma unroll
+        for (int jj = 0; jj < NV; ++jj) {
+          const int c4 = (int)lane + 32 * jj;
+          if (c4 < nvec) { const float4 x = ld_row4<DT>(p.V, pit, d, c4); n1 = fmaf(x.x, x.x, n1); n1 = fmaf(x.y, x.y, n1); n1 = fmaf(x.z, x.z, n1); n1 = fmaf(x.w, x.w, n1); }
+        }
+        n1 = warp_sum(n1);
+        if (lane == 0) pick_inv[r] = 1.0f / sqrtf(n1);
+        __syncwarp();
+      }
+      if (r == 0) {
+        // ---- cosines of all candidates with the FIRST pick, in one batched pass ----
+        // Before any evaluation a candidate's bound is lambda score + (1 - lambda) (cos >= -1): higher than every exact
+        // objective, so lazy greedy would refresh all C candidates one by one during the first picks -- C serial row
+        // loads per user.  Here the rows stream through once, four in flight, against the first pick's row.
+        const int item0 = pick_id[0];
+        float4 e0[NV];
+#pragma unroll
+        for (int jj = 0; jj < NV; ++jj) {
+          const int c4 = (int)lane + 32 * jj;
+          e0[jj] = c4 < nvec ? ld_row4<DT>(p.V, item0, d, c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        float n0 = 0.f;
+#pragma unroll
+        for (int jj = 0; jj < NV; ++jj) { n0 = fmaf(e0[jj].x, e0[jj].x, n0); n0 = fmaf(e0[jj].y, e0[jj].y, n0); n0 = fmaf(e0[jj].z, e0[jj].z, n0); n0 = fmaf(e0[jj].w, e0[jj].w, n0); }
+        const float inv0 = 1.0f / sqrtf(warp_sum(n0));
+        if (lane == 0) pick_inv[0] = inv0;
+        for (int c0 = 0; c0 < C; c0 += 4) {
+          float pd[4], ps[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int it = (c0 + q < C && sc[c0 + q] > -INFINITY) ? id[c0 + q] : -1;
+            float a = 0.f, b2 = 0.f;
+            if (it >= 0) {
+#pragma unroll
+              for (int jj = 0; jj < NV; ++jj) {
+                const int c4 = (int)lane + 32 * jj;
+                if (c4 < nvec) {
+                  const float4 x = ld_row4<DT>(p.V, it, d, c4);
+                  a = fmaf(e0[jj].x, x.x, a); a = fmaf(e0[jj].y, x.y, a); a = fmaf(e0[jj].z, x.z, a); a = fmaf(e0[jj].w, x.w, a);
+                  b2 = fmaf(x.x, x.x, b2); b2 = fmaf(x.y, x.y, b2); b2 = fmaf(x.z, x.z, b2); b2 = fmaf(x.w, x.w, b2);
+                }
+              }
+            }
+            pd[q] = a; ps[q] = b2;
+          }
+          const float vd = warp_sum4(pd, lane), vs = warp_sum4(ps, lane);
+          const int q = sum4_group(lane);
+          if ((lane & 7u) == 0u && c0 + q < C && sc[c0 + q] > -INFINITY) {  // one lane of each group writes its candidate
+            ms[c0 + q] = vd * inv0 / sqrtf(vs);
+            seen[c0 + q] = 1;
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+}
+
+template <int NV>
+cudaError_t launch_mmr_warp_t(const MmrParams& p, int grid, int Cp, size_t smem, cudaStream_t stream) {
+  cudaError_t e;
+  if (p.dtype == 0) {
+    e = cudaFuncSetAttribute(mmr_warp_kernel<NV, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    mmr_warp_kernel<NV, 0><<<grid, WPB * 32, smem, stream>>>(p, Cp);
+  } else {
+    e = cudaFuncSetAttribute(mmr_warp_kernel<NV, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    mmr_warp_kernel<NV, 1><<<grid, WPB * 32, smem, stream>>>(p, Cp);
+  }
+  return cudaGetLastError();
+}
+
 template <int S, int NV>
 cudaError_t launch_mmr_lazy_t(const MmrParams& p, int grid, size_t smem, cudaStream_t stream) {
   cudaError_t e;
@@ -386,7 +600,23 @@ size_t mmr_scratch_bytes(int C, int d, int* grid_out) {
 }
 
 cudaError_t launch_mmr(MmrParams p, cudaStream_t stream) {
-  // lazy greedy for the shapes it takes: 128-bit rows, C <= 1024, pick list + caches within shared memory
+  // warp-per-user lazy greedy: 128-bit rows, per-warp state within shared memory
+  const int Cp = (p.C + 31) & ~31;
+  const size_t warp_smem = (size_t)WPB * mmr_warp_smem_bytes(Cp, p.k);
+  if ((p.d & 3) == 0 && p.d <= 512 && p.k < 65536 && warp_smem <= 100 * 1024 && p.nI < ((int64_t)1 << 31) && !debug_env("DIVREC_DEBUG_MMR_BLOCK") &&
+      !debug_env("DIVREC_DEBUG_MMR_EAGER")) {
+    const int NV = p.d <= 128 ? 1 : p.d <= 256 ? 2 : 4;
+    int per_sm = (int)((size_t)232448 / (warp_smem + 1024));
+    if (per_sm > 12) per_sm = 12;
+    int64_t g = (int64_t)148 * per_sm;
+    if (g * WPB > p.nU) g = (p.nU + WPB - 1) / WPB;
+    cudaError_t e = NV == 1 ? launch_mmr_warp_t<1>(p, (int)g, Cp, warp_smem, stream)
+                  : NV == 2 ? launch_mmr_warp_t<2>(p, (int)g, Cp, warp_smem, stream)
+                            : launch_mmr_warp_t<4>(p, (int)g, Cp, warp_smem, stream);
+    count_launch();
+    return e;
+  }
+  // block-per-user lazy greedy (round 1; kept behind a debug knob for comparison): pick list + caches within shared memory
   const size_t lazy_smem = ((size_t)p.k * (size_t)(p.d + 4) + (size_t)LW * p.d) * sizeof(float);
   if ((p.d & 3) == 0 && p.d <= 512 && p.C <= 1024 && lazy_smem <= 200 * 1024 && p.nI < ((int64_t)1 << 31) &&
       !debug_env("DIVREC_DEBUG_MMR_EAGER")) {
