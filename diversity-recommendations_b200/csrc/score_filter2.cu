@@ -134,6 +134,9 @@ row_mask_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ 
   const uint32_t lane = lane_id();
   const int nw = HS + 2 * W;
   unsigned long long* m = rm_smem + (size_t)w * nw;
+  // bits are set through the 32-bit halves of the words: shared memory has a native 32-bit atomic OR, a 64-bit one is a
+  // compare-and-swap loop (ncu: 61 % of this kernel's stalls, 0.2 ms at cfg2 -- as long as a sixth of the filter itself)
+  uint32_t* m32 = reinterpret_cast<uint32_t*>(m);
   for (int64_t row = (int64_t)blockIdx.x * 8 + w; row < nU; row += (int64_t)gridDim.x * 8) {
     for (int i = lane; i < nw; i += 32) m[i] = 0ull;
     __syncwarp();
@@ -143,9 +146,11 @@ row_mask_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ 
       if (id >= 0 && id < nI) {
         const int tile = (int)(id >> 7);
         const int col = (int)(id & 127);
-        atomicOr(&m[HS + (col >> 6) * W + (tile >> 6)], 1ull << (tile & 63));
+        // dirty-block word (HS + half * W + tile / 64), bit tile % 64
+        atomicOr(&m32[2 * (HS + (col >> 6) * W + (tile >> 6)) + ((tile >> 5) & 1)], 1u << (tile & 31));
         const int s = tile / sample_stride;
-        if (s < n_sample && s * sample_stride == tile) atomicOr(&m[2 * s + (col >> 6)], 1ull << (col & 63));
+        if (s < n_sample && s * sample_stride == tile)   // sample-tile word (2 s + half), bit col % 64
+          atomicOr(&m32[2 * (2 * s + (col >> 6)) + ((col >> 5) & 1)], 1u << (col & 31));
       }
     }
     __syncwarp();
