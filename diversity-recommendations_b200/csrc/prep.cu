@@ -78,6 +78,55 @@ convert_f32_kernel(const float* __restrict__ X, int64_t rows, int d, int d_pad, 
   if (normmax_bits && lane == 0 && wmax > 0.f && wmax < INFINITY) atomicMax(normmax_bits, __float_as_uint(wmax));
 }
 
+// Item plane for the common shape (d_pad == 128, 16-byte aligned rows, d % 4 == 0): the table-wide exponent is known
+// (absmax pass), FOUR rows per warp, eight lanes per row, four independent 128-bit loads in flight per lane.
+__global__ void __launch_bounds__(256)
+convert_f32_128_kernel(const float* __restrict__ X, int64_t rows, int d, __half* __restrict__ out,
+                       const int32_t* __restrict__ scale_exp, float* __restrict__ norms, float* __restrict__ inv_norms,
+                       uint32_t* __restrict__ normmax_bits) {
+  const uint32_t lane = lane_id();
+  const int sub = lane & 7, grp = lane >> 3;
+  const int e = *scale_exp;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  float wmax = 0.f;
+  for (int64_t r0 = warp0 * 4; r0 < rows; r0 += nwarps * 4) {
+    const int64_t r = r0 + grp;
+    const bool on = r < rows;
+    const float* x = X + r * d;
+    float4 v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = (sub + 8 * j) * 4;
+      v[j] = (on && c < d) ? __ldg(reinterpret_cast<const float4*>(x + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { ss = fmaf(v[j].x, v[j].x, ss); ss = fmaf(v[j].y, v[j].y, ss); ss = fmaf(v[j].z, v[j].z, ss); ss = fmaf(v[j].w, v[j].w, ss); }
+#pragma unroll
+    for (int o2 = 1; o2 < 8; o2 <<= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o2);
+    if (on) {
+      __half* o = out + r * 128;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = (sub + 8 * j) * 4;
+        __half hv[4] = {__float2half_rn(ldexpf(v[j].x, e)), __float2half_rn(ldexpf(v[j].y, e)), __float2half_rn(ldexpf(v[j].z, e)),
+                        __float2half_rn(ldexpf(v[j].w, e))};
+        *reinterpret_cast<uint2*>(o + c) = *reinterpret_cast<const uint2*>(hv);
+      }
+      const float nrm = sqrtf(ss) * 1.000001f;  // round up: the norm feeds an error BOUND
+      if (sub == 0) {
+        if (norms) norms[r] = nrm;
+        if (inv_norms) inv_norms[r] = 1.0f / sqrtf(ss);
+      }
+      wmax = fmaxf(wmax, nrm);
+    }
+  }
+#pragma unroll
+  for (int o2 = 16; o2 > 0; o2 >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, o2));
+  if (normmax_bits && lane == 0 && wmax > 0.f && wmax < INFINITY) atomicMax(normmax_bits, __float_as_uint(wmax));
+}
+
 // User rows: ONE pass, each row scaled by its OWN power of two (max |x| of the row into [2^13, 2^14)): no global absmax pass
 // over the table, and small-norm rows keep their full fp16 precision.  row_exp[r] is the exponent used (the select kernel
 // and the list-tightening margin read it back), norms[r] the fp32 row norm (rounded up: it feeds an error bound).
@@ -220,7 +269,10 @@ cudaError_t launch_prep_f32(const float* X, int64_t rows, int d, int d_pad, __ha
   count_launch();
   scale_exp_kernel<<<1, 1, 0, stream>>>(amax_bits, scale_exp);
   count_launch();
-  convert_f32_kernel<<<grid_for(rows * 32, 256), 256, 0, stream>>>(X, rows, d, d_pad, out, scale_exp, norms, inv_norms, normmax_bits);
+  if (d_pad == 128 && (d & 3) == 0 && al16)
+    convert_f32_128_kernel<<<grid_for(rows * 8, 256), 256, 0, stream>>>(X, rows, d, out, scale_exp, norms, inv_norms, normmax_bits);
+  else
+    convert_f32_kernel<<<grid_for(rows * 32, 256), 256, 0, stream>>>(X, rows, d, d_pad, out, scale_exp, norms, inv_norms, normmax_bits);
   count_launch();
   return cudaGetLastError();
 }
