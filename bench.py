@@ -427,11 +427,11 @@ def bench_cfg3(ctx, args, steps, warmup, B=65536):
     kms = k0.elapsed_time(k1) / steps
     del gU1, gV1
     clocks = sampler.stop()
-    loss_h = torch.empty(2, dtype=torch.float64).pin_memory()
+    loss_h = torch.empty(1, dtype=torch.float32).pin_memory()
 
     def e2e_step():
         u.copy_(uh, non_blocking=True); p_.copy_(ph, non_blocking=True); n_.copy_(nh, non_blocking=True)
-        ls = step()
+        ls, _auc = step()
         loss_h.copy_(ls, non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
@@ -452,7 +452,7 @@ def bench_cfg3(ctx, args, steps, warmup, B=65536):
                        "l2": "tables + dense gradients (2 GB) exceed the 126 MB L2"},
             "clocks": clocks,
             "e2e": {"value": Bg / (e2e_ms * 1e-3), "unit": "triples/s", "h2d_bytes_per_step": 3 * B * 8,
-                    "d2h_bytes_per_step": 16, "api": "divrec.parallel.bpr_step_sharded (triples from pinned host memory, loss back)"},
+                    "d2h_bytes_per_step": 4, "api": "divrec.parallel.bpr_step_sharded (triples from pinned host memory, loss back)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
                          "traffic": traffic, "traffic_source": src, "kernel": "bpr_step_kernel", "kernel_ms": kms,

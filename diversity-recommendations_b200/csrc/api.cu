@@ -439,7 +439,7 @@ int divrec_bpr_bwd(const float* U, const float* V, int64_t nU, int64_t nI, const
 static int bpr_step_impl(const float* U, const float* V, int64_t nU, int64_t nI, const int64_t* u, const int64_t* p,
                          const int64_t* n, int64_t B, int d, float grad_scale, float* pos, float* neg, float* loss_sum,
                          int32_t* auc_sum, float* gU, float* gV, float* item_rows, float* const* slices, int64_t slice_rows,
-                         void* stream) {
+                         float* auc_f, void* stream) {
   int rc = check_rows(U, V, nU, nI, d, "bpr_step");
   if (rc != DIVREC_OK) return rc;
   if (!u || !p || !n) return fail(DIVREC_ERR_ARG, "bpr_step: null index pointer");
@@ -455,7 +455,7 @@ static int bpr_step_impl(const float* U, const float* V, int64_t nU, int64_t nI,
     return DIVREC_OK;
   }
   cudaError_t e = launch_bpr_step(U, V, nU, nI, u, p, n, B, d, grad_scale, pos, neg, loss_sum, auc_sum, gU, gV, item_rows, slices,
-                                  slice_rows, st);
+                                  slice_rows, auc_f, st);
   if (e != cudaSuccess) return cuda_fail(e, "bpr_step launch");
   return DIVREC_OK;
 }
@@ -463,16 +463,16 @@ static int bpr_step_impl(const float* U, const float* V, int64_t nU, int64_t nI,
 int divrec_bpr_step(const float* U, const float* V, int64_t nU, int64_t nI, const int64_t* u, const int64_t* p, const int64_t* n,
                     int64_t B, int d, float grad_scale, float* pos, float* neg, float* loss_sum, int32_t* auc_sum, float* gU,
                     float* gV, float* item_rows, void* stream) {
-  return bpr_step_impl(U, V, nU, nI, u, p, n, B, d, grad_scale, pos, neg, loss_sum, auc_sum, gU, gV, item_rows, nullptr, 1, stream);
+  return bpr_step_impl(U, V, nU, nI, u, p, n, B, d, grad_scale, pos, neg, loss_sum, auc_sum, gU, gV, item_rows, nullptr, 1, nullptr, stream);
 }
 
 int divrec_bpr_step_owner(const float* U, const float* V, int64_t nU, int64_t nI, const int64_t* u, const int64_t* p,
-                          const int64_t* n, int64_t B, int d, float grad_scale, float* pos, float* neg, float* loss_sum,
-                          int32_t* auc_sum, float* gU, float* const* gV_slices, int n_slices, int64_t slice_rows, void* stream) {
+                          const int64_t* n, int64_t B, int d, float grad_scale, float* pos, float* neg, float* stats2,
+                          float* gU, float* const* gV_slices, int n_slices, int64_t slice_rows, void* stream) {
   if (!gV_slices || n_slices <= 0 || slice_rows <= 0) return fail(DIVREC_ERR_ARG, "bpr_step_owner: need the slice table, n_slices > 0 and slice_rows > 0");
   if ((int64_t)n_slices * slice_rows < nI) return fail(DIVREC_ERR_ARG, "bpr_step_owner: n_slices * slice_rows must cover nI");
-  return bpr_step_impl(U, V, nU, nI, u, p, n, B, d, grad_scale, pos, neg, loss_sum, auc_sum, gU, nullptr, nullptr, gV_slices, slice_rows,
-                       stream);
+  return bpr_step_impl(U, V, nU, nI, u, p, n, B, d, grad_scale, pos, neg, stats2, nullptr, gU, nullptr, nullptr, gV_slices, slice_rows,
+                       stats2 ? stats2 + 1 : nullptr, stream);
 }
 
 int divrec_bad_index_count(int64_t* host_out, int reset, void* stream) {

@@ -146,7 +146,7 @@ bpr_step_kernel(const float* __restrict__ U, const float* __restrict__ V, int64_
                 const int64_t* __restrict__ p, const int64_t* __restrict__ n, int64_t B, int d, float grad_scale,
                 float* __restrict__ pos, float* __restrict__ neg, float* __restrict__ loss_sum,
                 int32_t* __restrict__ auc_sum, float* __restrict__ gU, float* __restrict__ gV,
-                float* __restrict__ item_rows, float* const* __restrict__ slices, int64_t slice_rows) {
+                float* __restrict__ item_rows, float* const* __restrict__ slices, int64_t slice_rows, float* __restrict__ auc_f) {
   __shared__ float red_loss[8];
   __shared__ int red_auc[8];
   const uint32_t lane = lane_id();
@@ -215,6 +215,7 @@ bpr_step_kernel(const float* __restrict__ U, const float* __restrict__ V, int64_
     for (int i = 0; i < 8; ++i) { l += red_loss[i]; au += red_auc[i]; }
     if (loss_sum) atomicAdd(loss_sum, l);
     if (auc_sum) atomicAdd(auc_sum, au);
+    if (auc_f) atomicAdd(auc_f, (float)au);   // the same count as a float (exact below 2^24): one all-reduce carries loss and AUC
   }
 }
 
@@ -401,16 +402,16 @@ cudaError_t launch_bpr_bwd(const float* U, const float* V, int64_t nU, int64_t n
 cudaError_t launch_bpr_step(const float* U, const float* V, int64_t nU, int64_t nI, const int64_t* u, const int64_t* p,
                             const int64_t* n, int64_t B, int d, float grad_scale, float* pos, float* neg, float* loss_sum,
                             int32_t* auc_sum, float* gU, float* gV, float* item_rows, float* const* slices, int64_t slice_rows,
-                            cudaStream_t stream) {
+                            float* auc_f, cudaStream_t stream) {
   // every resident warp loops over several triples, so loads of the next triple overlap the scatter-adds of this one
   int64_t g = (B + 7) / 8;
   if (g > 148 * 8) g = 148 * 8;
 #define DIVREC_BPR_STEP(NV)                                                                                                        \
   do {                                                                                                                             \
     if (slices) bpr_step_kernel<NV, true><<<(unsigned)g, 256, 0, stream>>>(U, V, nU, nI, u, p, n, B, d, grad_scale, pos, neg,      \
-                                                                            loss_sum, auc_sum, gU, nullptr, item_rows, slices, slice_rows); \
+                                                                            loss_sum, auc_sum, gU, nullptr, item_rows, slices, slice_rows, auc_f); \
     else bpr_step_kernel<NV, false><<<(unsigned)g, 256, 0, stream>>>(U, V, nU, nI, u, p, n, B, d, grad_scale, pos, neg, loss_sum,  \
-                                                                     auc_sum, gU, gV, item_rows, nullptr, 1);                     \
+                                                                     auc_sum, gU, gV, item_rows, nullptr, 1, auc_f);              \
   } while (0)
   if (d <= 128) DIVREC_BPR_STEP(1);
   else if (d <= 256) DIVREC_BPR_STEP(2);

@@ -180,7 +180,7 @@ cudaError_t launch_bpr_bwd(const float* U, const float* V, int64_t nU, int64_t n
 cudaError_t launch_bpr_step(const float* U, const float* V, int64_t nU, int64_t nI, const int64_t* u, const int64_t* p,
                             const int64_t* n, int64_t B, int d, float grad_scale, float* pos, float* neg, float* loss_sum,
                             int32_t* auc_sum, float* gU, float* gV, float* item_rows, float* const* slices, int64_t slice_rows,
-                            cudaStream_t stream);
+                            float* auc_f, cudaStream_t stream);
 cudaError_t launch_bpr_sample(const int64_t* pos_rowptr, const int32_t* pos_items, const int64_t* excl_rowptr,
                               const int32_t* excl_items, int64_t nU, int64_t nI, int m, uint64_t seed, int64_t* out_u,
                               int64_t* out_p, int64_t* out_n, cudaStream_t stream);

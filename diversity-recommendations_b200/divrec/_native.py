@@ -47,7 +47,7 @@ SIGNATURES = {
     "divrec_bpr_fwd": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp]),
     "divrec_bpr_bwd": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _i64, _i32, _vp, _vp, _vp]),
     "divrec_bpr_step": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _i64, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "divrec_bpr_step_owner": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _i64, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _vp]),
+    "divrec_bpr_step_owner": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _i64, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _vp]),
     "divrec_bad_index_count": (_i32, [_c.POINTER(_c.c_int64), _i32, _vp]),
     "divrec_peer_alloc": (_i32, [_sz, _c.POINTER(_vp), _c.POINTER(_c.c_ubyte)]),
     "divrec_peer_open": (_i32, [_c.POINTER(_c.c_ubyte), _c.POINTER(_vp)]),
@@ -506,9 +506,9 @@ class PeerBuffer:
 
 
 def bpr_step_owner(U, V, u, p, n, grad_scale: float, gU: Optional[torch.Tensor], slices: torch.Tensor, slice_rows: int,
-                   loss_sum: Optional[torch.Tensor] = None, auc_sum: Optional[torch.Tensor] = None):
+                   stats2: torch.Tensor):
     """One-pass BPR step whose item-gradient updates go straight to the owning rank's slice (`slices`: int64 device tensor
-    of per-rank slice addresses, PeerBuffer.ptrs).  Returns (loss_sum [1], auc_sum [1])."""
+    of per-rank slice addresses, PeerBuffer.ptrs).  stats2 (float32 [2], caller-zeroed) += (loss sum, AUC hit count)."""
     lib = load_library()
     U = _cuda(U, "U", torch.float32)
     V = _cuda(V, "V", torch.float32)
@@ -516,16 +516,13 @@ def bpr_step_owner(U, V, u, p, n, grad_scale: float, gU: Optional[torch.Tensor],
     p = _cuda(p, "positive_item_id", torch.int64)
     n = _cuda(n, "negative_item_id", torch.int64)
     slices = _cuda(slices, "slices", torch.int64)
-    if loss_sum is None:
-        loss_sum = torch.zeros(1, dtype=torch.float32, device=U.device)
-    if auc_sum is None:
-        auc_sum = torch.zeros(1, dtype=torch.int32, device=U.device)
+    stats2 = _cuda(stats2, "stats2", torch.float32)
     with torch.cuda.device(U.device):
         rc = lib.divrec_bpr_step_owner(_ptr(U), _ptr(V), U.shape[0], V.shape[0], _ptr(u), _ptr(p), _ptr(n), u.numel(), U.shape[1],
-                                       float(grad_scale), None, None, _ptr(loss_sum), _ptr(auc_sum), _ptr(gU), _ptr(slices),
-                                       slices.numel(), int(slice_rows), _stream(U.device))
+                                       float(grad_scale), None, None, _ptr(stats2), _ptr(gU), _ptr(slices), slices.numel(),
+                                       int(slice_rows), _stream(U.device))
     _check(rc, "divrec_bpr_step_owner")
-    return loss_sum, auc_sum
+    return stats2
 
 
 def bpr_apply_rows(rows: torch.Tensor, p: torch.Tensor, n: torch.Tensor, gV: torch.Tensor) -> None:

@@ -118,9 +118,12 @@ class BprShardedState:
         self.U, self.V, self.world, self.rank, self.batch, self.route, self.group = U, V, world, rank, batch, route, group
         dev, (nI, d) = U.device, V.shape
         self.gU = torch.zeros_like(U)
-        self.loss_sum = torch.zeros(1, dtype=torch.float32, device=dev)
-        self.auc_sum = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.stat = torch.zeros(2, dtype=torch.float64, device=dev)
+        # step statistics.  owner route: ONE float pair (loss sum, AUC hits) -> one all-reduce; the others: the kernel's float
+        # loss and int32 AUC accumulators side by side in one 8-byte buffer (one fill kernel clears both)
+        self.stats2 = torch.zeros(2, dtype=torch.float32, device=dev)
+        self._acc = torch.zeros(2, dtype=torch.int32, device=dev)
+        self.loss_sum = self._acc[0:1].view(torch.float32)
+        self.auc_sum = self._acc[1:2]
         self.gV = self.peer = self.gV_slice = None
         self.slice_rows = -(-nI // world)
         if route == "owner":
@@ -156,17 +159,21 @@ class BprShardedState:
             self.peer = None
 
 
-def bpr_step_sharded(state: BprShardedState, u: torch.Tensor, p: torch.Tensor, n: torch.Tensor, grad_scale: float) -> torch.Tensor:
+def bpr_step_sharded(state: BprShardedState, u: torch.Tensor, p: torch.Tensor, n: torch.Tensor, grad_scale: float):
     """One BPR forward/backward on this rank's triples (its users only), gradients accumulated into the state's buffers.
-    grad_scale = 1 / global_batch for the GLOBAL mean loss.  Returns a device tensor [2] float64: (loss sum, AUC hit count)
+    grad_scale = 1 / global_batch for the GLOBAL mean loss.  Returns (loss_sum [1], auc_hits [1]) device tensors summed
     over ALL ranks' triples of this step (divide by the global batch for the means); no host synchronisation."""
     K = _kernels()
     st = state
-    st.loss_sum.zero_()
-    st.auc_sum.zero_()
     if st.route == "owner":
-        K.bpr_step_owner(st.U, st.V, u, p, n, grad_scale, st.gU, st.peer.ptrs, st.slice_rows, loss_sum=st.loss_sum, auc_sum=st.auc_sum)
-    elif st.route == "sparse":
+        st.stats2.zero_()
+        K.bpr_step_owner(st.U, st.V, u, p, n, grad_scale, st.gU, st.peer.ptrs, st.slice_rows, st.stats2)
+        # the step's one collective, and the barrier of the remote reductions: when it completes, every rank's step kernel
+        # -- and with it every update of this rank's slice -- has finished
+        dist.all_reduce(st.stats2, group=st.group)
+        return st.stats2[0:1], st.stats2[1:2]
+    st._acc.zero_()
+    if st.route == "sparse":
         K.bpr_step(st.U, st.V, u, p, n, grad_scale, st.gU, None, want_scores=False, loss_sum=st.loss_sum, auc_sum=st.auc_sum, item_rows=st.rows)
         st.ids[0].copy_(p); st.ids[1].copy_(n)
         dist.all_gather_into_tensor(st.all_rows, st.rows, group=st.group)
@@ -177,13 +184,10 @@ def bpr_step_sharded(state: BprShardedState, u: torch.Tensor, p: torch.Tensor, n
         K.bpr_step(st.U, st.V, u, p, n, grad_scale, st.gU, st.gV, want_scores=False, loss_sum=st.loss_sum, auc_sum=st.auc_sum)
         if st.route == "dense":
             dist.all_reduce(st.gV, group=st.group)
-    st.stat[0] = st.loss_sum[0]
-    st.stat[1] = st.auc_sum[0]
     if st.world > 1:
-        # also the barrier of the owner route: when it completes, every rank's step kernel -- and with it every remote
-        # reduction into this rank's slice -- has finished
-        dist.all_reduce(st.stat, group=st.group)
-    return st.stat
+        dist.all_reduce(st.loss_sum, group=st.group)
+        dist.all_reduce(st.auc_sum, group=st.group)
+    return st.loss_sum, st.auc_sum
 
 
 def bpr_step_once(U: torch.Tensor, V: torch.Tensor, u: torch.Tensor, p: torch.Tensor, n: torch.Tensor,
@@ -203,8 +207,8 @@ def bpr_step_once(U: torch.Tensor, V: torch.Tensor, u: torch.Tensor, p: torch.Te
         bmax, bmin = int(mm[0]), -int(mm[1])
         route = "sparse" if (bmax == bmin and world * B * (d + 4) * 4 <= V.shape[0] * d * 4) else "dense"
     state = BprShardedState(U, V, world, rank, B, route=route, group=group)
-    stat = bpr_step_sharded(state, u, p, n, 1.0 / global_batch)
-    loss, auc = (stat[0] / global_batch).to(torch.float32), (stat[1] / global_batch).to(torch.float32)
+    loss_sum, auc_hits = bpr_step_sharded(state, u, p, n, 1.0 / global_batch)
+    loss, auc = (loss_sum[0] / global_batch).to(torch.float32), (auc_hits[0].to(torch.float64) / global_batch).to(torch.float32)
     gV = state.gV_slice.clone() if route == "owner" else state.gV
     gU = state.gU
     state.close()

@@ -210,11 +210,13 @@ int divrec_bpr_step(const float* U, const float* V, int64_t nU, int64_t nI, cons
  *   is scattered straight to its owner with red.global.add.v4.f32 over NVLink, overlapped with the gathers of the
  *   following triples: no packing, no all-to-all, no second apply pass; after the ranks' kernels and ONE barrier
  *   every rank holds the globally summed gradient of the items it owns (reduce-scatter semantics; the dense
- *   replicated table of autograd is the concatenation of the slices).  d % 4 == 0, 16-byte aligned tables. */
+ *   replicated table of autograd is the concatenation of the slices).  d % 4 == 0, 16-byte aligned tables.
+ *   The two step statistics come out as ONE float pair so that a single all-reduce (which is also the barrier behind
+ *   the remote reductions) carries both. */
 int divrec_bpr_step_owner(const float* U, const float* V, int64_t nU, int64_t nI, const int64_t* u, const int64_t* p,
                           const int64_t* n, int64_t B, int d, float grad_scale, float* pos, float* neg,
-                          float* loss_sum, int32_t* auc_sum, float* gU, float* const* gV_slices, int n_slices,
-                          int64_t slice_rows, void* stream);
+                          float* stats2 /*[2] caller-zeroed: += loss sum, += AUC hit count (as float, exact below 2^24)*/,
+                          float* gU, float* const* gV_slices, int n_slices, int64_t slice_rows, void* stream);
 
 /* (host call, synchronises `stream`) triples / pairs skipped since the last reset because an id was out of range */
 int divrec_bad_index_count(int64_t* host_out /*host*/, int reset, void* stream);

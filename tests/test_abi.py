@@ -54,7 +54,7 @@ def test_version_and_errors_without_gpu(native):
     assert lib.divrec_ild_cosine(None, 10, 8, 0, None, 1, 4, 0, None, None, None) == -1
     assert lib.divrec_bpr_fwd(None, None, 10, 10, None, None, None, 4, 8, None, None, None, None, None) == -1
     assert lib.divrec_bpr_step(None, None, 10, 10, None, None, None, 4, 8, 0.25, None, None, None, None, None, None, None, None) == -1
-    assert lib.divrec_bpr_step_owner(None, None, 10, 10, None, None, None, 4, 8, 0.25, None, None, None, None, None, None, 2, 5, None) == -1
+    assert lib.divrec_bpr_step_owner(None, None, 10, 10, None, None, None, 4, 8, 0.25, None, None, None, None, None, 2, 5, None) == -1
     assert lib.divrec_bpr_apply_rows(None, None, None, 4, 10, 8, None, None) == -1
     assert lib.divrec_pair_scores(None, None, 10, 10, None, None, 4, 8, None, None) == -1
     assert lib.divrec_bad_index_count(None, 0, None) == -1

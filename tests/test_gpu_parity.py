@@ -872,13 +872,13 @@ def _owner_worker(rank, world, port, out):
     Ud, Vd = U.to(dev), V.to(dev)
     state = parallel.BprShardedState(Ud, Vd, world, rank, B, route="owner")
     for _ in range(2):  # gradients accumulate across steps
-        stat = parallel.bpr_step_sharded(state, us[rank].to(dev), ps[rank].to(dev), ns[rank].to(dev), 1.0 / (world * B))
+        loss_sum, auc_hits = parallel.bpr_step_sharded(state, us[rank].to(dev), ps[rank].to(dev), ns[rank].to(dev), 1.0 / (world * B))
     torch.cuda.synchronize()
     ua, pa, na = torch.cat(us), torch.cat(ps), torch.cat(ns)
     _, _, o_loss, o_auc = O.bpr_forward(U, V, ua, pa, na)
     o_gU, o_gV = O.bpr_backward(U, V, ua, pa, na)
     lo, hi = state.owned_range()
-    ok = abs(float(stat[0]) / (world * B) - float(o_loss)) <= 1e-5 * abs(float(o_loss))
+    ok = abs(float(loss_sum) / (world * B) - float(o_loss)) <= 1e-5 * abs(float(o_loss)) and abs(float(auc_hits) / (world * B) - float(o_auc)) <= 1e-6
     ok = ok and (state.gV_slice[:hi - lo].cpu() - 2 * o_gV[lo:hi]).abs().max().item() <= 1e-5 * 2 * float(o_gV.abs().max())
     ok = ok and (state.gU[a:b].cpu() - 2 * o_gU[a:b]).abs().max().item() <= 1e-5 * 2 * float(o_gU.abs().max())
     # and the dense all-reduce route gives the same item gradient
