@@ -476,7 +476,7 @@ score_filter2_kernel(const __grid_constant__ CUtensorMap tmap_b, const FilterPar
           v[0] = (v[0] | 0xffu) ^ (xlo ^ (uint32_t)g);  // gi0 is a multiple of 8: its low three bits take g
           v[1] = (v[1] | 0xffu) ^ xhi;
 #endif
-#ifdef DIVREC_DIAG_NOSTORE
+#if defined(DIVREC_DIAG_NOSTORE)
           asm volatile(
               "{\n"
               ".reg .pred p;\n"

@@ -23,6 +23,9 @@ __device__ __forceinline__ void tmem_st_x32(uint32_t taddr, const uint32_t* r) {
 }
 
 constexpr int K = 64;  // one 128-byte swizzle k-block
+#ifndef PROBE_N
+#define PROBE_N 128   // MMA N under test for the timing modes (-DPROBE_N=96: the three-column-split epilogue's tile)
+#endif
 // mode 0: TS correctness (out = A B^T); mode 1: time `iters` TS MMAs; mode 2: time SS MMAs
 __global__ void __launch_bounds__(192) probe(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                              const __half* A, float* out, int mode, int iters, long long* cyc) {
@@ -58,7 +61,7 @@ __global__ void __launch_bounds__(192) probe(const __grid_constant__ CUtensorMap
   if (warp == 5 && lane == 0) {
     mbar_wait(smem_u32(&full), 0);
     tc_fence_after();
-    const uint32_t idesc = umma_idesc_f16(0, 128, 128);
+    const uint32_t idesc = umma_idesc_f16(0, 128, mode == 0 ? 128 : PROBE_N);
     const uint64_t bdesc = umma_desc_sw128(smem_u32(sB));
     const uint64_t adesc = umma_desc_sw128(smem_u32(sA));
     const long long t0 = clock64();
@@ -151,7 +154,7 @@ int main() {
     e = cudaDeviceSynchronize();
     long long h[148]; cudaMemcpy(h, dC, sizeof(h), cudaMemcpyDeviceToHost);
     double c = 0; for (int i = 0; i < 148; ++i) c += h[i]; c /= 148;
-    if (mode < 6) printf("%s: %.1f cycles per M128xN128xK16 MMA (%s)\n", names[mode], c / (iters * 4.0), cudaGetErrorString(e));
+    if (mode < 6) printf("%s: %.1f cycles per M128xN%dxK16 MMA (%s)\n", names[mode], c / (iters * 4.0), PROBE_N, cudaGetErrorString(e));
     else { long long t[25]; cudaMemcpy(t, dC + 148, sizeof(t), cudaMemcpyDeviceToHost); printf("issue timestamps:"); for (int i = 0; i < 25; ++i) printf(" %lld", t[i]); printf("\n"); }
   }
   return 0;
