@@ -120,6 +120,69 @@ __device__ __noinline__ float ladder_decide(const FilterParams& p, int64_t row, 
   return cand;
 }
 
+// The MMA-issuing thread's loop.  It shares its scheduler partition with a quarter of the epilogue warps and gets an issue
+// slot every fifth cycle or so: at ~240 instructions per item tile (runtime k-block loop, 64-bit descriptor arithmetic,
+// statistics) the THREAD, not the tensor pipe, set the kernel's pace -- a trace of its clock showed 1 300 cycles per tile
+// with every operand long resident, against 1 024 cycles of MMA work (tools/filter_trace.py).  So: k-blocks at compile
+// time, descriptors advanced in their low word only (the address field cannot carry out), all of a tile's stages awaited
+// before the first MMA, nothing else in the loop.
+template <int KB>
+__device__ __forceinline__ void mma_issue_loop(Smem2* sm, const FilterParams& p, uint32_t tmem_base, uint32_t b_ring_addr,
+                                               int n_sched, int n_dblocks) {
+  const uint32_t idesc = umma_idesc_f16(p.fmt, BM, BN);
+  const uint64_t bdesc0 = umma_desc_sw128(b_ring_addr);
+  const uint32_t d_hi = (uint32_t)(bdesc0 >> 32), d_lo0 = (uint32_t)bdesc0;
+  const uint32_t bar_b_full = smem_u32(&sm->b_full[0]), bar_b_empty = smem_u32(&sm->b_empty[0]);
+  const uint32_t bar_acc_full = smem_u32(&sm->acc_full[0]), bar_acc_empty = smem_u32(&sm->acc_empty[0]);
+  const uint32_t bar_a_full = smem_u32(&sm->a_full), bar_a_empty = smem_u32(&sm->a_empty);
+  const uint32_t b_stages = (uint32_t)p.b_stages;
+  constexpr uint32_t A_COLS = KB * (BK / 2);
+  const uint32_t a0 = tmem_base + TMEM_COLS - A_COLS, a1 = tmem_base + TMEM_COLS - 2 * A_COLS;
+  uint32_t stage = 0, phase = 0, a_phase = 0, acc = 0, acc_phase = 0;
+  for (int db = blockIdx.x; db < n_dblocks; db += gridDim.x) {
+    mbar_wait(bar_a_full, a_phase);
+    a_phase ^= 1;
+    tc_fence_after();
+    for (int s = 0; s < n_sched; ++s) {
+      uint32_t st[KB];
+      // ---- user block 0: the tile's stages arrive together, all awaited before the first MMA ----
+      mbar_wait(bar_acc_empty + 8 * acc, acc_phase ^ 1);
+#pragma unroll
+      for (int kb = 0; kb < KB; ++kb) {
+        st[kb] = stage;
+        mbar_wait(bar_b_full + 8 * stage, phase);
+        if (++stage == b_stages) { stage = 0; phase ^= 1; }
+      }
+      tc_fence_after();
+#pragma unroll
+      for (int kb = 0; kb < KB; ++kb) {
+        const uint32_t lo = d_lo0 + st[kb] * (uint32_t)(SLAB_BYTES >> 4);
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4)
+          umma_f16_ts(tmem_base + acc * BN, a0 + (uint32_t)(kb * (BK / 2) + 8 * k4), ((uint64_t)d_hi << 32) | (uint64_t)(lo + 2u * k4),
+                      idesc, (uint32_t)((kb | k4) != 0));
+      }
+      umma_commit(bar_acc_full + 8 * acc);
+      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+      // ---- user block 1 against the same stages, which are released behind it ----
+      mbar_wait(bar_acc_empty + 8 * acc, acc_phase ^ 1);
+      tc_fence_after();
+#pragma unroll
+      for (int kb = 0; kb < KB; ++kb) {
+        const uint32_t lo = d_lo0 + st[kb] * (uint32_t)(SLAB_BYTES >> 4);
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4)
+          umma_f16_ts(tmem_base + acc * BN, a1 + (uint32_t)(kb * (BK / 2) + 8 * k4), ((uint64_t)d_hi << 32) | (uint64_t)(lo + 2u * k4),
+                      idesc, (uint32_t)((kb | k4) != 0));
+        umma_commit(bar_b_empty + 8 * st[kb]);
+      }
+      umma_commit(bar_acc_full + 8 * acc);
+      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+    }
+    umma_commit(bar_a_empty);
+  }
+}
+
 // Seen-item patterns of every row, one pass over the CSR (one warp per row, words assembled in shared memory):
 //   words [0, HS):           out[(2 s + h) * stride_rows + row] has bit c set when item (sample tile s, column 64 h + c)
 //                            is in the row's seen list (the hint phase leaves such sample groups out of its statistic);
@@ -211,57 +274,8 @@ score_filter2_kernel(const __grid_constant__ CUtensorMap tmap_b, const FilterPar
   } else if (warp == W_MMA) {
     // ================= MMA issuer =================
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_f16(p.fmt, BM, BN);
-      const uint64_t bdesc0 = umma_desc_sw128(smem_u32(b_ring));
-      const uint32_t bar_b_full = smem_u32(&sm->b_full[0]), bar_b_empty = smem_u32(&sm->b_empty[0]);
-      const uint32_t bar_acc_full = smem_u32(&sm->acc_full[0]), bar_acc_empty = smem_u32(&sm->acc_empty[0]);
-      uint32_t stage = 0, phase = 0, a_phase = 0, acc = 0, acc_phase = 0;
-      long long w_a = 0, w_acc = 0, w_b = 0;
-      const bool stats = p.stats != nullptr;
-      const long long t_begin = clock64();
-      for (int db = blockIdx.x; db < n_dblocks; db += gridDim.x) {
-        long long t0 = stats ? clock64() : 0;
-        mbar_wait(smem_u32(&sm->a_full), a_phase);
-        if (stats) w_a += clock64() - t0;
-        a_phase ^= 1;
-        tc_fence_after();
-        for (int s = 0; s < n_sched; ++s) {
-          const uint32_t stage0 = stage, phase0 = phase;
-#pragma unroll
-          for (int b = 0; b < NB; ++b) {
-            if (stats) t0 = clock64();
-            mbar_wait(bar_acc_empty + 8 * acc, acc_phase ^ 1);
-            if (stats) w_acc += clock64() - t0;
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + acc * BN;
-            uint32_t a_tmem = tmem_base + TMEM_COLS - (uint32_t)(b + 1) * a_cols;
-            stage = stage0;
-            phase = phase0;
-            for (int kb = 0; kb < kblocks; ++kb, a_tmem += BK / 2) {
-              if (b == 0) {
-                if (stats) t0 = clock64();
-                mbar_wait(bar_b_full + 8 * stage, phase);
-                if (stats) w_b += clock64() - t0;
-                tc_fence_after();
-              }
-              const uint64_t bdesc = bdesc0 + (uint64_t)(stage * (SLAB_BYTES >> 4));
-              umma_f16_ts(d_tmem, a_tmem, bdesc, idesc, (uint32_t)(kb != 0));
-              umma_f16_ts(d_tmem, a_tmem + 8, bdesc + 2, idesc, 1u);
-              umma_f16_ts(d_tmem, a_tmem + 16, bdesc + 4, idesc, 1u);
-              umma_f16_ts(d_tmem, a_tmem + 24, bdesc + 6, idesc, 1u);
-              if (b == NB - 1) umma_commit(bar_b_empty + 8 * stage);  // both user blocks have read this stage
-              if (++stage == (uint32_t)b_stages) { stage = 0; phase ^= 1; }
-            }
-            umma_commit(bar_acc_full + 8 * acc);
-            if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
-          }
-        }
-        umma_commit(smem_u32(&sm->a_empty));
-      }
-      if (stats) {
-        long long* o = p.stats + (size_t)blockIdx.x * 8;
-        o[0] = clock64() - t_begin; o[1] = w_a; o[2] = w_acc; o[3] = w_b;
-      }
+      if (kblocks == 2) mma_issue_loop<2>(sm, p, tmem_base, smem_u32(b_ring), n_sched, n_dblocks);
+      else mma_issue_loop<1>(sm, p, tmem_base, smem_u32(b_ring), n_sched, n_dblocks);
     }
   } else if (warp < EPI_WARPS * NB) {
     // ================= epilogue: set `bset` owns user block `bset` of the pair =================

@@ -8,10 +8,11 @@ dev = torch.device("cuda:0")
 g = torch.Generator().manual_seed(0)
 nU, nI, d, k = 138493, 26744, 128, 100
 U, V = O.make_embeddings(nU, d, "gauss", g).to(dev), O.make_embeddings(nI, d, "gauss", g).to(dev)
-lib = N.load_library()
+lib = N.load_library(os.path.join(ROOT, "diversity-recommendations_b200", sys.argv[1])) if len(sys.argv) > 1 else N.load_library()
+N._lib = lib  # (an experiment build named on the command line)
 N.set_profiling(True)
 out = {}
-for mode in (0, 1, 3):
+for mode in (0, 1):
     lib.divrec_debug_filter_mode(mode)
     ms = []
     for _ in range(6):
@@ -22,7 +23,7 @@ for mode in (0, 1, 3):
     print(mode, out[f"mode{mode}"], flush=True)
 lib.divrec_debug_filter_mode(0)
 buf = torch.zeros((148, 8), dtype=torch.int64, device=dev)
-for mode in (0, 1, 3):
+for mode in (0, 1):
     lib.divrec_debug_filter_mode(mode)
     lib.divrec_debug_filter_stats(buf.data_ptr())
     N.score_topk(U, V, k); torch.cuda.synchronize()

@@ -23,6 +23,12 @@ __device__ __forceinline__ void tmem_st_x32(uint32_t taddr, const uint32_t* r) {
 }
 
 constexpr int K = 64;  // one 128-byte swizzle k-block
+#ifndef PROBE_DBASE
+#define PROBE_DBASE 0
+#endif
+#ifndef PROBE_DSTRIDE
+#define PROBE_DSTRIDE 128   // column stride between the two accumulators the timing modes alternate
+#endif
 #ifndef PROBE_N
 #define PROBE_N 128   // MMA N under test for the timing modes (-DPROBE_N=96: the three-column-split epilogue's tile)
 #endif
@@ -70,26 +76,26 @@ __global__ void __launch_bounds__(192) probe(const __grid_constant__ CUtensorMap
     } else if (mode <= 2) {
       for (int it = 0; it < iters; ++it)
         for (int k4 = 0; k4 < K / 16; ++k4) {
-          if (mode == 1) umma_f16_ts(tb + (it & 1) * 128, tb + A_COL + 8 * k4, bdesc + 2 * k4, idesc, k4 != 0);
-          else umma_f16(tb + (it & 1) * 128, adesc + 2 * k4, bdesc + 2 * k4, idesc, k4 != 0);
+          if (mode == 1) umma_f16_ts(tb + (it & 1) * PROBE_DSTRIDE + PROBE_DBASE, tb + A_COL + 8 * k4, bdesc + 2 * k4, idesc, k4 != 0);
+          else umma_f16(tb + (it & 1) * PROBE_DSTRIDE + PROBE_DBASE, adesc + 2 * k4, bdesc + 2 * k4, idesc, k4 != 0);
         }
     } else if (mode == 3) {  // kernel-like: 4 MMAs, then a wait on an already-completed barrier + fence + commit
       for (int it = 0; it < iters; ++it) {
         mbar_wait(smem_u32(&full), 0); tc_fence_after();
-        for (int k4 = 0; k4 < 4; ++k4) umma_f16_ts(tb + (it & 1) * 128, tb + A_COL + 8 * k4, bdesc + 2 * k4, idesc, k4 != 0);
+        for (int k4 = 0; k4 < 4; ++k4) umma_f16_ts(tb + (it & 1) * PROBE_DSTRIDE + PROBE_DBASE, tb + A_COL + 8 * k4, bdesc + 2 * k4, idesc, k4 != 0);
         umma_commit(smem_u32(&scratch));
       }
     } else if (mode == 4) {  // 8 MMAs per two waits
       for (int it = 0; it < iters / 2; ++it) {
         mbar_wait(smem_u32(&full), 0); tc_fence_after(); mbar_wait(smem_u32(&full), 0); tc_fence_after();
-        for (int k4 = 0; k4 < 8; ++k4) umma_f16_ts(tb + (it & 1) * 128, tb + A_COL + 8 * (k4 & 3), bdesc + 2 * (k4 & 3), idesc, k4 != 0);
+        for (int k4 = 0; k4 < 8; ++k4) umma_f16_ts(tb + (it & 1) * PROBE_DSTRIDE + PROBE_DBASE, tb + A_COL + 8 * (k4 & 3), bdesc + 2 * (k4 & 3), idesc, k4 != 0);
         umma_commit(smem_u32(&scratch)); umma_commit(smem_u32(&scratch));
       }
     } else if (mode == 5) {  // 8 MMAs per two waits, the waits issued before the last 3 MMAs of the previous group
       for (int it = 0; it < iters / 2; ++it) {
-        for (int k4 = 0; k4 < 5; ++k4) umma_f16_ts(tb + (it & 1) * 128, tb + A_COL + 8 * (k4 & 3), bdesc + 2 * (k4 & 3), idesc, k4 != 0);
+        for (int k4 = 0; k4 < 5; ++k4) umma_f16_ts(tb + (it & 1) * PROBE_DSTRIDE + PROBE_DBASE, tb + A_COL + 8 * (k4 & 3), bdesc + 2 * (k4 & 3), idesc, k4 != 0);
         mbar_wait(smem_u32(&full), 0); mbar_wait(smem_u32(&full), 0);
-        for (int k4 = 5; k4 < 8; ++k4) umma_f16_ts(tb + (it & 1) * 128, tb + A_COL + 8 * (k4 & 3), bdesc + 2 * (k4 & 3), idesc, 1);
+        for (int k4 = 5; k4 < 8; ++k4) umma_f16_ts(tb + (it & 1) * PROBE_DSTRIDE + PROBE_DBASE, tb + A_COL + 8 * (k4 & 3), bdesc + 2 * (k4 & 3), idesc, 1);
         umma_commit(smem_u32(&scratch)); umma_commit(smem_u32(&scratch)); tc_fence_after();
       }
     } else if (mode == 6) {  // issue timestamps of 24 back-to-back MMAs
