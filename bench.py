@@ -140,6 +140,10 @@ class Ctx:
         self.world = int(os.environ.get("WORLD_SIZE", "1"))
         torch.cuda.set_device(self.local_rank)
         self.dev = torch.device("cuda", self.local_rank)
+        # host placement: this rank's pinned buffers and copy threads on the NUMA node of its GPU (e2e at N > 2 staged half of
+        # the ranks through the other socket); undone for the CPU-baseline leg, which should see every core
+        from divrec.parallel import bind_host_to_gpu
+        self.numa = bind_host_to_gpu(self.local_rank)
         self.dist = None
         if self.world > 1:
             import torch.distributed as dist
@@ -250,6 +254,11 @@ def bench_eval(ctx, args, workload):
     for _ in range(2):
         res = host_recommend_and_score(Uh, Vh, rph, ith, k, dev, chunks=args.e2e_chunks)
     e2e_ms, res = ctx.timed(lambda: host_recommend_and_score(Uh, Vh, rph, ith, k, dev, chunks=args.e2e_chunks), args.steps)
+    # the same call with 32-bit recommendation ids (an option of the API; the headline e2e keeps the reference's int64)
+    for _ in range(2):
+        host_recommend_and_score(Uh, Vh, rph, ith, k, dev, chunks=args.e2e_chunks, index_dtype=torch.int32)
+    e2e32_ms, res32 = ctx.timed(lambda: host_recommend_and_score(Uh, Vh, rph, ith, k, dev, chunks=args.e2e_chunks, index_dtype=torch.int32),
+                                max(3, args.steps // 2))
     e2e_value = nU * world / (e2e_ms * 1e-3)
     if rank != 0:
         return None
@@ -281,7 +290,12 @@ def bench_eval(ctx, args, workload):
     bound_ms = (flop / (pk["bf16_tflops"] * 1e12) + nU * (k * (8 + 4 * d) + 4) / (pk["hbm_gbs"] * 1e9) + nU * k * 8 / (pk["hbm_gbs"] * 1e9)) * 1e3
     roof_step = {"bound": "tensor + hbm (serial sum of S1, S2, S3)", "achieved": nU / (ms_per_step * 1e-3), "peak": nU / (bound_ms * 1e-3),
                  "unit": "users/s per GPU", "frac": bound_ms / ms_per_step, "bound_ms": bound_ms, "step_ms": ms_per_step}
-    cpu = cpu_baseline(workload, sample_users=args.cpu_sample, literal_users=args.cpu_literal_users) if world == 1 and not args.no_cpu else None
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        from divrec.parallel import bind_host_to_gpu, unbind_host
+        unbind_host(ctx.numa)  # the CPU leg may use every core of the box
+        cpu = cpu_baseline(workload, sample_users=args.cpu_sample, literal_users=args.cpu_literal_users)
+        ctx.numa = bind_host_to_gpu(ctx.local_rank)
     dominant = roof_select if s_ms >= f_ms else roof_filter
     return {
         "metric": METRIC, "value": value, "unit": "users/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
@@ -294,7 +308,9 @@ def bench_eval(ctx, args, workload):
                    "l2": "inputs + candidate workspace (>1 GB) exceed the 126 MB L2; no explicit flush"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "users/s", "h2d_bytes_per_step": res["h2d_bytes"], "d2h_bytes_per_step": res["d2h_bytes"],
-                "api": "divrec.train.host_recommend_and_score (pinned host buffers -> C ABI -> host results)"},
+                "api": "divrec.train.host_recommend_and_score (pinned host buffers -> C ABI -> host results)",
+                "host_numa_node": ctx.numa["node"], "host_cpus_bound": ctx.numa["cpus"],
+                "int32_ids": {"value": world * nU / (e2e32_ms * 1e-3), "d2h_bytes_per_step": res32["d2h_bytes"]}},
         "gpu_launches": int(launches),
         "roofline": dominant, "roofline_select": roof_select, "roofline_filter": roof_filter, "roofline_step": roof_step,
         "cpu_baseline": cpu, "phases_ms": med, "rescued_rows_per_step": stats["rescued_rows"],

@@ -15,6 +15,8 @@ a seam in the product.)
 """
 from typing import Optional, Tuple
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -213,3 +215,47 @@ def bpr_step_once(U: torch.Tensor, V: torch.Tensor, u: torch.Tensor, p: torch.Te
     gU = state.gU
     state.close()
     return loss, auc, gU, gV
+
+
+# ---- host placement ------------------------------------------------------------------------------
+def _parse_cpulist(text: str):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        a, _, b = part.partition("-")
+        cpus.update(range(int(a), int(b or a) + 1))
+    return cpus
+
+
+def bind_host_to_gpu(device_index: int, sysfs: str = "/sys") -> dict:
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off, so that pinned host buffers allocated afterwards
+    (first touch) and the copy-issuing threads are local to the GPU's PCIe root.  One process per GPU on an 8-GPU box
+    otherwise leaves half of the ranks staging their host<->device traffic through the other socket.  Returns
+    {"node", "cpus", "saved"}; node is None (and nothing is changed) when the topology cannot be read -- a container
+    without sysfs, one NUMA node, no CUDA device.  Undo with unbind_host(info)."""
+    info = {"node": None, "cpus": 0, "saved": None}
+    try:
+        pr = torch.cuda.get_device_properties(device_index)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        with open(os.path.join(sysfs, "bus/pci/devices", bdf, "numa_node")) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return info
+        with open(os.path.join(sysfs, "devices/system/node", "node%d" % node, "cpulist")) as f:
+            cpus = _parse_cpulist(f.read())
+        saved = os.sched_getaffinity(0)
+        cpus &= saved
+        if not cpus or cpus == saved:
+            return info
+        os.sched_setaffinity(0, cpus)
+        info.update(node=node, cpus=len(cpus), saved=saved)
+    except (OSError, ValueError, RuntimeError, AssertionError, AttributeError):
+        pass
+    return info
+
+
+def unbind_host(info: dict) -> None:
+    """Restore the CPU affinity bind_host_to_gpu() replaced (e.g. before a CPU leg that should use every core)."""
+    if info.get("saved"):
+        os.sched_setaffinity(0, info["saved"])

@@ -253,7 +253,7 @@ _host_pipe = {}
 
 def host_recommend_and_score(U_host: torch.Tensor, V_host: torch.Tensor, seen_rowptr_host: torch.Tensor,
                              seen_items_host: torch.Tensor, k: int, device, want_recommendations: bool = True,
-                             chunks: int = 4):
+                             chunks: int = 4, index_dtype: torch.dtype = torch.int64):
     """The whole evaluation pass from HOST buffers: copy the embedding tables and the seen-item CSR to the
     device, run score + mask + top-k with the cosine ILD and the coverage histogram fused, and bring the
     results back to pinned host memory.  Equivalent of recommendations_score_loop(RankingDataset(test,
@@ -263,12 +263,18 @@ def host_recommend_and_score(U_host: torch.Tensor, V_host: torch.Tensor, seen_ro
     Users are processed in `chunks` contiguous ranges on three streams -- host->device copies of the next
     range, kernels of the current one, device->host copies of the previous one -- so the PCIe transfers hide
     behind the kernels.  Pass pinned tensors (pageable memory makes the copies synchronous).
+    index_dtype=torch.int32 brings the [U,k] recommendations back as 32-bit ids (narrowed on the device): the int64 table
+    the reference API returns is 40 % of the pass's PCIe traffic, and the link is what bounds this call.
     Returns a dict with host tensors and the bytes moved."""
     import math
     dev = torch.device(device)
     nU, d = U_host.shape
     nI = V_host.shape[0]
-    key = (dev.index, nU, nI, d, k, seen_items_host.numel(), chunks)
+    if index_dtype not in (torch.int64, torch.int32):
+        raise ValueError("index_dtype must be torch.int64 or torch.int32")
+    if index_dtype == torch.int32 and nI >= 2 ** 31:
+        raise ValueError("index_dtype=torch.int32 needs fewer than 2^31 items")
+    key = (dev.index, nU, nI, d, k, seen_items_host.numel(), chunks, index_dtype)
     st = _host_pipe.get(key)
     if st is None:
         wave = 148 * 128  # users scored by one wave of the persistent filter kernel
@@ -281,7 +287,8 @@ def host_recommend_and_score(U_host: torch.Tensor, V_host: torch.Tensor, seen_ro
             "recs": torch.empty((nU, k), dtype=torch.int64, device=dev),
             "scores": torch.empty((nU, k), dtype=torch.float32, device=dev),
             "ild": torch.empty(nU, dtype=torch.float32, device=dev),
-            "recs_h": torch.empty((nU, k), dtype=torch.int64).pin_memory(),
+            "recs_h": torch.empty((nU, k), dtype=index_dtype).pin_memory(),
+            "recs_n": torch.empty((nU, k), dtype=index_dtype, device=dev) if index_dtype != torch.int64 else None,
             "ild_h": torch.empty(nU, dtype=torch.float32).pin_memory(),
             "counts_h": torch.empty(nI, dtype=torch.int32).pin_memory(),
             "ent_h": torch.empty(2, dtype=torch.float32).pin_memory(),
@@ -329,8 +336,12 @@ def host_recommend_and_score(U_host: torch.Tensor, V_host: torch.Tensor, seen_ro
         with torch.cuda.stream(s_out):
             s_out.wait_event(done)
             if want_recommendations:
-                st["recs_h"][a:b].copy_(st["recs"][a:b], non_blocking=True)
-                d2h += (b - a) * k * 8
+                src = st["recs"]
+                if st["recs_n"] is not None:  # narrow on the device (on the copy stream, behind the kernels)
+                    st["recs_n"][a:b].copy_(st["recs"][a:b])
+                    src = st["recs_n"]
+                st["recs_h"][a:b].copy_(src[a:b], non_blocking=True)
+                d2h += (b - a) * k * src.element_size()
             st["ild_h"][a:b].copy_(st["ild"][a:b], non_blocking=True)
             d2h += (b - a) * 4
     ent = _native.entropy_from_counts(st["counts"])

@@ -663,6 +663,11 @@ def test_host_buffer_pipeline_equals_resident_path(native, dev):
         assert res["entropy_diversity"] == pytest.approx(float(O.entropy_diversity(i.cpu(), nI)), rel=1e-5)
         assert res["h2d_bytes"] == U.numel() * 4 + V.numel() * 4 + rowptr.numel() * 8 + items.numel() * 4
         assert res["d2h_bytes"] == nU * k * 8 + nU * 4 + nI * 4 + 8
+    # 32-bit recommendation ids: the same lists, narrowed on the device, half of the table's bytes over the link
+    res = host_recommend_and_score(U.pin_memory(), V.pin_memory(), rowptr.pin_memory(), items.pin_memory(), k, dev, chunks=3,
+                                   index_dtype=torch.int32)
+    assert res["recommendations"].dtype == torch.int32 and torch.equal(res["recommendations"].long(), i.cpu())
+    assert res["d2h_bytes"] == nU * k * 4 + nU * 4 + nI * 4 + 8
 
 
 def test_relevance_metrics_vs_reference_formulas(native, dev):

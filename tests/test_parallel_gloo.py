@@ -187,3 +187,31 @@ def test_shard_range_covers_everything():
             assert all(edges[i][1] == edges[i + 1][0] for i in range(w - 1))
             sizes = [b - a for a, b in edges]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_bind_host_to_gpu_is_harmless_without_topology(tmp_path, monkeypatch):
+    """bind_host_to_gpu: no CUDA device / no sysfs / one NUMA node -> nothing changes; with a (faked) two-node topology the
+    process is pinned to the GPU's node and unbind_host restores the previous affinity."""
+    import os
+    from types import SimpleNamespace
+    from divrec import parallel
+    before = os.sched_getaffinity(0)
+    info = parallel.bind_host_to_gpu(0, sysfs=str(tmp_path))
+    assert info["node"] is None and os.sched_getaffinity(0) == before
+    assert parallel._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    if len(before) < 2:
+        return
+    cpus = sorted(before)
+    half = cpus[: len(cpus) // 2]
+    monkeypatch.setattr(parallel.torch.cuda, "get_device_properties",
+                        lambda i: SimpleNamespace(pci_domain_id=0, pci_bus_id=0x1b, pci_device_id=0))
+    d = tmp_path / "bus/pci/devices/0000:1b:00.0"; d.mkdir(parents=True)
+    (d / "numa_node").write_text("1\n")
+    n = tmp_path / "devices/system/node/node1"; n.mkdir(parents=True)
+    (n / "cpulist").write_text(",".join(str(c) for c in half) + "\n")
+    try:
+        info = parallel.bind_host_to_gpu(0, sysfs=str(tmp_path))
+        assert info["node"] == 1 and info["cpus"] == len(half) and os.sched_getaffinity(0) == set(half)
+    finally:
+        parallel.unbind_host(info)
+    assert os.sched_getaffinity(0) == before
