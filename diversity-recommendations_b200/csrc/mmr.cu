@@ -388,7 +388,6 @@ __device__ __forceinline__ float warp_sum4(const float (&part)[4], uint32_t lane
   return v;
 }
 __device__ __forceinline__ int sum4_group(uint32_t lane) { return (int)(((lane >> 4) & 1u) | (((lane >> 3) & 1u) << 1)); }
-__device__ __forceinline__ int sum4_lane_of(int q) { return ((q & 1) << 4) | ((q >> 1) << 3); }
 
 // per-warp shared memory: candidate state [Cp] x (score, max cosine so far, item id, picks seen as u16) + the pick list
 // (14 bytes per candidate: the state is what bounds the users in flight per SM, and the kernel is latency-bound)
