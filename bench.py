@@ -102,6 +102,11 @@ class ClockSampler:
                                        "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
+        # nvidia-smi's start-up (NVML initialisation, tens to hundreds of ms on a fresh box) stalls kernel launches: wait for
+        # its first sample before the timed region begins, so that only the periodic queries fall inside it
+        t0 = time.time()
+        while self.p is not None and self.p.poll() is None and os.path.getsize(self.f.name) == 0 and time.time() - t0 < 10.0:
+            time.sleep(0.05)
         return self
 
     def stop(self):
