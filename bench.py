@@ -84,26 +84,67 @@ def make_inputs(name, seed):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and clock-event (throttle) reasons DURING the timed region: the B200_PROFILING.md clocks line, read through
+    NVML in-process (nvidia_ml_py, the library nvidia-smi itself calls) every 50 ms.  A looping `nvidia-smi --query-gpu`
+    process was measured to stall kernel launches: its start-up cost 250 ms inside a 4-step region, and on an 8-GPU box
+    one periodic query inside the region took the cfg2 step from 3.0 to 7.3 ms -- through the per-step all-reduce, on
+    every rank.  nvidia-smi remains the fallback when the NVML binding is missing."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index, active=True):
+    def __init__(self, gpu_index, active=True, period=0.05):
         self.gpu = gpu_index
         self.active = active
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False) if active else None
+        self.period = period
+        self.f = None
         self.p = None
+        self.thread = None
+        self.stop_flag = False
+        self.sm, self.mx, self.reasons = [], [], set()
+        self.source = None
+
+    def _nvml_loop(self, nv, h):
+        bits = []
+        for name, attr in (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown"), ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown"),
+                           ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown"), ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap")):
+            if hasattr(nv, attr):
+                bits.append((name, getattr(nv, attr)))
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                r = get_reasons(h)
+                for name, bit in bits:
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
 
     def start(self):
         if not self.active:
             return self
         try:
+            import pynvml as nv
+            import threading
+            nv.nvmlInit()
+            pr = torch.cuda.get_device_properties(self.gpu)  # NVML counts physical devices: find ours by its bus id
+            h = nv.nvmlDeviceGetHandleByPciBusId(("%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)).encode())
+            self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)))
+            self.source = "nvml"
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
+            self.thread.start()
+            return self
+        except Exception:
+            self.source = None
+        try:
+            self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "200"], stdout=self.f, stderr=subprocess.DEVNULL)
+            self.source = "nvidia-smi"
         except OSError:
             self.p = None
-        # nvidia-smi's start-up (NVML initialisation, tens to hundreds of ms on a fresh box) stalls kernel launches: wait for
-        # its first sample before the timed region begins, so that only the periodic queries fall inside it
+        # nvidia-smi's start-up (NVML initialisation) stalls kernel launches: wait for its first sample before timing
         t0 = time.time()
         while self.p is not None and self.p.poll() is None and os.path.getsize(self.f.name) == 0 and time.time() - t0 < 10.0:
             time.sleep(0.05)
@@ -112,28 +153,32 @@ class ClockSampler:
     def stop(self):
         if not self.active:
             return None
-        if self.p is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.p.terminate()
-        self.p.wait()
-        self.f.flush()
-        rows = [r.strip().split(", ") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
-        os.unlink(self.f.name)
-        sm, mx, reasons = [], [], set()
-        for r in rows:
-            try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
-            except (ValueError, IndexError):
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                if v.strip().lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
+        if self.thread is not None:
+            time.sleep(2 * self.period)
+            self.stop_flag = True
+            self.thread.join(timeout=1.0)
+        elif self.p is not None:
+            time.sleep(0.25)
+            self.p.terminate()
+            self.p.wait()
+            self.f.flush()
+            rows = [r.strip().split(", ") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+            os.unlink(self.f.name)
+            for r in rows:
+                try:
+                    self.sm.append(float(r[1])); self.mx.append(float(r[2]))
+                except (ValueError, IndexError):
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(name)
+        else:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML binding and no nvidia-smi"]}
+        sm = sorted(self.sm)
         # "under load": the upper half of the samples (idle samples before/after the region pull the median down)
         load = sm[len(sm) // 2:] if sm else []
-        return {"sm_mhz": load[len(load) // 2] if load else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": load[len(load) // 2] if load else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                "reasons": sorted(self.reasons), "samples": len(sm), "source": self.source}
 
 
 class Ctx:
