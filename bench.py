@@ -590,7 +590,8 @@ def bench_cfg5(ctx, args, steps, warmup):
                     "d2h_bytes_per_step": nU * k * 8, "api": "divrec.rerank.mmr_rerank (candidates from pinned host memory)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": None,
-                         "kernel": "mmr_kernel", "kernel_ms": ms_per_step, "algorithmic_bytes_per_launch": algo,
+                         "kernel": "mmr_warp_kernel", "kernel_ms": ms_per_step, "algorithmic_bytes_per_launch": algo,
+                         "traffic_note": "profiles/r02_ncu_mmr_warp.txt holds a full capture of a smaller launch (not per-launch comparable)",
                          "note": "lazy greedy: only candidates whose upper bound can still win are gathered and evaluated, so the kernel "
                                  "moves fewer bytes than the algorithmic figure; the rest is per-pick latency"},
             "cpu_baseline": None}
