@@ -1,4 +1,5 @@
-"""Timestamps of the MMA-issuing thread over 64 consecutive tiles (diagnostic build: -DDIVREC_DIAG_TRACE).
+"""Timestamps of the MMA-issuing thread over 64 consecutive tiles.  Needs a diagnostic build of score_filter2.cu with the TRACE
+hooks of the round-2 investigation (git history: the commit that introduced this tool); the release kernel has none.
 usage: python tools/filter_trace.py libdivrec_b200.t.so [mode]"""
 import os, sys, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
