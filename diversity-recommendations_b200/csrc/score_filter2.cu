@@ -89,22 +89,21 @@ __device__ __forceinline__ int sched_tile(int s, int n_sample, int stride) {
 // whose maximum reached level j; P(block max >= t) = q  <=>  per-item tail p = -log(1 - q) / 64; the count is taken
 // at a 2.5 sigma lower confidence bound of q, plus one sigma of the part of the catalogue still to come.
 // Returns -inf when no level qualifies.  Both threads of a row evaluate this on the same numbers.
-__device__ __noinline__ float ladder_decide(const FilterParams& p, int64_t row, float4 l4, uint32_t s01, uint32_t s23, float nc,
-                                            float frac) {
-  int64_t seen_u = 0;
-  if (p.seen_rowptr != nullptr) seen_u = p.seen_rowptr[row + 1] - p.seen_rowptr[row];
-  const float n_un = fmaxf(1.0f, (float)((int64_t)p.nI - seen_u));
-  const float need = (float)p.k + (float)max(16, p.k >> 2);
-  const float req = need + sqrtf(need * (1.0f - frac));
+__device__ __noinline__ float ladder_decide(float n_un, float need, float4 l4, uint32_t s01, uint32_t s23, float nc, float frac) {
+  // (a checkpoint used to cost ~9 500 cycles against ~2 000 for a tile -- 11 % of the kernel over the seven of a pass: two
+  // dependent global loads of the row's seen count, IEEE divisions, log1pf; the count now comes from shared memory and the
+  // arithmetic uses the fast intrinsics -- the result only steers a threshold whose safety is checked by the select kernel)
+  const float req = need + __fsqrt_rn(need * (1.0f - frac));
   const float cj[4] = {(float)(s01 & 0xffffu), (float)(s01 >> 16), (float)(s23 & 0xffffu), (float)(s23 >> 16)};
   const float lj[4] = {l4.x, l4.y, l4.z, l4.w};
+  const float inv_nc = __fdividef(1.0f, nc);
   float nlo[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const float qh = cj[j] / nc;
-    const float se = sqrtf(fmaxf(qh * (1.0f - qh), 1e-9f) / nc);
+    const float qh = cj[j] * inv_nc;
+    const float se = __fsqrt_rn(fmaxf(qh * (1.0f - qh), 1e-9f) * inv_nc);
     const float qlo = fminf(fmaxf(qh - DIVREC_Z_CP * se, 1e-6f), 0.999f);
-    nlo[j] = -log1pf(-qlo) * (1.0f / 64.0f) * n_un;  // items above level j, lower confidence bound
+    nlo[j] = -__logf(1.0f - qlo) * (1.0f / 64.0f) * n_un;  // items above level j, lower confidence bound
   }
   float cand = -INFINITY;
 #pragma unroll
@@ -112,7 +111,7 @@ __device__ __noinline__ float ladder_decide(const FilterParams& p, int64_t row, 
     if (cand == -INFINITY && lj[j] < 3.0e38f && nlo[j] >= req) {
       cand = lj[j];
       if (j < 3 && lj[j + 1] < 3.0e38f && lj[j + 1] > lj[j] && nlo[j + 1] < req && nlo[j + 1] > 0.0f) {
-        const float wgt = (__logf(nlo[j]) - __logf(req)) / fmaxf(__logf(nlo[j]) - __logf(nlo[j + 1]), 1e-6f);
+        const float wgt = __fdividef(__logf(nlo[j]) - __logf(req), fmaxf(__logf(nlo[j]) - __logf(nlo[j + 1]), 1e-6f));
         cand += (lj[j + 1] - lj[j]) * fminf(fmaxf(wgt, 0.0f), 1.0f);
       }
     }
@@ -145,6 +144,9 @@ __device__ __forceinline__ void mma_issue_loop(Smem2* sm, const FilterParams& p,
     tc_fence_after();
     for (int s = 0; s < n_sched; ++s) {
       uint32_t st[KB];
+#ifdef DIVREC_DIAG_TRACE2
+      if (p.stats != nullptr && blockIdx.x == 0) p.stats[148 * 8 + ((db - (int)blockIdx.x) / (int)gridDim.x) * 256 + s] = clock64();
+#endif
       // ---- user block 0: the tile's stages arrive together, all awaited before the first MMA ----
       mbar_wait(bar_acc_empty + 8 * acc, acc_phase ^ 1);
 #pragma unroll
@@ -430,6 +432,13 @@ score_filter2_kernel(const __grid_constant__ CUtensorMap tmap_b, const FilterPar
       // block's hint phase; both threads of a row write the same values)
       float4* const lv_s = reinterpret_cast<float4*>(&sm->sorted[bset][8][0]);
       lv_s[row_local] = lv;
+      // the row's unmasked item count for the ladder's projections (row 10 of the same area; both threads of a row write it)
+      float* const nun_s = &sm->sorted[bset][10][0];
+      {
+        int64_t seen_u = 0;
+        if (valid_row && p.seen_rowptr != nullptr) seen_u = p.seen_rowptr[row + 1] - p.seen_rowptr[row];
+        nun_s[row_local] = fmaxf(1.0f, (float)((int64_t)p.nI - seen_u));
+      }
 
       // ---- phase 2: group filter over every tile of this set's block ----
       // The epilogue is instruction-bound (16 warps share the SM's issue slots with nothing to hide behind), so an append
@@ -447,6 +456,7 @@ score_filter2_kernel(const __grid_constant__ CUtensorMap tmap_b, const FilterPar
           ? reinterpret_cast<const uint32_t*>(p.hint_mask + (size_t)(HS + h * p.mask_words) * (size_t)p.hint_mask_stride + row)
           : nullptr;
       const bool ladder = p.ladder_stride > 0;
+      const float inv_tiles = 1.0f / (float)p.n_tiles;
       int next_cp = ladder ? p.ladder_stride : 0x7fffffff;
       uint32_t* const exch = reinterpret_cast<uint32_t*>(&sm->sorted[bset][0][0]);  // checkpoint exchange: rows 0..5 of `sorted`
       for (int t = 0; t < p.n_tiles; ++t) {
@@ -541,7 +551,8 @@ score_filter2_kernel(const __grid_constant__ CUtensorMap tmap_b, const FilterPar
               const int pe = et ^ 128;  // the row's other column half
               const uint32_t s01 = c01 + exch[(slot + 0) * EPI_THREADS + pe], s23 = c23 + exch[(slot + 1) * EPI_THREADS + pe];
               const float nc = (float)(ncl + exch[(slot + 2) * EPI_THREADS + pe]);
-              if (valid_row && nc >= 16.0f) thr = fmaxf(thr, ladder_decide(p, row, l4, s01, s23, nc, (float)(t + 1) / (float)p.n_tiles));
+              if (valid_row && nc >= 16.0f)
+                thr = fmaxf(thr, ladder_decide(nun_s[row_local], (float)p.k + (float)max(16, p.k >> 2), l4, s01, s23, nc, (float)(t + 1) * inv_tiles));
             }
           }
         }
