@@ -195,6 +195,53 @@ __device__ __forceinline__ int sched_tile(int s, int n_sample, int stride) {
 
 // TIGHTEN: large catalogues only (the out-of-line tightening call costs the hot loop ~15 % in register shuffling,
 // and below ~500k items the sampled hint keeps the lists short anyway).
+// The MMA-issuing thread's loop, one instantiation per k-block count (see score_filter2.cu: the thread shares its scheduler
+// partition with a quarter of the epilogue warps, so its instruction count per tile is what has to be small): k-blocks at
+// compile time, descriptors advanced in their low word only, all of a tile's stages awaited before its first MMA.
+template <int KB>
+__device__ __forceinline__ void mma_issue_loop1(Smem* sm, const FilterParams& p, uint32_t tmem_base, uint32_t b_ring_addr,
+                                                int n_sched) {
+  const uint32_t idesc = umma_idesc_f16(p.fmt, BM, BN);
+  const uint64_t bdesc0 = umma_desc_sw128(b_ring_addr);
+  const uint32_t d_hi = (uint32_t)(bdesc0 >> 32), d_lo0 = (uint32_t)bdesc0;
+  const uint32_t bar_b_full = smem_u32(&sm->b_full[0]), bar_b_empty = smem_u32(&sm->b_empty[0]);
+  const uint32_t bar_acc_full = smem_u32(&sm->acc_full[0]), bar_acc_empty = smem_u32(&sm->acc_empty[0]);
+  const uint32_t bar_a_full = smem_u32(&sm->a_full), bar_a_empty = smem_u32(&sm->a_empty);
+  const uint32_t b_stages = (uint32_t)p.b_stages, acc_stages = (uint32_t)p.acc_stages;
+  const uint32_t a_op = tmem_base + TMEM_COLS - KB * (BK / 2);
+  uint32_t stage = 0, phase = 0, a_phase = 0, acc = 0, acc_phase = 0;
+  for (int ub = blockIdx.x; ub < p.n_ublocks; ub += gridDim.x) {
+    mbar_wait(bar_a_full, a_phase);  // the block's A operand has been written to TMEM
+    a_phase ^= 1;
+    tc_fence_after();
+    for (int s = 0; s < n_sched; ++s) {
+      uint32_t st[KB];
+      mbar_wait(bar_acc_empty + 8 * acc, acc_phase ^ 1);
+#pragma unroll
+      for (int kb = 0; kb < KB; ++kb) {
+        st[kb] = stage;
+        mbar_wait(bar_b_full + 8 * stage, phase);
+        if (++stage == b_stages) { stage = 0; phase ^= 1; }
+      }
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+#pragma unroll
+      for (int kb = 0; kb < KB; ++kb) {
+        const uint32_t lo = d_lo0 + st[kb] * (uint32_t)(SLAB_BYTES >> 4);
+        // B: +32 bytes (16 x 2 B) inside the 128-byte swizzle row = +2 in 16-byte units; A: 16 elements = 8 TMEM columns
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4)
+          umma_f16_ts(d_tmem, a_op + (uint32_t)(kb * (BK / 2) + 8 * k4), ((uint64_t)d_hi << 32) | (uint64_t)(lo + 2u * k4), idesc,
+                      (uint32_t)((kb | k4) != 0));
+        umma_commit(bar_b_empty + 8 * st[kb]);
+      }
+      umma_commit(bar_acc_full + 8 * acc);
+      if (++acc == acc_stages) { acc = 0; acc_phase ^= 1; }
+    }
+    umma_commit(bar_a_empty);  // every MMA that reads this block's A has completed
+  }
+}
+
 template <bool TIGHTEN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 score_filter_kernel(const __grid_constant__ CUtensorMap tmap_b, const FilterParams p) {
@@ -250,53 +297,16 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmap_b, const FilterPara
   } else if (warp == W_MMA) {
     // ================= MMA issuer =================
     if (lane == 0) {
-      // One thread feeds the tensor core, so this loop is kept to a handful of instructions per MMA: running
-      // counters instead of divisions, the shared-memory descriptor advanced by adding the stage offset (measured:
-      // the unoptimised loop, not the tensor pipe, set the pace at ~110 cycles per instruction against 73).
-      const uint32_t idesc = umma_idesc_f16(p.fmt, BM, BN);
-      const uint64_t bdesc0 = umma_desc_sw128(smem_u32(b_ring));
-      const uint32_t bar_b_full = smem_u32(&sm->b_full[0]), bar_b_empty = smem_u32(&sm->b_empty[0]);
-      const uint32_t bar_acc_full = smem_u32(&sm->acc_full[0]), bar_acc_empty = smem_u32(&sm->acc_empty[0]);
-      const uint32_t a_tmem0 = tmem_base + a_col;
-      uint32_t stage = 0, phase = 0, a_phase = 0, acc = 0, acc_phase = 0;
-      long long w_a = 0, w_acc = 0, w_b = 0;  // cycles this thread spent blocked on each dependency (p.stats)
-      const bool stats = p.stats != nullptr;
-      const long long t_begin = clock64();
-      for (int ub = blockIdx.x; ub < p.n_ublocks; ub += gridDim.x) {
-        long long t0 = stats ? clock64() : 0;
-        mbar_wait(smem_u32(&sm->a_full), a_phase);  // the block's A operand has been written to TMEM
-        if (stats) w_a += clock64() - t0;
-        a_phase ^= 1;
-        tc_fence_after();
-        for (int s = 0; s < n_sched; ++s) {
-          if (stats) t0 = clock64();
-          mbar_wait(bar_acc_empty + 8 * acc, acc_phase ^ 1);
-          if (stats) w_acc += clock64() - t0;
-          tc_fence_after();
-          const uint32_t d_tmem = tmem_base + acc * BN;
-          uint32_t a_tmem = a_tmem0;
-          for (int kb = 0; kb < kblocks; ++kb, a_tmem += BK / 2) {
-            if (stats) t0 = clock64();
-            mbar_wait(bar_b_full + 8 * stage, phase);
-            if (stats) w_b += clock64() - t0;
-            tc_fence_after();
-            const uint64_t bdesc = bdesc0 + (uint64_t)(stage * (SLAB_BYTES >> 4));
-            // B: +32 bytes (16 x 2 B) inside the 128-byte swizzle row = +2 in 16-byte units; A: 16 elements = 8 TMEM columns
-            umma_f16_ts(d_tmem, a_tmem, bdesc, idesc, (uint32_t)(kb != 0));
-            umma_f16_ts(d_tmem, a_tmem + 8, bdesc + 2, idesc, 1u);
-            umma_f16_ts(d_tmem, a_tmem + 16, bdesc + 4, idesc, 1u);
-            umma_f16_ts(d_tmem, a_tmem + 24, bdesc + 6, idesc, 1u);
-            umma_commit(bar_b_empty + 8 * stage);
-            if (++stage == (uint32_t)b_stages) { stage = 0; phase ^= 1; }
-          }
-          umma_commit(bar_acc_full + 8 * acc);
-          if (++acc == acc_stages) { acc = 0; acc_phase ^= 1; }
-        }
-        umma_commit(smem_u32(&sm->a_empty));  // every MMA that reads this block's A has completed
-      }
-      if (stats) {
-        long long* o = p.stats + (size_t)blockIdx.x * 8;
-        o[0] = clock64() - t_begin; o[1] = w_a; o[2] = w_acc; o[3] = w_b;
+      const uint32_t ring = smem_u32(b_ring);
+      switch (kblocks) {
+        case 1: mma_issue_loop1<1>(sm, p, tmem_base, ring, n_sched); break;
+        case 2: mma_issue_loop1<2>(sm, p, tmem_base, ring, n_sched); break;
+        case 3: mma_issue_loop1<3>(sm, p, tmem_base, ring, n_sched); break;
+        case 4: mma_issue_loop1<4>(sm, p, tmem_base, ring, n_sched); break;
+        case 5: mma_issue_loop1<5>(sm, p, tmem_base, ring, n_sched); break;
+        case 6: mma_issue_loop1<6>(sm, p, tmem_base, ring, n_sched); break;
+        case 7: mma_issue_loop1<7>(sm, p, tmem_base, ring, n_sched); break;
+        default: mma_issue_loop1<8>(sm, p, tmem_base, ring, n_sched); break;
       }
     }
   } else if (warp < EPI_WARPS * EPI_SETS) {
