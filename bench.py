@@ -131,6 +131,9 @@ class ClockSampler:
             pr = torch.cuda.get_device_properties(self.gpu)  # NVML counts physical devices: find ours by its bus id
             h = nv.nvmlDeviceGetHandleByPciBusId(("%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)).encode())
             self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)))
+            # first calls of the two queries here, outside the timed region (NVML initialises lazily per query type)
+            nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+            (getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons)(h)
             self.source = "nvml"
             self.thread = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
             self.thread.start()
