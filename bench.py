@@ -94,7 +94,7 @@ class ClockSampler:
 
     def __init__(self, gpu_index, active=True, period=0.05):
         self.gpu = gpu_index
-        self.active = active
+        self.active = active and not os.environ.get("DIVREC_BENCH_NO_CLOCKS")  # (diagnostic switch: is a stall the sampler's?)
         self.period = period
         self.f = None
         self.p = None
@@ -220,13 +220,18 @@ class Ctx:
     def timed(self, fn, steps):
         """barrier + sync, exactly `steps` calls between two CUDA events on the current stream, barrier + sync; max over ranks."""
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
         self.barrier()
         e0.record()
         out = None
-        for _ in range(steps):
+        for i in range(steps):
             out = fn()
+            marks[i].record()
         e1.record()
         self.barrier()
+        # per-step durations (diagnostic only: the reported figure is the bracket around all K steps)
+        per = [(e0 if i == 0 else marks[i - 1]).elapsed_time(marks[i]) for i in range(steps)]
+        self.last_steps_ms = {"median": sorted(per)[len(per) // 2], "max": max(per), "first": per[0]}
         return self.max_over_ranks(e0.elapsed_time(e1)) / steps, out
 
     def close(self):
@@ -281,13 +286,13 @@ def bench_eval(ctx, args, workload):
             dist.all_reduce(ild_sum)
         return s, i, ild
 
+    sampler = ClockSampler(ctx.local_rank, active=rank == 0).start()  # before the warm-up: no idle gap in front of the timed region
     for _ in range(warmup):
         step()
     ctx.barrier()
-    sampler = ClockSampler(ctx.local_rank, active=rank == 0).start()
-    time.sleep(0.3 if rank == 0 else 0.0)
     launches0 = N.launch_count()
     ms_per_step, _ = ctx.timed(step, args.steps)
+    step_spread = dict(ctx.last_steps_ms)
     launches = N.launch_count() - launches0
     # per-kernel durations: CUDA events recorded by the library around its launches, on the launching stream
     N.set_profiling(True)
@@ -366,7 +371,7 @@ def bench_eval(ctx, args, workload):
                 "int32_ids": {"value": world * nU / (e2e32_ms * 1e-3), "d2h_bytes_per_step": res32["d2h_bytes"]}},
         "gpu_launches": int(launches),
         "roofline": dominant, "roofline_select": roof_select, "roofline_filter": roof_filter, "roofline_step": roof_step,
-        "cpu_baseline": cpu, "phases_ms": med, "rescued_rows_per_step": stats["rescued_rows"],
+        "cpu_baseline": cpu, "phases_ms": med, "rescued_rows_per_step": stats["rescued_rows"], "step_ms_rank0": step_spread,
     }
 
 
@@ -397,10 +402,10 @@ def bench_cfg4(ctx, args, steps, warmup):
     def step():
         return parallel.recommend_item_sharded(Ud, V, a, k)
 
+    sampler = ClockSampler(ctx.local_rank, active=rank == 0).start()
     for _ in range(warmup):
         step()
     ctx.barrier()
-    sampler = ClockSampler(ctx.local_rank, active=rank == 0).start()
     l0 = N.launch_count()
     ms_per_step, _ = ctx.timed(step, steps)
     launches = N.launch_count() - l0
@@ -475,10 +480,10 @@ def bench_cfg3(ctx, args, steps, warmup, B=65536):
     def step():
         return parallel.bpr_step_sharded(state, u, p_, n_, 1.0 / Bg)
 
+    sampler = ClockSampler(ctx.local_rank, active=rank == 0).start()
     for _ in range(warmup):
         step()
     ctx.barrier()
-    sampler = ClockSampler(ctx.local_rank, active=rank == 0).start()
     l0 = N.launch_count()
     ms_per_step, _ = ctx.timed(step, steps)
     launches = N.launch_count() - l0
@@ -559,10 +564,10 @@ def bench_cfg5(ctx, args, steps, warmup):
     ch, sh = cand.cpu().pin_memory(), sc.cpu().pin_memory()
     out_h = torch.empty((nU, k), dtype=torch.int64).pin_memory()
     warmup = max(1, min(warmup, 3))
+    sampler = ClockSampler(ctx.local_rank, active=rank == 0).start()
     for _ in range(warmup):
         N.mmr_rerank(V, cand, sc, k, lam)
     ctx.barrier()
-    sampler = ClockSampler(ctx.local_rank, active=rank == 0).start()
     l0 = N.launch_count()
     ms_per_step, _ = ctx.timed(lambda: N.mmr_rerank(V, cand, sc, k, lam), steps)
     launches = N.launch_count() - l0
