@@ -83,6 +83,9 @@ def test_score_topk_vs_reference_golden(native, dev, name, exact):
     (128, 4096, 8, 1, 0, "grid"),             # exact tile multiples, tiny d, k = 1
     (300, 6000, 192, 64, 9000, "gauss"),      # d = 192: three k-blocks -> the one-block-per-CTA kernel
     (150, 5000, 512, 32, 0, "gauss"),         # d = 512: the widest tensor-core shape (two accumulator stages)
+    (140, 4000, 320, 20, 3000, "gauss"),      # d = 320: five k-blocks (every k-block count has its own issue loop)
+    (140, 4000, 384, 20, 0, "grid"),          # six
+    (140, 4000, 448, 20, 3000, "gauss"),      # seven
     (300, 26744, 128, 500, 40000, "gauss"),   # k = 500 (BASELINE.json config 5's candidate lists): the large-k buffers
     (130, 9000, 128, 500, 20000, "grid"),     # k = 500 with exact ties
     (90, 3000, 256, 300, 4000, "gauss"),      # k > 128 on the one-block kernel (d = 256)
